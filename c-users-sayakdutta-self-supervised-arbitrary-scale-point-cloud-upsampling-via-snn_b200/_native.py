@@ -1,0 +1,135 @@
+"""ctypes binding of libsapcu_b200.so (the C ABI declared in include/sapcu_b200.h).
+
+The library is built in-tree with nvcc for sm_100a by :func:`build`; :func:`lib` loads it and fails loudly
+when it is missing -- there is no Python / CPU fallback for any operator.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_HERE, "libsapcu_b200.so")
+_SOURCES = ["api.cu", "model.cu", "forward.cu", "gemm.cu", "gemm_tc.cu", "knn_seed.cu", "patch_ops.cu",
+            "intra_knn.cu", "fn_kernels.cu", "fd_kernels.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+MODEL_FN, MODEL_FD = 0, 1
+MODE_FP32, MODE_TC = 0, 1
+
+_lock = threading.Lock()
+_lib = None
+
+
+class SapcuError(RuntimeError):
+    pass
+
+
+def _stale():
+    if not os.path.exists(_SO):
+        return True
+    t = os.path.getmtime(_SO)
+    for f in os.listdir(_CSRC):
+        if os.path.getmtime(os.path.join(_CSRC, f)) > t:
+            return True
+    return os.path.getmtime(os.path.join(_HERE, "..", "include", "sapcu_b200.h")) > t
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into libsapcu_b200.so (sm_100a; cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return _SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(_HERE, "build"), exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    for src in _SOURCES:
+        obj = os.path.join(_HERE, "build", src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + flags + ["-c", os.path.join(_CSRC, src), "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise SapcuError("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode(errors="replace")))
+        if verbose and out:
+            print(out.decode(errors="replace"))
+    cmd = [nvcc, "-shared", "-o", _SO] + objs
+    subprocess.check_call(cmd)
+    return _SO
+
+
+_SIGS = {
+    "sapcu_last_error": (ctypes.c_char_p, []),
+    "sapcu_abi_version": (ctypes.c_int, []),
+    "sapcu_launch_count": (ctypes.c_int64, []),
+    "sapcu_knn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
+    "sapcu_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "sapcu_gather_center_rotate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p]),
+    "sapcu_renormalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "sapcu_displace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "sapcu_model_create": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
+    "sapcu_model_set_tensor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
+    "sapcu_model_finalize": (ctypes.c_int, [ctypes.c_void_p]),
+    "sapcu_model_destroy": (None, [ctypes.c_void_p]),
+    "sapcu_model_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "sapcu_fn_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                        ctypes.c_void_p]),
+    "sapcu_fd_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.c_int, ctypes.c_void_p]),
+    "sapcu_model_tap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                       ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "sapcu_lif_chain": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "sapcu_intra_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "sapcu_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """The loaded shared library; raises SapcuError when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_SO):
+                    raise SapcuError(
+                        "libsapcu_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                        "There is no CPU fallback for the sapcu_b200 hot path." % _SO)
+                h = ctypes.CDLL(_SO)
+                for name, (res, args) in _SIGS.items():
+                    fn = getattr(h, name)   # AttributeError = the .so is missing a declared symbol
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = h
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().sapcu_last_error()
+        raise SapcuError("%s failed (%d): %s" % (what or "sapcu call", rc, msg.decode(errors="replace") if msg else ""))
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,97 @@
+// C ABI glue: error string, launch counter, and the stand-alone operator entry points.
+#include <atomic>
+#include <stdarg.h>
+#include "../../include/sapcu_b200.h"
+#include "gemm_simt.cuh"
+#include "gemm_tc.h"
+#include "kernels.h"
+
+namespace sapcu {
+
+thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace sapcu
+
+using namespace sapcu;
+
+extern "C" {
+
+const char* sapcu_last_error(void) { return g_err; }
+int sapcu_abi_version(void) { return 1; }
+int64_t sapcu_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t sapcu_knn_workspace_bytes(int64_t N) {
+  if (N < 0) return 0;
+  return align_up((size_t)(3 * N) * sizeof(float), 256) + 256;
+}
+
+int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S, int K, int32_t* d_idx,
+              void* d_ws, size_t ws_bytes, void* stream) {
+  SAPCU_REQUIRE(N >= 1 && S >= 0, "sapcu_knn: bad sizes N=%lld S=%lld", (long long)N, (long long)S);
+  SAPCU_REQUIRE(d_cloud && (S == 0 || (d_seeds && d_idx)) && d_ws, "sapcu_knn: null pointer");
+  if (ws_bytes < sapcu_knn_workspace_bytes(N)) {
+    set_error("sapcu_knn: workspace %zu < %zu bytes", ws_bytes, sapcu_knn_workspace_bytes(N));
+    return SAPCU_EWORKSPACE;
+  }
+  float* c32 = reinterpret_cast<float*>(d_ws);
+  float* rmax = reinterpret_cast<float*>(reinterpret_cast<char*>(d_ws) + align_up((size_t)(3 * N) * sizeof(float), 256));
+  return launch_knn_seed(d_cloud, N, d_seeds, S, K, d_idx, c32, rmax, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sapcu_gather_center_rotate(const double* d_cloud, int64_t N, const double* d_seeds, const int32_t* d_idx,
+                               int64_t S, int K, const float* d_normals, float* d_patches, void* stream) {
+  SAPCU_REQUIRE(N >= 1 && S >= 0 && K >= 1, "gather_center_rotate: bad sizes");
+  SAPCU_REQUIRE(d_cloud && (S == 0 || (d_seeds && d_idx && d_patches)), "gather_center_rotate: null pointer");
+  return launch_gather_center_rotate(d_cloud, d_seeds, d_idx, S, K, d_normals, d_patches,
+                                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sapcu_renormalize(float* d_normals, int64_t S, void* stream) {
+  SAPCU_REQUIRE(S >= 0 && (S == 0 || d_normals), "renormalize: bad argument");
+  return launch_renormalize(d_normals, S, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sapcu_displace(const double* d_seeds, const float* d_normals, const float* d_dist, int64_t S, double* d_out,
+                   void* stream) {
+  SAPCU_REQUIRE(S >= 0 && (S == 0 || (d_seeds && d_normals && d_dist && d_out)), "displace: bad argument");
+  return launch_displace(d_seeds, d_normals, d_dist, S, d_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sapcu_lif_chain(const float* d_x, int64_t rows, int C, int T, const float* d_params4, const float* d_eif2,
+                    int all_steps, float* d_out, void* stream) {
+  SAPCU_REQUIRE(rows >= 0 && C >= 1 && T >= 1 && d_params4 && (rows == 0 || (d_x && d_out)), "lif_chain: bad argument");
+  // parameters arrive raw: clamp them on the fly into a small device scratch?  The ABI keeps this operator
+  // allocation-free by requiring the caller to pass CLAMPED parameters (the Python shim clamps).
+  return launch_neuron_unroll(d_eif2 != nullptr, true, d_x, C, rows, C, T, d_params4, d_eif2, all_steps, d_out, C,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sapcu_intra_knn(const float* d_feat, int64_t ld, int64_t S, int M, int C, int k, int32_t* d_idx, void* stream) {
+  SAPCU_REQUIRE(S >= 0 && C >= 1 && ld >= C && (S == 0 || (d_feat && d_idx)), "intra_knn: bad argument");
+  return launch_intra_knn(d_feat, ld, S, M, C, k, d_idx, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sapcu_gemm(const float* d_x, int64_t R, int K, const float* d_w, int N, const float* d_bias, float* d_y, int mode,
+               void* stream) {
+  SAPCU_REQUIRE(R >= 0 && K >= 1 && N >= 1 && d_w && (R == 0 || (d_x && d_y)), "gemm: bad argument");
+  GemmArgs g;
+  g.A = d_x; g.lda = K; g.R = R; g.K = K; g.W = d_w; g.N = N; g.bias = d_bias; g.Y = d_y; g.ldc = N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (mode == SAPCU_MODE_TC) {
+    if (!gemm_tc_supported(g, A_PLAIN)) { set_error("gemm: shape R=%lld K=%d N=%d not supported by the tensor-core engine", (long long)R, K, N); return SAPCU_EINVAL; }
+    return launch_gemm_tc(g, A_PLAIN, st);
+  }
+  SAPCU_REQUIRE(mode == SAPCU_MODE_FP32, "gemm: unknown mode %d", mode);
+  return launch_gemm_simt(g, A_PLAIN, true, st);
+}
+
+}  // extern "C"

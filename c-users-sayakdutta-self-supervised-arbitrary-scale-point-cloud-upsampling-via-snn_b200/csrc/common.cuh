@@ -1,0 +1,47 @@
+// Shared helpers for the sapcu_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace sapcu {
+
+// ---- error plumbing (thread-local message, negative return codes; never throws over the ABI)
+void set_error(const char* fmt, ...);
+extern thread_local char g_err[512];
+void count_launch(int n = 1);
+
+#define SAPCU_CUDA_CHECK(expr)                                                        \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      sapcu::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+#define SAPCU_LAUNCH_CHECK()                                                          \
+  do {                                                                                \
+    sapcu::count_launch();                                                            \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      sapcu::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+#define SAPCU_REQUIRE(cond, ...)                                                      \
+  do {                                                                                \
+    if (!(cond)) { sapcu::set_error(__VA_ARGS__); return -1; }                        \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;   // B200
+
+// ---- activation codes shared by the GEMM epilogues
+enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_GELU = 2, ACT_LIF = 3 };
+
+}  // namespace sapcu

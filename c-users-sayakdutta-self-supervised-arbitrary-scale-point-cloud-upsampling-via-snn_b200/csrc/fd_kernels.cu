@@ -1,0 +1,205 @@
+// Non-GEMM kernels of the fd (distance estimation) forward, fd/snn_coder.py:392-492,711-798.
+//   fd_block0        : the four multi-scale EdgeConvs on xyz (6 -> 64, BN, LeakyReLU, max over k_s), :413-417
+//   neuron_unroll    : T steps of an EIF/LIF layer from the zero state, every step's spikes stored (:432-474);
+//                      also the stand-alone LIF^T operator of the C ABI
+//   temporal_lif     : softmax-weighted sum over time of the pooled features + the final LIF step (:482-490)
+//   head_attention   : StandardSelfAttention core on [S,64] (:782-795)
+//   layernorm_rows   : LayerNorm over the last dim (:798)
+//   fd_tail          : Linear 32 -> 1 + Softplus(beta=5) (:722-725)
+#include "common.cuh"
+#include "kernels.h"
+#include "neuron.cuh"
+
+namespace sapcu {
+
+constexpr int B0_MAXK = 64;      // largest k_scale supported
+constexpr int B0_MAXSCALES = 8;
+
+struct Block0Args {
+  const float* xyz; const int32_t* idx; int ldi; int Mpts; int64_t P;
+  int nscales; int ks[B0_MAXSCALES];
+  const float* W[B0_MAXSCALES]; const float* scale[B0_MAXSCALES]; const float* shift[B0_MAXSCALES];
+  float* out;   // [P, nscales*64]
+};
+
+// one CTA per point, nscales*64 threads: thread (s, c) owns channel c of scale s
+__global__ void fd_block0_kernel(const Block0Args a) {
+  __shared__ float e[B0_MAXK][6];
+  const int64_t pt = blockIdx.x;
+  const int64_t patch0 = (pt / a.Mpts) * a.Mpts;
+  const int kmax = a.ks[a.nscales - 1];
+  const float cx = a.xyz[3 * pt], cy = a.xyz[3 * pt + 1], cz = a.xyz[3 * pt + 2];
+  for (int j = threadIdx.x; j < kmax; j += blockDim.x) {
+    const int64_t nb = patch0 + a.idx[pt * a.ldi + j];
+    const float nx = a.xyz[3 * nb], ny = a.xyz[3 * nb + 1], nz = a.xyz[3 * nb + 2];
+    e[j][0] = __fsub_rn(nx, cx); e[j][1] = __fsub_rn(ny, cy); e[j][2] = __fsub_rn(nz, cz);
+    e[j][3] = nx; e[j][4] = ny; e[j][5] = nz;
+  }
+  __syncthreads();
+  const int s = threadIdx.x >> 6, c = threadIdx.x & 63;
+  const float* w = a.W[s] + 6 * c;
+  const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5];
+  const float sc = a.scale[s][c], sh = a.shift[s][c];
+  float m = -INFINITY;
+  const int ks = a.ks[s];
+  for (int j = 0; j < ks; ++j) {
+    float y = __fmul_rn(w0, e[j][0]);
+    y = fmaf(w1, e[j][1], y); y = fmaf(w2, e[j][2], y); y = fmaf(w3, e[j][3], y);
+    y = fmaf(w4, e[j][4], y); y = fmaf(w5, e[j][5], y);
+    y = __fadd_rn(__fmul_rn(y, sc), sh);
+    m = fmaxf(m, act_leaky(y));
+  }
+  a.out[pt * (a.nscales * 64) + threadIdx.x] = m;
+}
+
+// out[row*(T*ldo) + t*ldo + c] = spike at step t of channel c for input U[row*ldu + c]   (all_steps)
+// out[row*ldo + c]             = spike at step T-1                                        (!all_steps)
+template <bool EIF, bool PRECISE>
+__global__ void neuron_unroll_kernel(const float* __restrict__ U, int64_t ldu, int64_t rows, int C, int T,
+                                     const float* __restrict__ np, const float* __restrict__ ep, int all_steps,
+                                     float* __restrict__ out, int64_t ldo) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= rows * C) return;
+  const int64_t row = e / C;
+  const int c = (int)(e - row * C);
+  const NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
+  EifParams q{1.0f, 1.0f};
+  if (EIF) { q.dT = ep[c]; q.thrh = ep[C + c]; }
+  NeuronState st = neuron_init(p);
+  float s = U[row * ldu + c];
+  float* o = all_steps ? out + row * (int64_t)T * ldo + c : out + row * ldo + c;
+  for (int t = 0; t < T; ++t) {
+    s = neuron_step<EIF, PRECISE>(s, st, p, q);
+    if (all_steps) o[(int64_t)t * ldo] = s;
+  }
+  if (!all_steps) *o = s;
+}
+
+template <bool PRECISE>
+__global__ void temporal_lif_kernel(const float* __restrict__ pool, int64_t S, int Tt, int C,
+                                    const float* __restrict__ wsm, const float* __restrict__ np,
+                                    float* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= S * C) return;
+  const int64_t s = e / C;
+  const int c = (int)(e - s * C);
+  float z = 0.0f;
+  for (int t = 0; t < Tt; ++t) z = fmaf(wsm[t], pool[(s * Tt + t) * C + c], z);
+  const NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
+  NeuronState st = neuron_init(p);
+  EifParams q{1.0f, 1.0f};
+  out[e] = neuron_step<false, PRECISE>(z, st, p, q);
+}
+
+// qkv: [S, 3*dim]; out: [S, dim]; softmax over heads of (q_h . k_h) * scale, then a_h * v_h
+__global__ void head_attention_kernel(const float* __restrict__ qkv, int64_t S, int H, int hd, float scale,
+                                      float* __restrict__ out) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int dim = H * hd;
+  const float* q = qkv + s * 3 * dim; const float* k = q + dim; const float* v = k + dim;
+  float a[16];
+  float mx = -INFINITY;
+  for (int h = 0; h < H; ++h) {
+    float d = 0.0f;
+    for (int i = 0; i < hd; ++i) d = fmaf(q[h * hd + i], k[h * hd + i], d);
+    a[h] = d * scale; mx = fmaxf(mx, a[h]);
+  }
+  float sum = 0.0f;
+  for (int h = 0; h < H; ++h) { a[h] = expf(a[h] - mx); sum += a[h]; }
+  for (int h = 0; h < H; ++h) {
+    const float w = a[h] / sum;
+    for (int i = 0; i < hd; ++i) out[s * dim + h * hd + i] = w * v[h * hd + i];
+  }
+}
+
+// one warp per row, in place allowed
+__global__ void layernorm_rows_kernel(const float* __restrict__ X, int64_t S, int C, const float* __restrict__ w,
+                                      const float* __restrict__ b, float* __restrict__ out) {
+  const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= S) return;
+  float sum = 0.0f;
+  for (int c = lane; c < C; c += 32) sum += X[s * C + c];
+  for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float mean = sum / (float)C;
+  float var = 0.0f;
+  for (int c = lane; c < C; c += 32) { const float d = X[s * C + c] - mean; var = fmaf(d, d, var); }
+  for (int off = 16; off; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
+  const float rstd = 1.0f / sqrtf(var / (float)C + 1e-5f);
+  for (int c = lane; c < C; c += 32) out[s * C + c] = (X[s * C + c] - mean) * rstd * w[c] + b[c];
+}
+
+__global__ void fd_tail_kernel(const float* __restrict__ H, int64_t S, int K, const float* __restrict__ w,
+                               const float* __restrict__ b, float* __restrict__ out) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float y = 0.0f;
+  for (int c = 0; c < K; ++c) y = fmaf(w[c], H[s * K + c], y);
+  y += b[0];
+  const float beta = 5.0f;
+  const float z = y * beta;
+  out[s] = (z > 20.0f) ? y : log1pf(expf(z)) / beta;
+}
+
+int launch_fd_block0(const float* xyz, const int32_t* idx, int ldi, int Mpts, int64_t P, int nscales, const int* ks,
+                     const float* const* W, const float* const* scale, const float* const* shift, float* out,
+                     cudaStream_t st) {
+  SAPCU_REQUIRE(nscales >= 1 && nscales <= B0_MAXSCALES, "fd_block0: %d scales unsupported", nscales);
+  Block0Args a;
+  a.xyz = xyz; a.idx = idx; a.ldi = ldi; a.Mpts = Mpts; a.P = P; a.nscales = nscales; a.out = out;
+  for (int s = 0; s < nscales; ++s) {
+    SAPCU_REQUIRE(ks[s] <= B0_MAXK && (s == 0 || ks[s] >= ks[s - 1]), "fd_block0: k_scales must be ascending and <= %d", B0_MAXK);
+    a.ks[s] = ks[s]; a.W[s] = W[s]; a.scale[s] = scale[s]; a.shift[s] = shift[s];
+  }
+  if (P == 0) return 0;
+  fd_block0_kernel<<<(unsigned)P, nscales * 64, 0, st>>>(a);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_neuron_unroll(bool eif, bool precise, const float* U, int64_t ldu, int64_t rows, int C, int T,
+                         const float* np, const float* ep, int all_steps, float* out, int64_t ldo, cudaStream_t st) {
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(rows * C, 256);
+#define SAPCU_NU(E, P) neuron_unroll_kernel<E, P><<<grid, 256, 0, st>>>(U, ldu, rows, C, T, np, ep, all_steps, out, ldo)
+  if (eif) { if (precise) SAPCU_NU(true, true); else SAPCU_NU(true, false); }
+  else     { if (precise) SAPCU_NU(false, true); else SAPCU_NU(false, false); }
+#undef SAPCU_NU
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_temporal_lif(bool precise, const float* pool, int64_t S, int Tt, int C, const float* wsm, const float* np,
+                        float* out, cudaStream_t st) {
+  if (S == 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(S * C, 256);
+  if (precise) temporal_lif_kernel<true><<<grid, 256, 0, st>>>(pool, S, Tt, C, wsm, np, out);
+  else         temporal_lif_kernel<false><<<grid, 256, 0, st>>>(pool, S, Tt, C, wsm, np, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_head_attention(const float* qkv, int64_t S, int H, int hd, float scale, float* out, cudaStream_t st) {
+  SAPCU_REQUIRE(H <= 16, "head_attention: %d heads > 16", H);
+  if (S == 0) return 0;
+  head_attention_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>(qkv, S, H, hd, scale, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_layernorm_rows(const float* X, int64_t S, int C, const float* w, const float* b, float* out, cudaStream_t st) {
+  if (S == 0) return 0;
+  layernorm_rows_kernel<<<(unsigned)ceil_div(S * 32, 256), 256, 0, st>>>(X, S, C, w, b, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_fd_tail(const float* H, int64_t S, int K, const float* w, const float* b, float* out, cudaStream_t st) {
+  if (S == 0) return 0;
+  fd_tail_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>(H, S, K, w, b, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sapcu

@@ -1,0 +1,169 @@
+// Non-GEMM kernels of the fn (normal estimation) forward, fn/snn_coder.py:294-396,430-476,542-549.
+//   pointwise3_lif : 3 -> C pointwise conv + BN + LIF^T, on points (conv1, :453-456) or on edge offsets
+//                    xyz_i - xyz_j (fc_delta, :308-310,355-358); K=3 is too thin for a GEMM tile
+//   attn_out       : softmax over the k neighbours of a/sqrt(head_dim) and sum_j a_ij (v_j + pos_ij) (:379-391)
+//   group_max      : max over the M points of a patch (adaptive_max_pool1d, :472; fd/snn_coder.py:479)
+//   fn_head        : Linear 256->3, LayerNorm(3), L2 normalise (:545-548)
+#include "common.cuh"
+#include "kernels.h"
+#include "neuron.cuh"
+
+namespace sapcu {
+
+template <bool EDGE, bool PRECISE>
+__global__ void pointwise3_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi,
+                                      int Mpts, int64_t rows, int C, const float* __restrict__ W,
+                                      const float* __restrict__ bias, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, const float* __restrict__ np, int T,
+                                      float* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= rows * C) return;
+  const int64_t row = e / C;
+  const int c = (int)(e - row * C);
+  float x0, x1, x2;
+  if (EDGE) {
+    const int64_t pt = row / kk;
+    const int j = (int)(row - pt * kk);
+    const int64_t nb = (pt / Mpts) * Mpts + idx[pt * ldi + j];
+    x0 = __fsub_rn(xyz[3 * pt], xyz[3 * nb]);
+    x1 = __fsub_rn(xyz[3 * pt + 1], xyz[3 * nb + 1]);
+    x2 = __fsub_rn(xyz[3 * pt + 2], xyz[3 * nb + 2]);
+  } else {
+    x0 = xyz[3 * row]; x1 = xyz[3 * row + 1]; x2 = xyz[3 * row + 2];
+  }
+  float y = fmaf(W[3 * c + 2], x2, fmaf(W[3 * c + 1], x1, __fmul_rn(W[3 * c], x0)));
+  y = __fadd_rn(y, bias[c]);
+  y = __fadd_rn(__fmul_rn(y, scale[c]), shift[c]);
+  NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
+  out[e] = lif_chain<PRECISE>(y, p, T);
+}
+
+constexpr int ATT_KMAX = 32;
+
+template <bool PRECISE>
+__global__ void attn_out_kernel(const float* __restrict__ logits, const float* __restrict__ pos,
+                                const float* __restrict__ V, int64_t ldv, const int32_t* __restrict__ idx, int ldi,
+                                int kk, int Mpts, int64_t P, int D, float sqrt_hd, float* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= P * D) return;
+  const int64_t pt = e / D;
+  const int c = (int)(e - pt * D);
+  const int64_t patch0 = (pt / Mpts) * Mpts;
+  float a[ATT_KMAX];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < ATT_KMAX; ++j) {
+    if (j < kk) {
+      a[j] = __fdiv_rn(logits[(pt * kk + j) * D + c], sqrt_hd);
+      mx = fmaxf(mx, a[j]);
+    }
+  }
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < ATT_KMAX; ++j) {
+    if (j < kk) {
+      a[j] = sapcu_exp<PRECISE>(__fsub_rn(a[j], mx));
+      sum = __fadd_rn(sum, a[j]);
+    }
+  }
+  float res = 0.0f;
+#pragma unroll
+  for (int j = 0; j < ATT_KMAX; ++j) {
+    if (j < kk) {
+      const int64_t nb = patch0 + idx[pt * ldi + j];
+      const float vp = __fadd_rn(V[nb * ldv + c], pos[(pt * kk + j) * D + c]);
+      res = __fadd_rn(res, __fmul_rn(__fdiv_rn(a[j], sum), vp));
+    }
+  }
+  out[e] = res;
+}
+
+// out[(s*Tt + t)*C + c] = max_m X[((s*M + m)*Tt + t)*C + c]
+__global__ void group_max_kernel(const float* __restrict__ X, int64_t S, int M, int Tt, int C, float* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= S * Tt * C) return;
+  const int c = (int)(e % C);
+  const int64_t st = e / C;
+  const int t = (int)(st % Tt);
+  const int64_t s = st / Tt;
+  const float* p = X + ((s * M) * Tt + t) * (int64_t)C + c;
+  const int64_t stride = (int64_t)Tt * C;
+  float m = -INFINITY;
+  for (int i = 0; i < M; ++i) m = fmaxf(m, p[i * stride]);
+  out[e] = m;
+}
+
+// one warp per patch: y = W[3,K] h + b ; LayerNorm(3) ; x / max(||x||, 1e-12)
+__global__ void fn_head_kernel(const float* __restrict__ H, int K, int64_t S, const float* __restrict__ W,
+                               const float* __restrict__ b, const float* __restrict__ lnw,
+                               const float* __restrict__ lnb, float* __restrict__ out) {
+  const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= S) return;
+  float y[3] = {0.f, 0.f, 0.f};
+  for (int c = lane; c < K; c += 32) {
+    const float h = H[s * K + c];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) y[o] = fmaf(W[o * K + c], h, y[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+    for (int off = 16; off; off >>= 1) y[o] += __shfl_xor_sync(0xffffffffu, y[o], off);
+  if (lane == 0) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) y[o] += b[o];
+    const float mean = (y[0] + y[1] + y[2]) / 3.0f;
+    const float d0 = y[0] - mean, d1 = y[1] - mean, d2 = y[2] - mean;
+    const float var = (d0 * d0 + d1 * d1 + d2 * d2) / 3.0f;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    float z[3] = {d0 * rstd * lnw[0] + lnb[0], d1 * rstd * lnw[1] + lnb[1], d2 * rstd * lnw[2] + lnb[2]};
+    const float nn = sqrtf(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+    const float den = fmaxf(nn, 1e-12f);
+    out[3 * s] = z[0] / den; out[3 * s + 1] = z[1] / den; out[3 * s + 2] = z[2] / den;
+  }
+}
+
+int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32_t* idx, int kk, int ldi, int Mpts,
+                          int64_t rows, int C, const float* W, const float* bias, const float* scale,
+                          const float* shift, const float* np, int T, float* out, cudaStream_t st) {
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(rows * C, 256);
+  if (edge) {
+    if (precise) pointwise3_lif_kernel<true, true><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
+    else         pointwise3_lif_kernel<true, false><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
+  } else {
+    if (precise) pointwise3_lif_kernel<false, true><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
+    else         pointwise3_lif_kernel<false, false><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
+  }
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_attn_out(bool precise, const float* logits, const float* pos, const float* V, int64_t ldv,
+                    const int32_t* idx, int ldi, int kk, int Mpts, int64_t P, int D, float sqrt_hd, float* out,
+                    cudaStream_t st) {
+  SAPCU_REQUIRE(kk <= ATT_KMAX, "attn_out: k=%d > %d", kk, ATT_KMAX);
+  if (P == 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(P * D, 256);
+  if (precise) attn_out_kernel<true><<<grid, 256, 0, st>>>(logits, pos, V, ldv, idx, ldi, kk, Mpts, P, D, sqrt_hd, out);
+  else         attn_out_kernel<false><<<grid, 256, 0, st>>>(logits, pos, V, ldv, idx, ldi, kk, Mpts, P, D, sqrt_hd, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_group_max(const float* X, int64_t S, int M, int Tt, int C, float* out, cudaStream_t st) {
+  if (S == 0) return 0;
+  group_max_kernel<<<(unsigned)ceil_div(S * Tt * C, 256), 256, 0, st>>>(X, S, M, Tt, C, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_fn_head(const float* H, int K, int64_t S, const float* W, const float* b, const float* lnw,
+                   const float* lnb, float* out, cudaStream_t st) {
+  if (S == 0) return 0;
+  fn_head_kernel<<<(unsigned)ceil_div(S * 32, 256), 256, 0, st>>>(H, K, S, W, b, lnw, lnb, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sapcu

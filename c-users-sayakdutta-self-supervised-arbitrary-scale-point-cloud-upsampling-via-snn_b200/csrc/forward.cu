@@ -1,0 +1,313 @@
+// fn / fd forward orchestration: workspace plans, chunking over patches, the layer schedule.
+//
+// Schedule notes (exactness-preserving):
+//  * every `for t in range(T): x, *st = lif(x, *st)` chain of fn is evaluated as one element-wise function
+//    fused into the epilogue of the contraction that produces its input (the fed-back spike is gated
+//    to zero by the refractory term after step 0, but the gate is still evaluated literally);
+//  * fd's time loop (fd/snn_coder.py:408-480) feeds each block's conv output through a gate that is
+//    closed for t >= 1, so the graph convolutions and feature-space kNN are evaluated once (t = 0) and
+//    only the neuron recurrences + the 960 -> emb contraction + max-pool run for all T steps.
+#include "../../include/sapcu_b200.h"
+#include "gemm_simt.cuh"
+#include "gemm_tc.h"
+#include "kernels.h"
+#include "model.h"
+
+using namespace sapcu;
+
+namespace {
+
+struct Bump {
+  char* base; size_t off = 0;
+  explicit Bump(void* b) : base(reinterpret_cast<char*>(b)) {}
+  template <class T> T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Tap { const char* name; const void* ptr; int64_t rows, cols, ld; };
+
+struct FnPlan {
+  int32_t* idx; float *F0, *FCAT, *X, *QKV, *E1, *E2, *E3, *RES, *R1, *G, *GM, *H0, *H1, *H2, *H3;
+  size_t bytes; int kmax; int Dl, kl;
+};
+FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
+  FnPlan p; Bump b(base);
+  const int64_t P = s * M;
+  p.kmax = 0; size_t emax = 0;
+  for (int i = 0; i < 3; ++i) {
+    const int k = f.blk[i].k < M ? f.blk[i].k : M;
+    p.kmax = k > p.kmax ? k : p.kmax;
+    emax = (size_t)k * f.blk[i].D > emax ? (size_t)k * f.blk[i].D : emax;
+  }
+  p.idx = b.take<int32_t>(P * p.kmax);
+  p.F0 = b.take<float>(P * 64); p.FCAT = b.take<float>(P * 192);
+  p.X = b.take<float>(P * 512); p.QKV = b.take<float>(P * 1536);
+  p.E1 = b.take<float>(P * emax); p.E2 = b.take<float>(P * emax); p.E3 = b.take<float>(P * emax);
+  p.RES = b.take<float>(P * 512); p.R1 = b.take<float>(P * 512);
+  p.G = b.take<float>(P * f.emb); p.GM = b.take<float>(s * f.emb);
+  p.H0 = b.take<float>(s * 2048); p.H1 = b.take<float>(s * 1024); p.H2 = b.take<float>(s * 512); p.H3 = b.take<float>(s * 256);
+  p.bytes = align_up(b.off, 256);
+  p.Dl = f.blk[2].D; p.kl = f.blk[2].k < M ? f.blk[2].k : M;
+  return p;
+}
+
+struct FdPlan {
+  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *SPK, *AGG, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
+  size_t bytes; int k, kmax0;
+};
+FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
+  FdPlan p; Bump b(base);
+  const int64_t P = s * M;
+  p.k = f.k < M ? f.k : M;
+  p.kmax0 = f.kscales[f.nscales - 1] < M ? f.kscales[f.nscales - 1] : M;
+  p.idx0 = b.take<int32_t>(P * p.kmax0); p.idxf = b.take<int32_t>(P * p.k);
+  p.F0 = b.take<float>(P * 64 * f.nscales);
+  p.U0 = b.take<float>(P * 64); p.U1 = b.take<float>(P * 128); p.U2 = b.take<float>(P * 256); p.U3 = b.take<float>(P * 512);
+  p.SPK = b.take<float>(P * f.T * 960);
+  p.AGG = b.take<float>(P * f.T * f.emb);
+  p.POOL = b.take<float>(s * f.T * f.emb); p.Z = b.take<float>(s * f.emb);
+  p.D0 = b.take<float>(s * 256); p.T1 = b.take<float>(s * 128); p.R = b.take<float>(s * 128);
+  p.D1 = b.take<float>(s * 128); p.D2 = b.take<float>(s * 64); p.QKV = b.take<float>(s * 192);
+  p.O = b.take<float>(s * 64); p.AO = b.take<float>(s * 64); p.LN = b.take<float>(s * 64); p.HH = b.take<float>(s * 32);
+  p.bytes = align_up(b.off, 256);
+  return p;
+}
+
+int64_t pick_chunk(const sapcu_model* m, int64_t S, int M, size_t ws_bytes) {
+  auto need = [&](int64_t s) {
+    return m->kind == SAPCU_MODEL_FN ? fn_plan(m->fn, s, M, nullptr).bytes : fd_plan(m->fd, s, M, nullptr).bytes;
+  };
+  if (need(S) <= ws_bytes) return S;
+  int64_t lo = 0, hi = S;   // need(lo) fits (lo = 0 trivially), need(hi) does not
+  while (hi - lo > 1) { const int64_t mid = (lo + hi) / 2; if (need(mid) <= ws_bytes) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// ---- GEMM helper: dispatch on the arithmetic mode
+struct G {
+  int mode; cudaStream_t st;
+  int run(GemmArgs& g, int amode) const {
+    if (mode == SAPCU_MODE_TC && gemm_tc_supported(g, amode)) return launch_gemm_tc(g, amode, st);
+    return launch_gemm_simt(g, amode, mode == SAPCU_MODE_FP32, st);
+  }
+  // plain layer: Y[R, L.N] (ldc) = act(affine(X[R, L.K] (lda)))
+  int layer(const Layer& L, const float* X, int64_t lda, int64_t R, float* Y, int64_t ldc, int act,
+            const Neuron* nr = nullptr, int T = 0, const float* res = nullptr, int64_t ldr = 0) const {
+    GemmArgs g;
+    g.A = X; g.lda = lda; g.R = R; g.K = L.K; g.W = L.W; g.N = L.N; g.bias = L.bias; g.scale = L.scale; g.shift = L.shift;
+    g.act = act; g.T = T; g.nparams = nr ? nr->np : nullptr; g.residual = res; g.ldr = ldr; g.Y = Y; g.ldc = ldc;
+    return run(g, A_PLAIN);
+  }
+};
+
+#define SAPCU_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals, const FnPlan& p, int mode, cudaStream_t st) {
+  const int64_t P = s * M;
+  const bool precise = mode == SAPCU_MODE_FP32;
+  const G g{mode, st};
+  SAPCU_TRY(launch_intra_knn(xyz, 3, s, M, 3, p.kmax, p.idx, st));
+  SAPCU_TRY(launch_pointwise3_lif(false, precise, xyz, nullptr, 0, 0, M, P, 64, f.conv1.W, f.conv1.bias, f.conv1.scale,
+                                  f.conv1.shift, f.snn_init.np, f.T_enc, p.F0, st));
+  for (int b = 0; b < 3; ++b) {
+    const FnBlock& k = f.blk[b];
+    const int D = k.D, kk = k.k < M ? k.k : M;
+    const float* fin = b == 0 ? p.F0 : p.FCAT + 64 * (b - 1);
+    const int64_t ldin = b == 0 ? 64 : 192;
+    const int64_t E = P * kk;
+    SAPCU_TRY(g.layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
+    SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
+    SAPCU_TRY(launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias,
+                                    k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, p.E1, st));
+    SAPCU_TRY(g.layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
+    {
+      GemmArgs a;
+      a.A = p.E2; a.lda = D; a.R = E; a.K = D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
+      a.Q = p.QKV; a.Kf = p.QKV + D; a.ldq = 3 * D;
+      a.W = k.fc_gamma.W; a.N = D; a.bias = k.fc_gamma.bias; a.scale = k.fc_gamma.scale; a.shift = k.fc_gamma.shift;
+      a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_gamma.np; a.Y = p.E3; a.ldc = D;
+      SAPCU_TRY(g.run(a, A_ATTNIN));
+    }
+    SAPCU_TRY(g.layer(k.fc_gamma2, p.E3, D, E, p.E1, D, ACT_NONE));
+    // torch (CPU) divides the logits by the python scalar sqrt(head_dim)
+    const float sq = sqrtf((float)(D / f.heads));
+    SAPCU_TRY(launch_attn_out(precise, p.E1, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, sq, p.RES, st));
+    SAPCU_TRY(g.layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
+    SAPCU_TRY(g.layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
+  }
+  SAPCU_TRY(g.layer(f.conv_final, p.FCAT, 192, P, p.G, f.emb, ACT_LIF, &f.snn_final, f.T_enc));
+  SAPCU_TRY(launch_group_max(p.G, s, M, 1, f.emb, p.GM, st));
+  SAPCU_TRY(g.layer(f.fc_out, p.GM, f.emb, s, p.H0, 2048, ACT_NONE));
+  SAPCU_TRY(g.layer(f.mlp[0], p.H0, 2048, s, p.H1, 1024, ACT_GELU));
+  SAPCU_TRY(g.layer(f.mlp[1], p.H1, 1024, s, p.H2, 512, ACT_GELU));
+  SAPCU_TRY(g.layer(f.mlp[2], p.H2, 512, s, p.H3, 256, ACT_GELU));
+  SAPCU_TRY(launch_fn_head(p.H3, 256, s, f.head.W, f.head.bias, f.ln_w, f.ln_b, normals, st));
+  return 0;
+}
+
+int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, const int32_t* const forced[3],
+             const FdPlan& p, int mode, cudaStream_t st) {
+  const int64_t P = s * M;
+  const bool precise = mode == SAPCU_MODE_FP32;
+  const G g{mode, st};
+  const int T = f.T;
+  SAPCU_TRY(launch_intra_knn(xyz, 3, s, M, 3, p.kmax0, p.idx0, st));
+  {
+    int ks[8]; const float* W[8]; const float* sc[8]; const float* sh[8];
+    for (int i = 0; i < f.nscales; ++i) {
+      ks[i] = f.kscales[i] < M ? f.kscales[i] : M; W[i] = f.first[i].W; sc[i] = f.first[i].scale; sh[i] = f.first[i].shift;
+    }
+    SAPCU_TRY(launch_fd_block0(xyz, p.idx0, p.kmax0, M, P, f.nscales, ks, W, sc, sh, p.F0, st));
+  }
+  SAPCU_TRY(g.layer(f.fusion, p.F0, 64 * f.nscales, P, p.U0, 64, ACT_LEAKY));
+  const int64_t ldspk = (int64_t)T * 960;
+  SAPCU_TRY(launch_neuron_unroll(true, precise, p.U0, 64, P, 64, T, f.blk[0].np, f.blk[0].ep, 1, p.SPK, 960, st));
+  const int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 512};
+  const int off_in[3] = {0, 64, 192}, off_out[3] = {64, 192, 448};
+  float* U[3] = {p.U1, p.U2, p.U3};
+  for (int b = 0; b < 3; ++b) {
+    const int32_t* idx = forced[b];
+    if (!idx) {
+      SAPCU_TRY(launch_intra_knn(p.SPK + off_in[b], ldspk, s, M, cin[b], p.k, p.idxf, st));
+      idx = p.idxf;
+    }
+    GemmArgs a;
+    a.R = P * p.k; a.K = 2 * cin[b]; a.idx = idx; a.ldi = p.k; a.kk = p.k; a.Mpts = M;
+    a.F = p.SPK + off_in[b]; a.ldf = ldspk; a.C = cin[b];
+    a.W = f.conv[b].W; a.N = cout[b]; a.scale = f.conv[b].scale; a.shift = f.conv[b].shift;
+    a.act = ACT_LEAKY; a.group = 32; a.Y = U[b]; a.ldc = cout[b];
+    SAPCU_TRY(g.run(a, A_EDGECAT));
+    SAPCU_TRY(launch_neuron_unroll(b == 0, precise, U[b], cout[b], P, cout[b], T, f.blk[b + 1].np, f.blk[b + 1].ep, 1,
+                                   p.SPK + off_out[b], 960, st));
+  }
+  SAPCU_TRY(g.layer(f.msc, p.SPK, 960, P * T, p.AGG, f.emb, ACT_LEAKY));
+  SAPCU_TRY(launch_group_max(p.AGG, s, M, T, f.emb, p.POOL, st));
+  SAPCU_TRY(launch_temporal_lif(precise, p.POOL, s, T, f.emb, f.tw, f.snn_fc.np, p.Z, st));
+  // StandardDistanceDecoder
+  SAPCU_TRY(g.layer(f.fc_in, p.Z, f.emb, s, p.D0, 256, ACT_GELU));
+  const float* x = p.D0; int xin = 256;
+  float* outs[2] = {p.D1, p.D2};
+  for (int r = 0; r < 2; ++r) {
+    const int ho = f.rb_fc1[r].N;
+    SAPCU_TRY(g.layer(f.rb_res[r], x, xin, s, p.R, ho, ACT_NONE));
+    SAPCU_TRY(g.layer(f.rb_fc0[r], x, xin, s, p.T1, ho, ACT_GELU));
+    SAPCU_TRY(g.layer(f.rb_fc1[r], p.T1, ho, s, outs[r], ho, ACT_GELU, nullptr, 0, p.R, ho));
+    x = outs[r]; xin = ho;
+  }
+  SAPCU_TRY(g.layer(f.to_qkv, p.D2, 64, s, p.QKV, 192, ACT_NONE));
+  const int hd = 64 / f.heads;
+  SAPCU_TRY(launch_head_attention(p.QKV, s, f.heads, hd, 1.0f / sqrtf((float)hd), p.O, st));
+  SAPCU_TRY(g.layer(f.to_out, p.O, 64, s, p.AO, 64, ACT_NONE, nullptr, 0, p.D2, 64));
+  SAPCU_TRY(launch_layernorm_rows(p.AO, s, 64, f.ln_w, f.ln_b, p.LN, st));
+  SAPCU_TRY(g.layer(f.fc_hidden, p.LN, 64, s, p.HH, 32, ACT_GELU));
+  SAPCU_TRY(launch_fd_tail(p.HH, s, 32, f.fc_dist.W, f.fc_dist.bias, dist, st));
+  return 0;
+}
+
+int check_common(const sapcu_model* m, int kind, const float* patches, int64_t S, int M, const void* out,
+                 const void* ws, int mode) {
+  SAPCU_REQUIRE(m, "forward: null model");
+  SAPCU_REQUIRE(m->kind == kind, "forward: model kind %d used with the wrong entry point", m->kind);
+  if (!m->finalized) { set_error("forward: model not finalized"); return SAPCU_ESTATE; }
+  SAPCU_REQUIRE(S >= 0 && M >= 1 && M <= 128, "forward: need S >= 0 and 1 <= M <= 128 (got S=%lld M=%d)", (long long)S, M);
+  SAPCU_REQUIRE(S == 0 || (patches && out && ws), "forward: null pointer");
+  SAPCU_REQUIRE(mode == SAPCU_MODE_FP32 || mode == SAPCU_MODE_TC, "forward: unknown mode %d", mode);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t sapcu_model_workspace_bytes(const sapcu_model* m, int64_t S, int M) {
+  if (!m || S < 0 || M < 1) return 0;
+  if (S == 0) S = 1;
+  return m->kind == SAPCU_MODEL_FN ? fn_plan(m->fn, S, M, nullptr).bytes : fd_plan(m->fd, S, M, nullptr).bytes;
+}
+
+int sapcu_fn_forward(const sapcu_model* m, const float* d_patches, int64_t S, int M, float* d_normals, void* d_ws,
+                     size_t ws_bytes, int mode, void* stream) {
+  SAPCU_TRY(check_common(m, SAPCU_MODEL_FN, d_patches, S, M, d_normals, d_ws, mode));
+  if (S == 0) return 0;
+  // the reference reads a [B,3,M] input whenever shape[1]==3 (fn/snn_coder.py:441): M==3 is ambiguous there
+  SAPCU_REQUIRE(M != 3, "fn_forward: M == 3 is ambiguous in the reference ([B,3,N] layout) and unsupported");
+  const int64_t chunk = pick_chunk(m, S, M, ws_bytes);
+  if (chunk < 1) { set_error("fn_forward: workspace of %zu bytes cannot hold one patch (need %zu)", ws_bytes, sapcu_model_workspace_bytes(m, 1, M)); return SAPCU_EWORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+    const int64_t s = (S - s0) < chunk ? (S - s0) : chunk;
+    const FnPlan p = fn_plan(m->fn, s, M, d_ws);
+    SAPCU_TRY(fn_chunk(m->fn, d_patches + s0 * M * 3, s, M, d_normals + s0 * 3, p, mode, st));
+  }
+  return 0;
+}
+
+int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, int M, float* d_dist,
+                     const int32_t* d_forced_idx, void* d_ws, size_t ws_bytes, int mode, void* stream) {
+  SAPCU_TRY(check_common(m, SAPCU_MODEL_FD, d_patches, S, M, d_dist, d_ws, mode));
+  if (S == 0) return 0;
+  const int k = m->fd.k < M ? m->fd.k : M;
+  SAPCU_REQUIRE(k == 32, "fd_forward: the fused EdgeConv max-pool is built for min(k, M) == 32 (got %d)", k);
+  const int64_t chunk = pick_chunk(m, S, M, ws_bytes);
+  if (chunk < 1) { set_error("fd_forward: workspace of %zu bytes cannot hold one patch (need %zu)", ws_bytes, sapcu_model_workspace_bytes(m, 1, M)); return SAPCU_EWORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+    const int64_t s = (S - s0) < chunk ? (S - s0) : chunk;
+    const FdPlan p = fd_plan(m->fd, s, M, d_ws);
+    const int32_t* forced[3] = {nullptr, nullptr, nullptr};
+    if (d_forced_idx)
+      for (int b = 0; b < 3; ++b) forced[b] = d_forced_idx + ((int64_t)b * S + s0) * M * k;
+    SAPCU_TRY(fd_chunk(m->fd, d_patches + s0 * M * 3, s, M, d_dist + s0, forced, p, mode, st));
+  }
+  return 0;
+}
+
+int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, int64_t* off_floats, int64_t* rows,
+                    int64_t* cols, int64_t* ld) {
+  SAPCU_REQUIRE(m && name && off_floats && rows && cols && ld && S >= 1 && M >= 1, "model_tap: bad argument");
+  const std::string n(name);
+  const int64_t P = S * M;
+  auto set = [&](const void* p, int64_t r, int64_t c, int64_t l) {
+    *off_floats = (int64_t)(reinterpret_cast<const char*>(p) - (const char*)nullptr) / 4; *rows = r; *cols = c; *ld = l; return 0;
+  };
+  if (m->kind == SAPCU_MODEL_FN) {
+    const FnPlan p = fn_plan(m->fn, S, M, nullptr);
+    const int D = p.Dl; const int64_t E = P * p.kl;
+    if (n == "idx") return set(p.idx, P, p.kmax, p.kmax);            // int32 payload
+    if (n == "snn_init") return set(p.F0, P, 64, 64);
+    if (n == "fcat") return set(p.FCAT, P, 192, 192);
+    if (n == "trans3.snn1") return set(p.X, P, D, D);
+    if (n == "trans3.snn_qkv") return set(p.QKV, P, 3 * D, 3 * D);
+    if (n == "trans3.snn_delta2") return set(p.E2, E, D, D);
+    if (n == "trans3.snn_gamma") return set(p.E3, E, D, D);
+    if (n == "trans3.logits") return set(p.E1, E, D, D);
+    if (n == "trans3.res") return set(p.RES, P, D, D);
+    if (n == "snn_final") return set(p.G, P, m->fn.emb, m->fn.emb);
+    if (n == "gmax") return set(p.GM, S, m->fn.emb, m->fn.emb);
+    if (n == "enc_out") return set(p.H0, S, 2048, 2048);
+    if (n == "dec_h3") return set(p.H3, S, 256, 256);
+  } else {
+    const FdPlan p = fd_plan(m->fd, S, M, nullptr);
+    const int T = m->fd.T;
+    if (n == "idx0") return set(p.idx0, P, p.kmax0, p.kmax0);        // int32 payload
+    if (n == "idxf") return set(p.idxf, P, p.k, p.k);                // int32 payload (block 3's graph)
+    if (n == "f0") return set(p.F0, P, 64 * m->fd.nscales, 64 * m->fd.nscales);
+    if (n == "u0") return set(p.U0, P, 64, 64);
+    if (n == "u1") return set(p.U1, P, 128, 128);
+    if (n == "u2") return set(p.U2, P, 256, 256);
+    if (n == "u3") return set(p.U3, P, 512, 512);
+    if (n == "spikes") return set(p.SPK, P * T, 960, 960);           // row = point*T + t
+    if (n == "pool") return set(p.POOL, S * T, m->fd.emb, m->fd.emb);
+    if (n == "z") return set(p.Z, S, m->fd.emb, m->fd.emb);
+    if (n == "dec_d2") return set(p.D2, S, 64, 64);
+    if (n == "dec_hidden") return set(p.HH, S, 32, 32);
+  }
+  set_error("model_tap: unknown tap '%s'", name);
+  return SAPCU_EINVAL;
+}
+
+}  // extern "C"

@@ -1,0 +1,10 @@
+// tcgen05 tensor-core GEMM engine (SAPCU_MODE_TC): interface used by forward.cu.
+#pragma once
+#include "gemm_simt.cuh"
+
+namespace sapcu {
+// true when the tensor-core engine implements this (loader, epilogue, shape) combination;
+// everything else stays on the fp32 SIMT engine.
+bool gemm_tc_supported(const GemmArgs& g, int amode);
+int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st);
+}  // namespace sapcu

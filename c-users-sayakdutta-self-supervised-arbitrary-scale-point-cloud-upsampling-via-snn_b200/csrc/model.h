@@ -1,0 +1,51 @@
+// Model handle: host-side weight registry, folded device parameters and the per-chunk workspace plans
+// of the fn / fd forwards.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace sapcu {
+
+struct Layer {     // 1x1 conv / Linear (+ folded eval BatchNorm):  y = (x W^T + bias) * scale + shift
+  const float* W = nullptr; const float* bias = nullptr; const float* scale = nullptr; const float* shift = nullptr;
+  int N = 0, K = 0;
+};
+struct Neuron {    // clamped per-channel parameters: np = [4][C] (d, a, r, th0); ep = [2][C] (dT, th_rh) for EIF
+  const float* np = nullptr; const float* ep = nullptr; int C = 0;
+};
+
+struct FnBlock {
+  int D = 0, k = 0;
+  Layer fc1, qkv, fc_delta, fc_delta2, fc_gamma, fc_gamma2, out_proj, fc2;
+  Neuron snn1, snn_qkv, snn_delta, snn_delta2, snn_gamma;
+};
+struct FnNet {
+  int kvals[3] = {0, 0, 0}; int emb = 0, T_enc = 0, heads = 0;
+  Layer conv1, conv_final, fc_out, mlp[3], head; Neuron snn_init, snn_final;
+  const float* ln_w = nullptr; const float* ln_b = nullptr;
+  FnBlock blk[3];
+};
+struct FdNet {
+  int k = 0, emb = 0, T = 0, heads = 0, nscales = 0; int kscales[8] = {0};
+  Layer first[8], fusion, conv[3], msc;
+  Neuron blk[4], snn_fc;
+  const float* tw = nullptr;   // softmax(temporal weights) [T]
+  Layer fc_in, rb_fc0[2], rb_fc1[2], rb_res[2], to_qkv, to_out, fc_hidden, fc_dist;
+  const float* ln_w = nullptr; const float* ln_b = nullptr;
+};
+
+}  // namespace sapcu
+
+struct sapcu_model {
+  int kind = 0;
+  std::vector<int> cfg;
+  std::map<std::string, std::vector<float>> host;   // raw state_dict tensors (host fp32)
+  bool finalized = false;
+  float* dev = nullptr;                              // one device allocation holding every derived array
+  size_t dev_floats = 0;
+  sapcu::FnNet fn;
+  sapcu::FdNet fd;
+};

@@ -1,0 +1,108 @@
+// Membrane recurrences of the LIF / EIF neurons, evaluated entirely in registers.
+//
+// Semantics follow the reference neuron step in eval mode
+// (fn/snn_coder.py:109-153, fd/snn_coder.py:117-155 LIF, fd/snn_coder.py:223-275 EIF):
+//   x  = x * float(rho <= 0)
+//   m  = m*d*(1-rho) + x (+ e)         e = dT*exp(clamp((m_prev - th_rh)/(dT+1e-6), -5, 5))   [EIF]
+//   s  = 0.5*exp(-(vc^2)/2)/sqrt(2pi) + 0.5*sigmoid(10*vc),  vc = clamp(m - th, -10, 10)
+//   m  = m*(1-s) ; rho = rho*r + s ; th = th + a*s ; th = th0 + (th - th0)*0.95
+// The soft spike s is strictly positive, so rho > 0 after the first step and the gate
+// `float(rho <= 0)` is closed for every later step; the gate is still
+// evaluated literally here so the kernels stay faithful for any state.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sapcu {
+
+struct NeuronParams {   // per channel, already clamped to the reference's ranges
+  float d;     // membrane_decay   in [0.1, 0.99]
+  float a;     // threshold_adapt  in [0.001, 0.1]
+  float r;     // refractory_decay in [0.1, 0.95]
+  float th0;   // threshold_base
+};
+struct EifParams {      // per channel, clamped
+  float dT;    // delta_T  in [0.1, 5]
+  float thrh;  // theta_rh in [0.1, 2]
+};
+
+// PRECISE=true : libdevice expf (<= 1 ulp) -- the fp32 parity mode
+// PRECISE=false: ex2.approx based __expf     -- the tensor-core mode
+template <bool PRECISE>
+__device__ __forceinline__ float sapcu_exp(float x) {
+  if (PRECISE) return expf(x);
+  return __expf(x);
+}
+
+// In PRECISE mode every product/sum is a separately rounded fp32 operation (the reference runs one
+// ATen kernel per operation, so nothing is ever contracted into an FMA); the fast mode lets the
+// compiler contract.
+template <bool PRECISE> __device__ __forceinline__ float mulp(float a, float b) {
+  return PRECISE ? __fmul_rn(a, b) : a * b;
+}
+template <bool PRECISE> __device__ __forceinline__ float addp(float a, float b) {
+  return PRECISE ? __fadd_rn(a, b) : a + b;
+}
+template <bool PRECISE> __device__ __forceinline__ float subp(float a, float b) {
+  return PRECISE ? __fsub_rn(a, b) : a - b;
+}
+
+template <bool PRECISE>
+__device__ __forceinline__ float spike_fn(float v) {
+  const float vc = fminf(fmaxf(v, -10.0f), 10.0f);
+  const float inv_sqrt_2pi = 1.0f / 2.5066282746310002f;
+  // CPU torch divides by the python scalar sqrt(2*pi) (rounded to fp32); the fast mode multiplies by 1/x
+  const float e = sapcu_exp<PRECISE>(-mulp<PRECISE>(mulp<PRECISE>(vc, vc), 0.5f));
+  const float g = PRECISE ? __fdiv_rn(e, 2.5066282746310002f) : e * inv_sqrt_2pi;
+  float sg;
+  if (PRECISE) sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__fmul_rn(10.0f, vc))));
+  else         sg = __fdividef(1.0f, 1.0f + __expf(-(10.0f * vc)));
+  return addp<PRECISE>(mulp<PRECISE>(0.5f, g), mulp<PRECISE>(0.5f, sg));
+}
+
+struct NeuronState { float m, th, rho; };
+
+__device__ __forceinline__ NeuronState neuron_init(const NeuronParams& p) {
+  NeuronState s; s.m = 0.0f; s.th = p.th0; s.rho = 0.0f; return s;
+}
+
+// One step; returns the soft spike.
+template <bool EIF, bool PRECISE>
+__device__ __forceinline__ float neuron_step(float x, NeuronState& st, const NeuronParams& p,
+                                             const EifParams& e) {
+  float ex = 0.0f;
+  if (EIF) {
+    float arg = PRECISE ? __fdiv_rn(__fsub_rn(st.m, e.thrh), __fadd_rn(e.dT, 1e-6f))
+                        : __fdividef(st.m - e.thrh, e.dT + 1e-6f);
+    arg = fminf(fmaxf(arg, -5.0f), 5.0f);
+    ex = mulp<PRECISE>(e.dT, sapcu_exp<PRECISE>(arg));
+  }
+  const float gate = (st.rho <= 0.0f) ? 1.0f : 0.0f;
+  x = mulp<PRECISE>(x, gate);
+  float m = addp<PRECISE>(mulp<PRECISE>(mulp<PRECISE>(st.m, p.d), subp<PRECISE>(1.0f, st.rho)), x);
+  if (EIF) m = addp<PRECISE>(m, ex);
+  const float s = spike_fn<PRECISE>(subp<PRECISE>(m, st.th));
+  st.m = mulp<PRECISE>(m, subp<PRECISE>(1.0f, s));
+  st.rho = addp<PRECISE>(mulp<PRECISE>(st.rho, p.r), s);
+  const float th = addp<PRECISE>(st.th, mulp<PRECISE>(p.a, s));
+  st.th = addp<PRECISE>(p.th0, mulp<PRECISE>(subp<PRECISE>(th, p.th0), 0.95f));
+  return s;
+}
+
+// LIF^T(u): T steps from the zero state, the emitted spike fed back as the next input
+// (fn/snn_coder.py:319-320 and every other `for t in range(T)` loop of the fn model).
+template <bool PRECISE>
+__device__ __forceinline__ float lif_chain(float u, const NeuronParams& p, int T) {
+  NeuronState st = neuron_init(p);
+  EifParams e{1.0f, 1.0f};
+  float s = u;
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) s = neuron_step<false, PRECISE>(s, st, p, e);
+  return s;
+}
+
+__device__ __forceinline__ float act_leaky(float x) { return x >= 0.0f ? x : 0.2f * x; }
+__device__ __forceinline__ float act_gelu(float x) {   // exact (erf) GELU, torch default
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+}  // namespace sapcu

@@ -1,0 +1,137 @@
+/*
+ * sapcu_b200 -- C ABI of the B200-native inference hot path of the SNN point-cloud
+ * upsampler (reference: generation.py:122-172 + fn/snn_coder.py + fd/snn_coder.py).
+ *
+ * The reference has no FFI of its own: its boundary is the
+ * Python level (Generator3D6, fn/fd nn.Modules).  Every entry point below names the
+ * reference call site it replaces; the Python shims in the package bind them with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (a stream is `void*`,
+ *     i.e. a cudaStream_t; NULL = legacy default stream).
+ *   - pointers named d_* are DEVICE pointers borrowed from the caller (never freed,
+ *     never retained after the call returns); h_* are HOST pointers.
+ *   - every function returns 0 on success or a negative SAPCU_E* code and never
+ *     throws; sapcu_last_error() returns a thread-local description.
+ *   - nothing here allocates device memory except sapcu_model_finalize (the model's
+ *     own weights); scratch space is always a caller-provided workspace.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef SAPCU_B200_H
+#define SAPCU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAPCU_OK            0
+#define SAPCU_EINVAL       -1   /* bad argument (shape, null pointer, unsupported size) */
+#define SAPCU_ECUDA        -2   /* a CUDA runtime call or kernel launch failed */
+#define SAPCU_EWORKSPACE   -3   /* workspace too small for even one patch */
+#define SAPCU_ESTATE       -4   /* model not finalized / missing tensor */
+
+#define SAPCU_MODEL_FN      0   /* ImprovedSNNNormalEstimation   (fn/snn_coder.py:627) */
+#define SAPCU_MODEL_FD      1   /* EnhancedSNNDistanceEstimation (fd/snn_coder.py:805) */
+
+/* arithmetic modes of the dense contractions */
+#define SAPCU_MODE_FP32     0   /* fp32 FFMA everywhere: the "fp32 parity mode" */
+#define SAPCU_MODE_TC       1   /* tcgen05 tensor-core GEMMs (bf16 operands, fp32 accumulate) for the
+                                   per-edge contractions; everything else as in FP32 mode */
+
+const char* sapcu_last_error(void);
+int         sapcu_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t     sapcu_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1  seed -> input-cloud kNN.  Replaces sklearn KDTree(data).query(chunk, K)
+ *     (generation.py:110,127,153).  Exact: ordering by fp64 squared distance
+ *     accumulated as ((dx*dx)+(dy*dy))+(dz*dz) without contraction, ties broken by the lowest
+ *     cloud index; d_idx[s*K + j] ascending in distance.  K <= 128, K <= N.
+ * ---------------------------------------------------------------------------------- */
+size_t sapcu_knn_workspace_bytes(int64_t N);   /* fp32 copy of the cloud + one scalar */
+int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S, int K,
+              int32_t* d_idx, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  gather + centre (+ rotate).  Replaces data[idx] - seed and the per-seed Rodrigues
+ *     loop (generation.py:128-129,154-160, rotation_matrix_from_vectors :30-47).
+ *     d_patches[s][j][:] = (float) R_s * (cloud[idx[s][j]] - seed[s])   (fp64 until the cast)
+ *     d_normals == NULL  -> R_s = I (the fn pass); otherwise R_s rotates normal_s onto +x.
+ * ---------------------------------------------------------------------------------- */
+int sapcu_gather_center_rotate(const double* d_cloud, int64_t N, const double* d_seeds,
+                               const int32_t* d_idx, int64_t S, int K,
+                               const float* d_normals, float* d_patches, void* stream);
+
+/* F.normalize(n, dim=-1) of generation.py:139, in place on [S,3] fp32. */
+int sapcu_renormalize(float* d_normals, int64_t S, void* stream);
+
+/* displacement, generation.py:171-172: out = seed + (double)(n * d)  (product in fp32). */
+int sapcu_displace(const double* d_seeds, const float* d_normals, const float* d_dist,
+                   int64_t S, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Models.  A handle is built from the same hyper-parameters get_model() consumes
+ * (fn/config.py:183-210, fd/config.py:89-117) and the tensors of the module's
+ * state_dict (host fp32 pointers, names = state_dict keys).
+ *   fn cfg ints : { k0, k1, k2, emb_dims, time_steps_enc, num_heads }
+ *   fd cfg ints : { k, emb_dims, time_steps_enc, num_heads, n_scales, k_scale_0 .. }
+ * After finalize the handle is immutable and may be used from several streams.
+ * ---------------------------------------------------------------------------------- */
+typedef struct sapcu_model sapcu_model;
+
+sapcu_model* sapcu_model_create(int kind, const int32_t* cfg, int ncfg);
+int  sapcu_model_set_tensor(sapcu_model* m, const char* name, const float* h_data, int64_t numel);
+int  sapcu_model_finalize(sapcu_model* m);       /* folds eval-mode BN, clamps neuron params, uploads */
+void sapcu_model_destroy(sapcu_model* m);
+
+/* workspace needed to run `S` patches of M points in ONE internal chunk (forward accepts
+ * less and chunks internally; it needs at least the size for S = 1). */
+size_t sapcu_model_workspace_bytes(const sapcu_model* m, int64_t S, int M);
+
+/* fn: ImprovedSNNNormalEstimation.forward([S,M,3]) -> [S,3] unit normals (fn/snn_coder.py:670-699). */
+int sapcu_fn_forward(const sapcu_model* m, const float* d_patches, int64_t S, int M,
+                     float* d_normals, void* d_ws, size_t ws_bytes, int mode, void* stream);
+
+/* fd: EnhancedSNNDistanceEstimation.forward([S,M,3]) -> [S] distances (fd/snn_coder.py:853-871).
+ * d_forced_idx (nullable): int32 [3][S][M][k] feature-space neighbour lists for blocks 1..3 taken
+ * from the oracle ("teacher-forced" parity runs, SURVEY.md section 7 hard-part 4). */
+int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, int M,
+                     float* d_dist, const int32_t* d_forced_idx,
+                     void* d_ws, size_t ws_bytes, int mode, void* stream);
+
+/* Debug taps for the parity tests: location of a named intermediate inside the workspace of the
+ * LAST chunk a forward call processed (valid when S fits one chunk).  Element (row r, col c) is at
+ * float offset  off + r*ld + c.  Returns SAPCU_EINVAL for an unknown name. */
+int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M,
+                    int64_t* off_floats, int64_t* rows, int64_t* cols, int64_t* ld);
+
+/* ------------------------------------------------------------------------------------
+ * Stand-alone operators exported for unit parity tests (each is used by the forwards above).
+ * ---------------------------------------------------------------------------------- */
+/* LIF^T / EIF^T chain from the zero state (fn/snn_coder.py:87-153, fd/snn_coder.py:198-275 applied T
+ * times, each step's soft spike fed back as the next step's input):
+ * d_params4 = [4][C] rows {decay, adapt, refr_decay, theta0}, ALREADY CLAMPED to the reference's ranges;
+ * d_eif2 (nullable -> LIF) = [2][C] rows {delta_T, theta_rh}, clamped.
+ * x: [rows, C] row-major.  all_steps == 0 -> out [rows, C] = last step's spikes;
+ * all_steps != 0 -> out [rows, T, C] holds every step's spikes. */
+int sapcu_lif_chain(const float* d_x, int64_t rows, int C, int T, const float* d_params4,
+                    const float* d_eif2 /*nullable {delta_T, theta_rh}*/, int all_steps,
+                    float* d_out, void* stream);
+/* intra-patch kNN of fn/fd `knn()` (fn/snn_coder.py:31-39, fd/snn_coder.py:25-32): features
+ * [S*M, C] rows (ld floats apart), top-k of -|xi-xj|^2 in the reference's expanded form, ties -> lowest
+ * index.  d_idx: int32 [S*M, k] patch-local indices. */
+int sapcu_intra_knn(const float* d_feat, int64_t ld, int64_t S, int M, int C, int k,
+                    int32_t* d_idx, void* stream);
+/* Y[R,N] = X[R,K] * W[N,K]^T  (+bias) in the selected mode; exported to test the GEMM engines. */
+int sapcu_gemm(const float* d_x, int64_t R, int K, const float* d_w, int N, const float* d_bias,
+               float* d_y, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAPCU_B200_H */
