@@ -13,7 +13,8 @@ namespace sapcu {
 // a = n / ||n|| in fp32, everything after that in fp64; identity when cross(a, x̂) == 0.
 __device__ __forceinline__ void rodrigues_to_x(const float* __restrict__ n, double (&R)[3][3]) {
   const float n0 = n[0], n1 = n[1], n2 = n[2];
-  const float nn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(n0, n0), __fmul_rn(n1, n1)), __fmul_rn(n2, n2)));
+  // np.linalg.norm(float32[3]) = sqrt(x.dot(x)): products rounded to fp32, accumulated in double, sum rounded to fp32
+  const float nn = sqrtf((float)(((double)__fmul_rn(n0, n0) + (double)__fmul_rn(n1, n1)) + (double)__fmul_rn(n2, n2)));
   const double a0 = (double)__fdiv_rn(n0, nn), a1 = (double)__fdiv_rn(n1, nn), a2 = (double)__fdiv_rn(n2, nn);
   // v = a x (1,0,0) = (0, a2, -a1)
   const double v0 = 0.0, v1 = a2, v2 = -a1;
