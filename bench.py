@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Benchmark of the generation.py hot path (seed->cloud kNN, gather/centre, fn, rotate, fd, x + n*d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode fp32|tc]
+
+Workload (BASELINE.json configs[1]): one 2,048-point synthetic cloud, x4 -> 8,192 seeds per GPU, K = 100
+neighbours, seeded random-init config/fn.yaml + config/fd.yaml weights, fp32 parity mode.  A step is one pass of
+the whole hot path over the rank's 8,192 seeds.  N > 1: the seed set grows with N (weak scaling, 8,192 per rank),
+the cloud is replicated and one NCCL all-gather of the displaced points ends every step.
+
+Prints ONE JSON line (rank 0).  `value` = seeds/s with inputs resident in HBM; `e2e` = the same through
+Generator3D6.displace_host (host numpy in, host numpy out, H2D/D2H inside the timed region).
+`--impl reference` times the reference algorithm's CPU path (the oracle restatement, bit-identical to the
+reference) on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_CLOUD, RATIO, K_NEIGH = 2048, 4, 100
+METRIC = "upsampled points/sec (fn+fd, device-timed)"
+UNIT = "points/s"
+
+
+def build_models(device=None, stress=False):
+    import sapcu_b200
+    import sapcu_b200.synthetic as syn
+    from sapcu_b200.fn import config as fc
+    from sapcu_b200.fd import config as dc
+    mfn = fc.get_model(fc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fn.yaml")))
+    mfd = dc.get_model(dc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fd.yaml")), None)
+    syn.init_weights(mfn, seed=100, stress=stress)
+    syn.init_weights(mfd, seed=200, stress=stress)
+    sd_fn = {k: v.clone() for k, v in mfn.state_dict().items()}
+    sd_fd = {k: v.clone() for k, v in mfd.state_dict().items()}
+    if device is not None:
+        mfn, mfd = mfn.to(device), mfd.to(device)
+    return mfn, mfd, sd_fn, sd_fd
+
+
+def workload(world):
+    import sapcu_b200.synthetic as syn
+    cloud = syn.cloud(N_CLOUD, seed=0, shape="sphere")
+    seeds = syn.seeds(cloud, RATIO * world, seed=1)
+    return cloud, seeds
+
+
+def cpu_reference_rate(sd_fn, sd_fd, cloud, seeds, n_sample, steps=1, warmup=0):
+    """The reference algorithm's CPU path (oracle, faithful schedule) on `n_sample` seeds per step."""
+    import sapcu_oracle as orc
+    times = []
+    for i in range(warmup + steps):
+        sl = seeds[(i * n_sample) % max(1, len(seeds) - n_sample):][:n_sample]
+        t0 = time.perf_counter()
+        orc.pipeline(sd_fn, sd_fd, cloud, sl, K=K_NEIGH, batch=256, schedule="faithful")
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_sample * len(times) / sum(times), sum(times) / len(times)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, _, sd_fn, sd_fd = build_models(None)
+    cloud, seeds = workload(1)
+    n_sample = 16
+    rate, sec = cpu_reference_rate(sd_fn, sd_fd, cloud, seeds, n_sample, steps=args.steps, warmup=args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 2,048-pt sphere cloud x4 (8,192 seeds), K=100, fn.yaml+fd.yaml random-init, fp32",
+                   "bounded_sample": "%d seeds per step (cost is per-seed independent)" % n_sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d seeds/step x %d steps through oracle.pipeline (reference algorithm, faithful schedule)" % (n_sample, args.steps)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import sapcu_b200
+    from sapcu_b200 import _native as N
+    from sapcu_b200.generation import Generator3D6
+    from sapcu_b200.sharding import shard_range, all_gather_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sapcu_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = sapcu_b200.lib()
+    mode = args.mode
+    mfn, mfd, sd_fn, sd_fd = build_models(dev)
+    mfn.set_mode(mode), mfd.set_mode(mode)
+    cloud, seeds = workload(world)
+    S_total = seeds.shape[0]
+    lo, hi = shard_range(S_total, rank, world)
+    gen = Generator3D6(mfn, mfd, dev, k_neighbors=K_NEIGH, remove_outliers=False)
+    d_cloud = torch.from_numpy(cloud).to(dev)
+    d_seeds = torch.from_numpy(seeds[lo:hi]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        out = gen.displace_device(d_cloud, d_seeds)
+        return all_gather_rows(out, S_total) if world > 1 else out
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.sapcu_profile(1)
+    launches0 = L.sapcu_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()                        # L2 flush between timed iterations (outside the event pair)
+        a.record()
+        out = step()
+        b.record()
+    barrier()
+    launches = L.sapcu_launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    gms, gfl, gn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    N.check(L.sapcu_profile_read(ctypes.byref(gms), ctypes.byref(gfl), ctypes.byref(gn)), "profile_read")
+    L.sapcu_profile(0)
+    sampler.stop_flag.set()
+    sampler.join(timeout=5)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = S_total * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public host API (pinned H2D of cloud+seeds, D2H of the points, every step)
+    h_seeds = np.ascontiguousarray(seeds[lo:hi])
+    gen.displace_host(cloud, h_seeds)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pts = gen.displace_host(cloud, h_seeds)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = S_total * args.steps / float(t.item())
+    assert pts.shape == (hi - lo, 3) and np.isfinite(pts).all()
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved_tf = (gfl.value / max(gms.value, 1e-9)) / 1e9        # FLOP / ms -> TFLOP/s
+        cores = torch.get_num_threads()
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, _ = cpu_reference_rate(sd_fn, sd_fd, cloud, seeds, 24)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "24 seeds of the same workload through oracle.pipeline (reference algorithm, faithful schedule)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if mode == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: 2,048-pt sphere cloud x4 -> 8,192 seeds per GPU, K=100, fn.yaml+fd.yaml "
+                                   "random-init weights, %s mode" % ("fp32 parity" if mode == "fp32" else "tensor-core"),
+                       "seeds_total": S_total, "l2": "256 MiB flush buffer written between timed steps",
+                       "collective": "one all-gather of [S,3] f64 per step" if world > 1 else "none"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(cloud.nbytes + h_seeds.nbytes), "d2h_bytes_per_step": int(h_seeds.shape[0] * 24)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_simt_kernel (all 1x1-conv/linear contractions, fused LIF epilogues)"
+                         if mode == "fp32" else "gemm_tc_kernel + gemm_simt_kernel",
+                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s",
+                         "traffic": None, "kernel_ms_per_step": gms.value / args.steps, "kernel_launches_per_step": gn.value / args.steps,
+                         "kernel_share_of_step": gms.value / max(ms, 1e-9), "algorithmic_gflop_per_step": gfl.value / args.steps / 1e9},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

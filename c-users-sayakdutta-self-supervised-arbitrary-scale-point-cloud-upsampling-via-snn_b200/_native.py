@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
             raise SapcuError("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode(errors="replace")))
         if verbose and out:
             print(out.decode(errors="replace"))
-    cmd = [nvcc, "-shared", "-o", _SO] + objs
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", _SO] + objs
     subprocess.check_call(cmd)
     return _SO
 
@@ -66,6 +66,9 @@ _SIGS = {
     "sapcu_last_error": (ctypes.c_char_p, []),
     "sapcu_abi_version": (ctypes.c_int, []),
     "sapcu_launch_count": (ctypes.c_int64, []),
+    "sapcu_profile": (ctypes.c_int, [ctypes.c_int]),
+    "sapcu_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(ctypes.c_int64)]),
     "sapcu_knn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
     "sapcu_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

@@ -1,5 +1,7 @@
 // C ABI glue: error string, launch counter, and the stand-alone operator entry points.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include "../../include/sapcu_b200.h"
 #include "gemm_simt.cuh"
@@ -19,6 +21,28 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional live timing of the contraction kernels (bench.py roofline)
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
+static double g_prof_flops = 0.0;
+
+bool prof_begin(cudaStream_t st, double flops, int* slot) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return false;
+  cudaEvent_t a, b;
+  if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+  cudaEventRecord(a, st);
+  g_prof_ev.emplace_back(a, b);
+  g_prof_flops += flops;
+  *slot = (int)g_prof_ev.size() - 1;
+  return true;
+}
+void prof_end(cudaStream_t st, int slot) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot >= 0 && slot < (int)g_prof_ev.size()) cudaEventRecord(g_prof_ev[slot].second, st);
+}
+
 }  // namespace sapcu
 
 using namespace sapcu;
@@ -28,6 +52,29 @@ extern "C" {
 const char* sapcu_last_error(void) { return g_err; }
 int sapcu_abi_version(void) { return 1; }
 int64_t sapcu_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int sapcu_profile(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& e : g_prof_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  g_prof_ev.clear();
+  g_prof_flops = 0.0;
+  g_prof_on = enable != 0;
+  return 0;
+}
+
+int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  SAPCU_REQUIRE(gemm_ms && gemm_flops && gemm_launches, "profile_read: null pointer");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0;
+  for (auto& e : g_prof_ev) {
+    SAPCU_CUDA_CHECK(cudaEventSynchronize(e.second));
+    float t = 0.f;
+    SAPCU_CUDA_CHECK(cudaEventElapsedTime(&t, e.first, e.second));
+    ms += t;
+  }
+  *gemm_ms = ms; *gemm_flops = g_prof_flops; *gemm_launches = (int64_t)g_prof_ev.size();
+  return 0;
+}
 
 size_t sapcu_knn_workspace_bytes(int64_t N) {
   if (N < 0) return 0;

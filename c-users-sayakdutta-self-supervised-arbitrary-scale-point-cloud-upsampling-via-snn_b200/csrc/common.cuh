@@ -11,6 +11,8 @@ namespace sapcu {
 void set_error(const char* fmt, ...);
 extern thread_local char g_err[512];
 void count_launch(int n = 1);
+bool prof_begin(cudaStream_t st, double flops, int* slot);
+void prof_end(cudaStream_t st, int slot);
 
 #define SAPCU_CUDA_CHECK(expr)                                                        \
   do {                                                                                \

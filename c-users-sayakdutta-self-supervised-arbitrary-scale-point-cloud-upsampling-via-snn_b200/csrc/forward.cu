@@ -91,8 +91,13 @@ int64_t pick_chunk(const sapcu_model* m, int64_t S, int M, size_t ws_bytes) {
 struct G {
   int mode; cudaStream_t st;
   int run(GemmArgs& g, int amode) const {
-    if (mode == SAPCU_MODE_TC && gemm_tc_supported(g, amode)) return launch_gemm_tc(g, amode, st);
-    return launch_gemm_simt(g, amode, mode == SAPCU_MODE_FP32, st);
+    int slot = -1;
+    const bool prof = prof_begin(st, 2.0 * (double)g.R * g.K * g.N, &slot);
+    int rc;
+    if (mode == SAPCU_MODE_TC && gemm_tc_supported(g, amode)) rc = launch_gemm_tc(g, amode, st);
+    else rc = launch_gemm_simt(g, amode, mode == SAPCU_MODE_FP32, st);
+    if (prof) prof_end(st, slot);
+    return rc;
   }
   // plain layer: Y[R, L.N] (ldc) = act(affine(X[R, L.K] (lda)))
   int layer(const Layer& L, const float* X, int64_t lda, int64_t R, float* Y, int64_t ldc, int act,

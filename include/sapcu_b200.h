@@ -47,6 +47,12 @@ int         sapcu_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t     sapcu_launch_count(void);
 
+/* Live kernel timing for bench.py's roofline line: when enabled, every contraction launch (the dominant kernel
+ * family) is bracketed by CUDA events on its launch stream.  sapcu_profile_read synchronises those events and
+ * returns their summed duration, the algorithmic FLOPs (2*R*K*N per launch) and the launch count since enable. */
+int sapcu_profile(int enable);
+int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+
 /* ------------------------------------------------------------------------------------
  * K1  seed -> input-cloud kNN.  Replaces sklearn KDTree(data).query(chunk, K)
  *     (generation.py:110,127,153).  Exact: ordering by fp64 squared distance

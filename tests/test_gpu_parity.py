@@ -1,0 +1,331 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star, fp32 parity mode): kNN indices bit-exact; spike agreement >= 99.9 %;
+normals within 0.1 degree; distances within 1e-3 relative.  Floating-point layers are additionally compared
+on their soft values (max-abs), because random-init networks never cross threshold.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sapcu_b200
+import sapcu_b200.synthetic as syn
+from sapcu_b200 import _native as N
+import sapcu_oracle as orc
+import oracle_c
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+HARD = 0.449471      # soft spike value at v = 0: "binary spike" := soft > HARD
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return N.lib()
+
+
+@pytest.fixture(scope="module")
+def sphere():
+    cloud = syn.cloud(2048, seed=0, shape="sphere")
+    return cloud, syn.seeds(cloud, 4, seed=1)
+
+
+def _models(stress, device=DEV):
+    from sapcu_b200.fn import config as fc
+    from sapcu_b200.fd import config as dc
+    mfn = fc.get_model(fc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fn.yaml")))
+    mfd = dc.get_model(dc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fd.yaml")), None)
+    syn.init_weights(mfn, seed=100, stress=stress)
+    syn.init_weights(mfd, seed=200, stress=stress)
+    sd_fn = {k: v.clone() for k, v in mfn.state_dict().items()}
+    sd_fd = {k: v.clone() for k, v in mfd.state_dict().items()}
+    return mfn.to(device), mfd.to(device), sd_fn, sd_fd
+
+
+def _knn(lib, cloud, seeds, K):
+    dc, ds = torch.from_numpy(cloud).to(DEV), torch.from_numpy(seeds).to(DEV)
+    idx = torch.full((seeds.shape[0], K), -1, dtype=torch.int32, device=DEV)
+    ws = torch.empty(lib.sapcu_knn_workspace_bytes(cloud.shape[0]), dtype=torch.uint8, device=DEV)
+    N.check(lib.sapcu_knn(N.ptr(dc), cloud.shape[0], N.ptr(ds), seeds.shape[0], K, N.ptr(idx), N.ptr(ws), ws.numel(), None))
+    torch.cuda.synchronize()
+    return idx.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------- K1
+def test_knn_bit_exact_golden_and_oracle(lib, sphere, golden):
+    cloud, seeds = sphere
+    idx = _knn(lib, cloud, seeds, 100)                      # the full 8192-seed configuration
+    assert np.array_equal(idx[:512], golden.knn["idx_sphere"])          # sklearn KDTree, generated from the reference
+    assert np.array_equal(idx, oracle_c.knn(cloud, seeds, 100))
+    cb = syn.cloud(1500, seed=3, shape="boxes")
+    sb = syn.seeds(cb, 0.2, seed=4)
+    assert np.array_equal(_knn(lib, cb, sb, 48), golden.knn["idx_boxes"])
+
+
+def test_knn_edge_cases(lib):
+    rng = np.random.default_rng(5)
+    # K == N, S not a multiple of the CTA's warps, duplicated points (exact ties -> lowest index first)
+    cloud = rng.normal(size=(37, 3))
+    cloud[20:30] = cloud[5:15]
+    seeds = rng.normal(size=(13, 3))
+    assert np.array_equal(_knn(lib, cloud, seeds, 37), oracle_c.knn(cloud, seeds, 37))
+    # a cloud far from the origin and at a large scale: the fp32 pre-filter must stay conservative
+    cloud = rng.normal(size=(5000, 3)) * 1e-3 + np.array([1000.0, -2000.0, 500.0])
+    seeds = cloud[rng.integers(0, 5000, size=300)] + rng.normal(size=(300, 3)) * 1e-4
+    assert np.array_equal(_knn(lib, cloud, seeds, 100), oracle_c.knn(cloud, seeds, 100))
+    cloud = rng.normal(size=(3000, 3)) * 1e4
+    seeds = rng.normal(size=(100, 3)) * 1e4
+    assert np.array_equal(_knn(lib, cloud, seeds, 128), oracle_c.knn(cloud, seeds, 128))
+    # seed == cloud point (distance 0 first), K = 1, and the empty seed set
+    assert np.array_equal(_knn(lib, cloud, cloud[:50].copy(), 1)[:, 0], np.arange(50))
+    assert _knn(lib, cloud, np.zeros((0, 3)), 8).shape == (0, 8)
+    # argument errors come back as codes + message, not crashes
+    dc = torch.from_numpy(cloud).to(DEV)
+    ws = torch.empty(lib.sapcu_knn_workspace_bytes(3000), dtype=torch.uint8, device=DEV)
+    idx = torch.empty(4, 200, dtype=torch.int32, device=DEV)
+    assert lib.sapcu_knn(N.ptr(dc), 3000, N.ptr(dc), 4, 200, N.ptr(idx), N.ptr(ws), ws.numel(), None) == -1
+    assert b"K=200" in lib.sapcu_last_error()
+    assert lib.sapcu_knn(N.ptr(dc), 3000, N.ptr(dc), 4, 8, N.ptr(idx), N.ptr(ws), 16, None) == -3
+
+
+# ----------------------------------------------------------------------------------------- K2 / displacement
+def test_gather_center_rotate_and_displace(lib, sphere, golden):
+    cloud, seeds = sphere
+    g = golden.patch_ops
+    S = 40
+    idx = torch.from_numpy(golden.knn["idx_sphere"][:S]).to(DEV)
+    dc, ds = torch.from_numpy(cloud).to(DEV), torch.from_numpy(seeds[:S]).to(DEV)
+    out = torch.empty(S, 100, 3, dtype=torch.float32, device=DEV)
+    N.check(lib.sapcu_gather_center_rotate(N.ptr(dc), 2048, N.ptr(ds), N.ptr(idx), S, 100, None, N.ptr(out), None))
+    assert np.array_equal(out.cpu().numpy(), g["patch"])                # fp64 subtract + one cast: bit-exact
+    nrm = torch.from_numpy(g["normals"]).to(DEV)
+    N.check(lib.sapcu_gather_center_rotate(N.ptr(dc), 2048, N.ptr(ds), N.ptr(idx), S, 100, N.ptr(nrm), N.ptr(out), None))
+    got = out.cpu().numpy()
+    np.testing.assert_allclose(got, g["rotated"], rtol=0, atol=1e-8)   # fp64 products may be fused differently by BLAS
+    assert np.array_equal(got[0], g["patch"][0]) and np.array_equal(got[1], g["patch"][1])   # n = +-x: identity (reference quirk)
+    un, dd = torch.from_numpy(g["unit_normals"]).to(DEV), torch.from_numpy(g["dist"]).to(DEV)
+    disp = torch.empty(S, 3, dtype=torch.float64, device=DEV)
+    N.check(lib.sapcu_displace(N.ptr(ds), N.ptr(un), N.ptr(dd), S, N.ptr(disp), None))
+    assert np.array_equal(disp.cpu().numpy(), g["displaced"])
+    n2 = torch.from_numpy(g["normals"]).to(DEV).clone()
+    N.check(lib.sapcu_renormalize(N.ptr(n2), S, None))
+    ref = torch.nn.functional.normalize(torch.from_numpy(g["normals"]), dim=-1)
+    np.testing.assert_allclose(n2.cpu().numpy(), ref.numpy(), rtol=0, atol=1.2e-7)
+
+
+# ----------------------------------------------------------------------------------------- neurons
+def test_neuron_chain_known_answers(lib, golden):
+    g = golden.neuron
+    x = torch.from_numpy(g["x"]).to(DEV)
+    rows, C = x.shape
+    clamp = {"membrane_decay": (0.1, 0.99), "threshold_adapt": (0.001, 0.1), "refractory_decay": (0.1, 0.95),
+             "threshold_base": (-1e30, 1e30), "delta_T": (0.1, 5.0), "theta_rh": (0.1, 2.0)}
+    p = {k: np.clip(g["p_" + k], *clamp[k]).astype(np.float32) for k in clamp}
+    p4 = torch.from_numpy(np.stack([p["membrane_decay"], p["threshold_adapt"], p["refractory_decay"], p["threshold_base"]])).to(DEV)
+    e2 = torch.from_numpy(np.stack([p["delta_T"], p["theta_rh"]])).to(DEV)
+    for tag, ep in (("lif", None), ("eif", e2)):
+        out = torch.empty(rows, 7, C, dtype=torch.float32, device=DEV)
+        N.check(lib.sapcu_lif_chain(N.ptr(x), rows, C, 7, N.ptr(p4), N.ptr(ep), 1, N.ptr(out), None))
+        got = out.permute(1, 0, 2).cpu().numpy()            # [T, rows, C] like the fixture
+        ref = g[tag]
+        assert np.abs(got - ref).max() < 2e-6
+        assert ((got > HARD) == (ref > HARD)).mean() >= 0.999
+        last = torch.empty(rows, C, dtype=torch.float32, device=DEV)
+        N.check(lib.sapcu_lif_chain(N.ptr(x), rows, C, 7, N.ptr(p4), N.ptr(ep), 0, N.ptr(last), None))
+        assert torch.equal(last, out[:, 6, :])
+
+
+# ----------------------------------------------------------------------------------------- K3 / GEMM engine
+def test_intra_knn_matches_reference_formula(lib, sphere, golden):
+    patches = torch.from_numpy(golden.models["patches"])
+    cloud, seeds = sphere
+    idxs = oracle_c.knn(cloud, seeds[:64], 100)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:64], idxs))
+    ref = orc.intra_knn(p.permute(0, 2, 1).contiguous(), 48).numpy()
+    out = torch.empty(64 * 100, 48, dtype=torch.int32, device=DEV)
+    N.check(lib.sapcu_intra_knn(N.ptr(p.to(DEV)), 3, 64, 100, 3, 48, N.ptr(out), None))
+    got = out.view(64, 100, 48).cpu().numpy()
+    assert (got == ref).mean() >= 0.999          # fp32 expanded-form distances: near-ties may swap
+    assert (got[:, :, 0] == np.arange(100)[None, :]).all()
+    # feature space (C=64, strided rows) on well separated random features: exact
+    f = torch.randn(5, 100, 80, generator=torch.Generator().manual_seed(3))
+    ref = orc.intra_knn(f[:, :, :64].permute(0, 2, 1).contiguous(), 32).numpy()
+    out = torch.empty(500, 32, dtype=torch.int32, device=DEV)
+    N.check(lib.sapcu_intra_knn(N.ptr(f.to(DEV)), 80, 5, 100, 64, 32, N.ptr(out), None))
+    assert (out.view(5, 100, 32).cpu().numpy() == ref).mean() >= 0.9995
+    assert patches.shape == (3, 100, 3)
+
+
+def test_gemm_engine_fp32(lib):
+    g = torch.Generator().manual_seed(1)
+    for R, K, Nn in ((1000, 64, 128), (77, 512, 512), (4099, 960, 768), (5, 2048, 1024), (300, 32, 1), (129, 192, 640)):
+        x = torch.randn(R, K, generator=g)
+        w = torch.randn(Nn, K, generator=g) / math.sqrt(K)
+        b = torch.randn(Nn, generator=g)
+        y = torch.empty(R, Nn, dtype=torch.float32, device=DEV)
+        N.check(lib.sapcu_gemm(N.ptr(x.to(DEV)), R, K, N.ptr(w.to(DEV)), Nn, N.ptr(b.to(DEV)), N.ptr(y), N.MODE_FP32, None))
+        ref = (x.double() @ w.double().t() + b.double()).float()
+        assert (y.cpu() - ref).abs().max() < 2e-5 * math.sqrt(K)
+
+
+# ----------------------------------------------------------------------------------------- models
+def _angle_deg(a, b):
+    cos = (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
+    return np.degrees(np.arccos(np.clip(cos, -1, 1)))
+
+
+def _agree(a, b):
+    return float(((a > HARD) == (b > HARD)).mean())
+
+
+@pytest.mark.parametrize("stress", [False, True], ids=["default_init", "stress_init"])
+def test_fn_forward_parity(lib, sphere, golden, stress):
+    cloud, seeds = sphere
+    tag = "stress" if stress else "default"
+    mfn, _, sd_fn, _ = _models(stress)
+    B = 8
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx))
+    taps = {}
+    with torch.no_grad():
+        ref = orc.fn_forward(sd_fn, p, taps=taps).numpy()
+    got = mfn(p.to(DEV))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    # golden (reference-generated) vectors are the first 3 patches
+    g = golden.models
+    assert np.array_equal(p[:3].numpy(), g["patches"])
+    assert _angle_deg(got[:3], g[tag + "_normals"]).max() < 0.1
+    assert _angle_deg(got, ref).max() < 0.1
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-6)
+    # per-layer soft values + binarised spikes at the tapped layers
+    P = B * 100
+    def tap(name, dtype=torch.float32):
+        return mfn.tap(name, B, 100, dtype).cpu().numpy()
+    def cf(t):   # oracle [B,C,M(,k)] -> rows x C
+        t = t.numpy()
+        return np.moveaxis(t, 1, -1).reshape(-1, t.shape[1])
+    k3 = taps["encoder.trans3"]
+    assert (tap("idx", torch.int32).reshape(B, 100, 24)[:, :, :12] == k3["idx"].numpy()).mean() >= 0.999
+    checks = [("snn_init", cf(taps["snn_init"])), ("trans3.snn1", cf(k3["snn1"])),
+              ("trans3.snn_qkv", np.concatenate([cf(k3["q"]), cf(k3["k"]), cf(k3["v"])], 1)),
+              ("trans3.snn_delta2", cf(k3["pos"])), ("trans3.snn_gamma", cf(k3["a1"])),
+              ("snn_final", cf(taps["snn_final"]))]
+    for name, r in checks:
+        t = tap(name)
+        assert t.shape == r.shape, name
+        assert np.abs(t - r).max() < 2e-3, (name, np.abs(t - r).max())
+        assert _agree(t, r) >= 0.999, (name, _agree(t, r))
+    np.testing.assert_allclose(tap("fcat"), taps["fcat"].numpy().reshape(P, 192), rtol=0, atol=5e-3)
+    np.testing.assert_allclose(tap("gmax"), taps["gmax"].numpy(), rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("stress", [False, True], ids=["default_init", "stress_init"])
+def test_fd_forward_parity(lib, sphere, golden, stress):
+    tag = "stress" if stress else "default"
+    _, mfd, _, sd_fd = _models(stress)
+    g = golden.models
+    cloud, seeds = sphere
+    B = 8
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    rng = np.random.default_rng(9)
+    nrm = rng.normal(size=(B, 3)).astype(np.float32)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx, nrm))
+    p[:3] = torch.from_numpy(g[tag + "_patches_fd"])
+    taps = {}
+    with torch.no_grad():
+        ref = orc.fd_forward(sd_fd, p, schedule="dce", taps=taps).numpy()
+    np.testing.assert_allclose(ref[:3], g[tag + "_dist"], rtol=1e-5, atol=1e-7)      # oracle(dce, B=8) vs reference fixture
+    # (1) teacher-forced: the oracle's feature-space graphs are injected -> isolates arithmetic parity
+    forced = torch.stack([gi.to(torch.int32) for gi in taps["graph_idx"]], 0)
+    got_tf = mfd(p.to(DEV), forced_idx=forced).cpu().numpy()
+    spk = mfd.tap("spikes", B, 100).cpu().numpy().reshape(B, 100, 7, 960)
+    ref_spk = taps["spikes"].permute(1, 3, 0, 2).numpy()                                # [T,B,960,M] -> [B,M,T,960]
+    assert np.abs(spk - ref_spk).max() < 2e-3
+    assert _agree(spk, ref_spk) >= 0.999
+    np.testing.assert_allclose(mfd.tap("pool", B, 100).cpu().numpy().reshape(B, 7, 768), taps["pool"].permute(1, 0, 2).numpy(), rtol=0, atol=2e-3)
+    rel_tf = np.abs(got_tf - ref) / np.maximum(np.abs(ref), 1e-6)
+    assert rel_tf.max() < 1e-3, rel_tf
+    assert np.abs(got_tf[:3] - g[tag + "_dist"]).max() / np.abs(g[tag + "_dist"]).max() < 1e-3
+    # (2) free-running: own feature-space kNN; near-ties may pick other neighbours -> reported, bounded
+    got = mfd(p.to(DEV)).cpu().numpy()
+    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
+    print("fd %s: teacher-forced max rel %.2e, free-running max rel %.2e" % (tag, rel_tf.max(), rel.max()))
+    assert rel.max() < 5e-3
+    assert (got >= 0).all()
+
+
+def test_model_input_layouts_and_errors(lib, golden):
+    mfn, mfd, _, _ = _models(False)
+    p = torch.from_numpy(golden.models["patches"]).to(DEV)
+    n = mfn(p)
+    assert torch.equal(mfn(p.permute(0, 2, 1).contiguous()), n)                 # [B,3,M] layout
+    assert torch.equal(mfn(p.unsqueeze(0)).squeeze(0), n)                       # [B,Np,M,3] layout
+    d = mfd(p)
+    assert torch.equal(mfd(p.unsqueeze(0)).squeeze(0), d)
+    assert mfn(p[:0]).shape == (0, 3) and mfd(p[:0]).shape == (0,)
+    assert mfn.reset_states() is None
+    with pytest.raises(N.SapcuError):
+        mfn(torch.zeros(2, 3, 3, device=DEV))
+    with pytest.raises(N.SapcuError):
+        mfn(torch.zeros(2, 200, 3, device=DEV))
+    # a workspace too small for S patches only changes the chunking, never the result
+    big = torch.cat([p] * 5, 0)
+    ref = mfn(big)
+    mfn.WORKSPACE_CAP = N.lib().sapcu_model_workspace_bytes(mfn._ensure_handle(), 4, 100)
+    mfn._ws = None
+    assert torch.equal(mfn(big), ref)
+    # weights changed in place -> handle is rebuilt
+    with torch.no_grad():
+        mfn.decoder.fc_out.bias.add_(1.0)
+    assert not torch.equal(mfn(p), n)
+
+
+# ----------------------------------------------------------------------------------------- pipeline
+def test_pipeline_golden_and_invariants(lib, sphere, golden):
+    from sapcu_b200.generation import Generator3D6
+    cloud, seeds = sphere
+    mfn, mfd, sd_fn, sd_fd = _models(True)
+    gen = Generator3D6(mfn, mfd, DEV, k_neighbors=100, remove_outliers=False)
+    g = golden.pipeline
+    pts = gen.upsample(np.expand_dims(cloud, 0), seeds=g["seeds"])
+    assert pts.dtype == np.float64 and pts.shape == (32, 3)
+    d_c, d_s = torch.from_numpy(cloud).to(DEV), torch.from_numpy(g["seeds"]).to(DEV)
+    out, idx, n, d = gen.displace_device(d_c, d_s, return_parts=True)
+    assert np.array_equal(out.cpu().numpy(), pts)
+    assert _angle_deg(n.cpu().numpy(), g["normals"]).max() < 0.1
+    # the fd input depends on fn's normal, so the end-to-end distance carries both deviations
+    assert (np.abs(d.cpu().numpy() - g["dist"]) / np.abs(g["dist"])).max() < 5e-3
+    assert np.abs(pts - g["points"]).max() < 5e-3 * np.abs(g["dist"]).max()
+    # full configuration-2 size: size-independent properties
+    S = 8192
+    gen2 = Generator3D6(mfn, mfd, DEV, k_neighbors=100, remove_outliers=False)
+    d_s = torch.from_numpy(seeds[:S]).to(DEV)
+    out, idx, n, d = gen2.displace_device(d_c, d_s, return_parts=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and (d >= 0).all()
+    np.testing.assert_allclose(n.norm(dim=1).cpu().numpy(), 1.0, atol=1e-6)
+    assert np.array_equal(out.cpu().numpy(), orc.displace(seeds[:S], n.cpu().numpy(), d.cpu().numpy()))   # x + n*d identity
+    i_np = idx.cpu().numpy()
+    assert (np.sort(i_np, axis=1)[:, 1:] != np.sort(i_np, axis=1)[:, :-1]).all()                          # no duplicates
+    dd = np.linalg.norm(cloud[i_np] - seeds[:S, None, :], axis=2)
+    assert (np.diff(dd, axis=1) >= -1e-15).all()                                                         # ascending
+    # seeds are independent units: any split of the seed set gives bit-identical points (multi-GPU invariance)
+    gen2.seeds_per_pass = 1000
+    out2 = gen2.displace_device(d_c, d_s)
+    assert torch.equal(out2, out)
+    lo = gen2.displace_device(d_c, d_s[:3000].contiguous())
+    hi = gen2.displace_device(d_c, d_s[3000:].contiguous())
+    assert torch.equal(torch.cat([lo, hi]), out)
+    # outlier filter (next-row scope) keeps the reference's semantics
+    gen2.remove_outliers = True
+    gen2.seeds_per_pass = None
+    filtered = gen2.upsample(np.expand_dims(cloud, 0), seeds=seeds[:256])
+    assert 0 < filtered.shape[0] <= 256

@@ -1,0 +1,130 @@
+"""CPU: host-side logic -- the C ABI surface, configuration / checkpoint boundary, seed sharding."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import sapcu_b200
+from sapcu_b200 import _native as N
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    """include/sapcu_b200.h <-> libsapcu_b200.so <-> the ctypes table (no compute calls: no GPU here)."""
+    hdr = open(os.path.join(ROOT, "include", "sapcu_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sapcu_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(N.EXPORTS)
+    sapcu_b200.build()
+    lib = N.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sapcu_abi_version() == 1
+    assert lib.sapcu_launch_count() == 0
+    assert lib.sapcu_knn_workspace_bytes(2048) >= 2048 * 12
+
+
+def test_no_cpu_fallback_and_error_reporting():
+    lib = N.lib()
+    # bad hyper-parameters are rejected with a message, never a crash
+    import ctypes
+    cfg = (ctypes.c_int32 * 6)(24, 18, 12, 640, 6, 7)
+    assert not lib.sapcu_model_create(N.MODEL_FN, cfg, 6)
+    assert b"num_heads" in lib.sapcu_last_error()
+    from sapcu_b200.fn import config as fc
+    m = fc.get_model(fc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fn.yaml")))
+    with pytest.raises(N.SapcuError, match="no CPU fallback"):
+        m(torch.zeros(2, 100, 3))
+    with pytest.raises(N.SapcuError):
+        m.train()
+    if not torch.cuda.is_available():
+        # finalize needs a device: it must fail loudly rather than run anything on the host
+        with pytest.raises(N.SapcuError):
+            m._ensure_handle()
+
+
+def test_config_and_checkpoint_boundary(tmp_path):
+    from sapcu_b200.fn import config as fc, checkpoints as fck
+    from sapcu_b200.fd import config as dc, checkpoints as dck
+    import sapcu_b200.synthetic as syn
+    # inherit_from + defaults
+    base = tmp_path / "base.yaml"
+    base.write_text("model:\n  k_values: [24, 18, 12]\n  emb_dims: 640\n  num_heads: 8\n")
+    child = tmp_path / "child.yaml"
+    child.write_text("inherit_from: base.yaml\nmodel:\n  time_steps_enc: 6\n  time_steps_dec: 9\n")
+    cfg = fc.load_config(str(child))
+    assert cfg["model"]["k_values"] == [24, 18, 12] and cfg["model"]["time_steps_enc"] == 6
+    assert cfg["model"]["decoder_dropout"] == 0.1
+    with pytest.raises(FileNotFoundError):
+        fc.load_config(str(tmp_path / "nope.yaml"))
+    with pytest.raises(ValueError):
+        fc.get_model({"model": {"emb_dims": 640}})
+    m = fc.get_model(cfg)
+    assert m._cfg_ints() == [24, 18, 12, 640, 6, 8]
+    d = dc.get_model(dc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fd.yaml")), None)
+    assert d._cfg_ints() == [32, 768, 7, 8, 4, 8, 16, 32, 48]
+    # checkpoint round trip, incl. the DataParallel 'module.' prefix the reference strips
+    syn.init_weights(m, 5, True)
+    sd = {("module." + k): v.clone() for k, v in m.state_dict().items()}
+    torch.save({"model": sd, "epoch_it": 3}, tmp_path / "model_best.pt")
+    m2 = fc.get_model(cfg)
+    scalars = fck.CheckpointIO(str(tmp_path), model=m2).load("model_best.pt")
+    assert scalars == {"epoch_it": 3}
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    with pytest.raises(FileExistsError):
+        fck.CheckpointIO(str(tmp_path), model=m2).load("missing.pt")
+    with pytest.raises(FileNotFoundError):
+        dck.CheckpointIO(str(tmp_path), model=d).load("missing.pt")
+
+
+def test_reference_yaml_loads_unchanged():
+    ref = "/root/reference/config"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present (GPU box)")
+    from sapcu_b200.fn import config as fc
+    from sapcu_b200.fd import config as dc
+    assert fc.get_model(fc.load_config(ref + "/fn.yaml"))._cfg_ints() == [24, 18, 12, 640, 6, 8]
+    assert dc.get_model(dc.load_config(ref + "/fd.yaml"), None)._cfg_ints() == [32, 768, 7, 8, 4, 8, 16, 32, 48]
+
+
+def test_shard_bounds():
+    from sapcu_b200.sharding import shard_bounds
+    for S in (0, 1, 7, 8192, 370000):
+        for G in (1, 2, 4, 8):
+            b = shard_bounds(S, G)
+            assert b[0][0] == 0 and b[-1][1] == S
+            assert all(b[i][1] == b[i + 1][0] for i in range(G - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import sapcu_b200
+from sapcu_b200.sharding import shard_range, all_gather_rows
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% sys.argv[2], rank=int(sys.argv[1]), world_size=2)
+S = 11
+full = torch.arange(S * 3, dtype=torch.float64).view(S, 3) * 0.5
+lo, hi = shard_range(S, dist.get_rank(), 2)
+out = all_gather_rows(full[lo:hi].clone(), S)
+assert torch.equal(out, full), out
+dist.destroy_process_group()
+print('ok')
+"""
+
+
+def test_all_gather_rows_world2_gloo(tmp_path):
+    """N>1 path on CPU: two gloo ranks shard 11 rows (ragged: 6 + 5), pad, all-gather, trim."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % ROOT)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0 and b"ok" in out, out.decode()
