@@ -150,7 +150,8 @@ def test_intra_knn_matches_reference_formula(lib, sphere, golden):
     p = torch.from_numpy(orc.gather_center(cloud, seeds[:64], idxs))
     ref = orc.intra_knn(p.permute(0, 2, 1).contiguous(), 48).numpy()
     out = torch.empty(64 * 100, 48, dtype=torch.int32, device=DEV)
-    N.check(lib.sapcu_intra_knn(N.ptr(p.to(DEV)), 3, 64, 100, 3, 48, N.ptr(out), None))
+    dp = p.to(DEV)
+    N.check(lib.sapcu_intra_knn(N.ptr(dp), 3, 64, 100, 3, 48, N.ptr(out), None))
     got = out.view(64, 100, 48).cpu().numpy()
     assert (got == ref).mean() >= 0.999          # fp32 expanded-form distances: near-ties may swap
     assert (got[:, :, 0] == np.arange(100)[None, :]).all()
@@ -158,7 +159,8 @@ def test_intra_knn_matches_reference_formula(lib, sphere, golden):
     f = torch.randn(5, 100, 80, generator=torch.Generator().manual_seed(3))
     ref = orc.intra_knn(f[:, :, :64].permute(0, 2, 1).contiguous(), 32).numpy()
     out = torch.empty(500, 32, dtype=torch.int32, device=DEV)
-    N.check(lib.sapcu_intra_knn(N.ptr(f.to(DEV)), 80, 5, 100, 64, 32, N.ptr(out), None))
+    df = f.to(DEV)
+    N.check(lib.sapcu_intra_knn(N.ptr(df), 80, 5, 100, 64, 32, N.ptr(out), None))
     assert (out.view(5, 100, 32).cpu().numpy() == ref).mean() >= 0.9995
     assert patches.shape == (3, 100, 3)
 
@@ -170,7 +172,8 @@ def test_gemm_engine_fp32(lib):
         w = torch.randn(Nn, K, generator=g) / math.sqrt(K)
         b = torch.randn(Nn, generator=g)
         y = torch.empty(R, Nn, dtype=torch.float32, device=DEV)
-        N.check(lib.sapcu_gemm(N.ptr(x.to(DEV)), R, K, N.ptr(w.to(DEV)), Nn, N.ptr(b.to(DEV)), N.ptr(y), N.MODE_FP32, None))
+        dx, dw, db = x.to(DEV), w.to(DEV), b.to(DEV)          # keep the device buffers alive across the call
+        N.check(lib.sapcu_gemm(N.ptr(dx), R, K, N.ptr(dw), Nn, N.ptr(db), N.ptr(y), N.MODE_FP32, None))
         ref = (x.double() @ w.double().t() + b.double()).float()
         assert (y.cpu() - ref).abs().max() < 2e-5 * math.sqrt(K)
 
