@@ -135,7 +135,8 @@ int sapcu_gemm(const float* d_x, int64_t R, int K, const float* d_w, int N, cons
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == SAPCU_MODE_TC) {
     if (!gemm_tc_supported(g, A_PLAIN)) { set_error("gemm: shape R=%lld K=%d N=%d not supported by the tensor-core engine", (long long)R, K, N); return SAPCU_EINVAL; }
-    return launch_gemm_tc(g, A_PLAIN, st);
+    int rc = launch_gemm_tc(g, A_PLAIN, st);
+    return rc ? rc : gemm_tc_check(st);
   }
   SAPCU_REQUIRE(mode == SAPCU_MODE_FP32, "gemm: unknown mode %d", mode);
   return launch_gemm_simt(g, A_PLAIN, true, st);

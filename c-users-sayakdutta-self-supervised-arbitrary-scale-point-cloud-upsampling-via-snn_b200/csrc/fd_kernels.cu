@@ -52,6 +52,35 @@ __global__ void fd_block0_kernel(const Block0Args a) {
   a.out[pt * (a.nscales * 64) + threadIdx.x] = m;
 }
 
+// Factorised EdgeConv (tensor-core mode):  W cat(x_j - x_i, x_j) = (Wa+Wb) x_j - Wa x_i =: P_j - Q_i, so
+// out[i,c] = max_j LeakyReLU(scale_c (P[nb_j,c] - Q[i,c]) + shift_c).  PQ: [P, 2*C] rows = (P | Q).
+__global__ void edge_gather_max_kernel(const float* __restrict__ PQ, int C, const int32_t* __restrict__ idx, int ldi,
+                                       int kk, int Mpts, int64_t P, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, float* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= P * C) return;
+  const int64_t pt = e / C;
+  const int c = (int)(e - pt * C);
+  const int64_t patch0 = (pt / Mpts) * Mpts;
+  const float qv = PQ[pt * 2 * C + C + c];
+  const float sc = scale[c], sh = shift[c];
+  float m = -INFINITY;
+  for (int j = 0; j < kk; ++j) {
+    const int64_t nb = patch0 + idx[pt * ldi + j];
+    const float y = fmaf(PQ[nb * 2 * C + c] - qv, sc, sh);
+    m = fmaxf(m, act_leaky(y));
+  }
+  out[e] = m;
+}
+
+int launch_edge_gather_max(const float* PQ, int C, const int32_t* idx, int ldi, int kk, int Mpts, int64_t P,
+                           const float* scale, const float* shift, float* out, cudaStream_t st) {
+  if (P == 0) return 0;
+  edge_gather_max_kernel<<<(unsigned)ceil_div(P * C, 256), 256, 0, st>>>(PQ, C, idx, ldi, kk, Mpts, P, scale, shift, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
 // out[row*(T*ldo) + t*ldo + c] = spike at step t of channel c for input U[row*ldu + c]   (all_steps)
 // out[row*ldo + c]             = spike at step T-1                                        (!all_steps)
 template <bool EIF, bool PRECISE>

@@ -78,6 +78,35 @@ __global__ void attn_out_kernel(const float* __restrict__ logits, const float* _
   out[e] = res;
 }
 
+// fn attention input materialised for the tensor-core engine: out[e,c] = (q[pt,c] - k[nb,c]) + pos[e,c]
+__global__ void attn_in_kernel(const float* __restrict__ Q, const float* __restrict__ Kf, int64_t ldq,
+                               const float* __restrict__ pos, const int32_t* __restrict__ idx, int ldi, int kk,
+                               int Mpts, int64_t E, int D, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // over E * D/4 float4s
+  const int D4 = D >> 2;
+  if (i >= E * D4) return;
+  const int64_t e = i / D4;
+  const int c4 = (int)(i - e * D4);
+  const int64_t pt = e / kk;
+  const int64_t nb = (pt / Mpts) * Mpts + idx[pt * ldi + (e - pt * kk)];
+  const float4 q = reinterpret_cast<const float4*>(Q + pt * ldq)[c4];
+  const float4 k = reinterpret_cast<const float4*>(Kf + nb * ldq)[c4];
+  const float4 x = reinterpret_cast<const float4*>(pos + e * D)[c4];
+  float4 o;
+  o.x = __fadd_rn(__fsub_rn(q.x, k.x), x.x); o.y = __fadd_rn(__fsub_rn(q.y, k.y), x.y);
+  o.z = __fadd_rn(__fsub_rn(q.z, k.z), x.z); o.w = __fadd_rn(__fsub_rn(q.w, k.w), x.w);
+  reinterpret_cast<float4*>(out + e * D)[c4] = o;
+}
+
+int launch_attn_in(const float* Q, const float* Kf, int64_t ldq, const float* pos, const int32_t* idx, int ldi, int kk,
+                   int Mpts, int64_t E, int D, float* out, cudaStream_t st) {
+  SAPCU_REQUIRE((D & 3) == 0 && (ldq & 3) == 0, "attn_in: D and ldq must be multiples of 4");
+  if (E == 0) return 0;
+  attn_in_kernel<<<(unsigned)ceil_div(E * (D >> 2), 256), 256, 0, st>>>(Q, Kf, ldq, pos, idx, ldi, kk, Mpts, E, D, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
 // out[(s*Tt + t)*C + c] = max_m X[((s*M + m)*Tt + t)*C + c]
 __global__ void group_max_kernel(const float* __restrict__ X, int64_t S, int M, int Tt, int C, float* __restrict__ out) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -56,7 +56,7 @@ FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
 }
 
 struct FdPlan {
-  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *SPK, *AGG, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
+  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *PQ, *SPK, *AGG, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
   size_t bytes; int k, kmax0;
 };
 FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
@@ -67,6 +67,7 @@ FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
   p.idx0 = b.take<int32_t>(P * p.kmax0); p.idxf = b.take<int32_t>(P * p.k);
   p.F0 = b.take<float>(P * 64 * f.nscales);
   p.U0 = b.take<float>(P * 64); p.U1 = b.take<float>(P * 128); p.U2 = b.take<float>(P * 256); p.U3 = b.take<float>(P * 512);
+  p.PQ = b.take<float>(P * 1024);          // factorised EdgeConv (P | Q) rows, tensor-core mode
   p.SPK = b.take<float>(P * f.T * 960);
   p.AGG = b.take<float>(P * f.T * f.emb);
   p.POOL = b.take<float>(s * f.T * f.emb); p.Z = b.take<float>(s * f.emb);
@@ -129,7 +130,11 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     SAPCU_TRY(launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias,
                                     k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, p.E1, st));
     SAPCU_TRY(g.layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
-    {
+    if (mode == SAPCU_MODE_TC) {
+      // the TMA-fed tensor-core engine reads plain row-major operands: materialise q_i - k_j + pos_ij (E1 is free)
+      SAPCU_TRY(launch_attn_in(p.QKV, p.QKV + D, 3 * D, p.E2, p.idx, p.kmax, kk, M, E, D, p.E1, st));
+      SAPCU_TRY(g.layer(k.fc_gamma, p.E1, D, E, p.E3, D, ACT_LIF, &k.snn_gamma, 4));
+    } else {
       GemmArgs a;
       a.A = p.E2; a.lda = D; a.R = E; a.K = D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
       a.Q = p.QKV; a.Kf = p.QKV + D; a.ldq = 3 * D;
@@ -180,12 +185,19 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
       SAPCU_TRY(launch_intra_knn(p.SPK + off_in[b], ldspk, s, M, cin[b], p.k, p.idxf, st));
       idx = p.idxf;
     }
-    GemmArgs a;
-    a.R = P * p.k; a.K = 2 * cin[b]; a.idx = idx; a.ldi = p.k; a.kk = p.k; a.Mpts = M;
-    a.F = p.SPK + off_in[b]; a.ldf = ldspk; a.C = cin[b];
-    a.W = f.conv[b].W; a.N = cout[b]; a.scale = f.conv[b].scale; a.shift = f.conv[b].shift;
-    a.act = ACT_LEAKY; a.group = 32; a.Y = U[b]; a.ldc = cout[b];
-    SAPCU_TRY(g.run(a, A_EDGECAT));
+    if (mode == SAPCU_MODE_TC) {
+      // factorised EdgeConv: one per-POINT contraction [P, Cin] x [2 Cout, Cin]^T, then gather / BN / LeakyReLU / max_k
+      Layer L = f.convf[b];
+      SAPCU_TRY(g.layer(L, p.SPK + off_in[b], ldspk, P, p.PQ, 2 * cout[b], ACT_NONE));
+      SAPCU_TRY(launch_edge_gather_max(p.PQ, cout[b], idx, p.k, p.k, M, P, f.conv[b].scale, f.conv[b].shift, U[b], st));
+    } else {
+      GemmArgs a;
+      a.R = P * p.k; a.K = 2 * cin[b]; a.idx = idx; a.ldi = p.k; a.kk = p.k; a.Mpts = M;
+      a.F = p.SPK + off_in[b]; a.ldf = ldspk; a.C = cin[b];
+      a.W = f.conv[b].W; a.N = cout[b]; a.scale = f.conv[b].scale; a.shift = f.conv[b].shift;
+      a.act = ACT_LEAKY; a.group = 32; a.Y = U[b]; a.ldc = cout[b];
+      SAPCU_TRY(g.run(a, A_EDGECAT));
+    }
     SAPCU_TRY(launch_neuron_unroll(b == 0, precise, U[b], cout[b], P, cout[b], T, f.blk[b + 1].np, f.blk[b + 1].ep, 1,
                                    p.SPK + off_out[b], 960, st));
   }
@@ -248,6 +260,7 @@ int sapcu_fn_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
     const FnPlan p = fn_plan(m->fn, s, M, d_ws);
     SAPCU_TRY(fn_chunk(m->fn, d_patches + s0 * M * 3, s, M, d_normals + s0 * 3, p, mode, st));
   }
+  if (mode == SAPCU_MODE_TC) SAPCU_TRY(gemm_tc_check(st));
   return 0;
 }
 
@@ -256,7 +269,7 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
   SAPCU_TRY(check_common(m, SAPCU_MODEL_FD, d_patches, S, M, d_dist, d_ws, mode));
   if (S == 0) return 0;
   const int k = m->fd.k < M ? m->fd.k : M;
-  SAPCU_REQUIRE(k == 32, "fd_forward: the fused EdgeConv max-pool is built for min(k, M) == 32 (got %d)", k);
+  SAPCU_REQUIRE(k == 32 || mode == SAPCU_MODE_TC, "fd_forward(fp32): the fused EdgeConv max-pool is built for min(k, M) == 32 (got %d)", k);
   const int64_t chunk = pick_chunk(m, S, M, ws_bytes);
   if (chunk < 1) { set_error("fd_forward: workspace of %zu bytes cannot hold one patch (need %zu)", ws_bytes, sapcu_model_workspace_bytes(m, 1, M)); return SAPCU_EWORKSPACE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -268,6 +281,7 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
       for (int b = 0; b < 3; ++b) forced[b] = d_forced_idx + ((int64_t)b * S + s0) * M * k;
     SAPCU_TRY(fd_chunk(m->fd, d_patches + s0 * M * 3, s, M, d_dist + s0, forced, p, mode, st));
   }
+  if (mode == SAPCU_MODE_TC) SAPCU_TRY(gemm_tc_check(st));
   return 0;
 }
 

@@ -1,11 +1,439 @@
-// tcgen05 tensor-core GEMM engine -- placeholder until the engine lands: reports "unsupported" so that
-// SAPCU_MODE_TC transparently uses the SIMT engine for every contraction.
+// tcgen05 tensor-core GEMM engine (SAPCU_MODE_TC):  Y[R,N] = epi( X[R,K] * W[N,K]^T ), fp32 in / fp32 out.
+//
+// fp32-faithful products on the 5th-gen tensor cores by the 3xTF32 split
+//     x = x_hi + x_lo,  w = w_hi + w_lo   (hi = top 19 bits, lo = x - hi, exact in fp32)
+//     x*w ~= w_hi*x_hi + w_hi*x_lo + w_lo*x_hi        (the dropped w_lo*x_lo term is <= 2^-20 relative)
+// accumulated in fp32 in TMEM.  This keeps the "fp32 parity mode" tolerances while moving every large
+// contraction off the FFMA pipe.
+//
+// Orientation: the WEIGHT tile is the UMMA A operand (M = 128 output channels -> TMEM lanes) and the
+// ACTIVATION tile is the B operand (N = 128 rows -> TMEM columns).  One epilogue thread therefore owns one
+// output channel: bias / BatchNorm / neuron parameters live in registers, the LIF^T recurrence runs on
+// register-resident accumulators, a max over 32 consecutive rows (EdgeConv k = 32) is thread-local, and
+// the 32 lanes of a warp store 32 consecutive channels of one row (one 128-byte line).
+//
+// Persistent, warp-specialised CTA (1 per SM, 448 threads):
+//   warp 0        TMA producer   cp.async.bulk.tensor of the raw fp32 W and X tiles (128B swizzle)
+//   warp 1        MMA issuer     tcgen05.mma.kind::tf32 (12 per k-block), tcgen05.commit; owns TMEM alloc
+//   warps 2..5    splitter       rewrite the landed tile as hi (in place) and lo (second buffer)
+//   warps 6..13   epilogue       tcgen05.ld -> bias/BN/activation/LIF -> coalesced global stores
+// Pipelines: smem ring of 3 stages x 64 KiB (mbarriers raw-full / split-full / empty) and 4 TMEM accumulator
+// buffers of 128 columns (mbarriers tmem-full / tmem-empty) so the epilogue of tile i overlaps the MMAs of
+// tile i+1..i+3.  Every mbarrier wait carries a clock64() watchdog: a protocol error surfaces as an error
+// code, never as a hung GPU.
+//
+// Roofline: tensor pipe (tf32: 2048 MAC/clk/SM, x3 passes); the LIF epilogue is MUFU bound (3 MUFU per
+// element-step, 16/clk/SM) and overlaps the MMA stream.
+#include <cuda.h>
 #include "gemm_tc.h"
+#include "neuron.cuh"
 
 namespace sapcu {
-bool gemm_tc_supported(const GemmArgs&, int) { return false; }
-int launch_gemm_tc(const GemmArgs&, int, cudaStream_t) {
-  set_error("gemm_tc: not built");
-  return -1;
+
+constexpr int TC_BM = 128;        // output channels per tile (UMMA M)
+constexpr int TC_BN = 128;        // activation rows per tile (UMMA N)
+constexpr int TC_BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_ACC = 4;         // TMEM accumulator buffers: 4 x 128 columns = all 512
+constexpr int TC_THREADS = 448;
+constexpr int TC_SPLIT_WARP0 = 2, TC_SPLIT_WARPS = 4;
+constexpr int TC_EPI_WARP0 = 6, TC_EPI_WARPS = 8;
+constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB (BM == BN)
+constexpr uint32_t TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // W_hi, W_lo, X_hi, X_lo
+constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr long long TC_WATCHDOG_CLOCKS = 6000000000LL;         // ~3 s at 1.9 GHz
+
+struct TcParams {
+  int64_t R; int N, K;
+  const float* bias; const float* scale; const float* shift;
+  int act, T; const float* nparams;
+  const float* residual; int64_t ldr;
+  float* Y; int64_t ldc;
+  int group;                  // 0 or 32
+  int m_tiles; int64_t n_tiles;
+  int* err;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// returns false after the watchdog fired (here or in another role)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  int spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023) == 0) {
+      if (*reinterpret_cast<volatile int*>(err) != 0) return false;
+      if (clock64() - t0 > TC_WATCHDOG_CLOCKS) { atomicExch(err, 1); return false; }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzled operand tile (rows of 32 fp32 = 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address        bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset  bits [16,30) (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// LIF^T on NV independent accumulators of one channel (interleaved for ILP); fast-math flavour.
+template <int NV>
+__device__ __forceinline__ void lif_chain_vec(float (&u)[NV], const NeuronParams& p, int T) {
+  float m[NV], th[NV], rho[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { m[i] = 0.0f; th[i] = p.th0; rho[i] = 0.0f; }
+  const float c_g = 0.5f / 2.5066282746310002f;        // 0.5 / sqrt(2 pi)
+  const float k_g = -0.5f * 1.4426950408889634f;       // exp(-v^2/2) = 2^(k_g v^2)
+  const float k_s = -10.0f * 1.4426950408889634f;      // exp(-10 v)  = 2^(k_s v)
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float x = (rho[i] <= 0.0f) ? u[i] : 0.0f;
+      const float mm = fmaf(m[i] * p.d, 1.0f - rho[i], x);
+      const float vc = fminf(fmaxf(mm - th[i], -10.0f), 10.0f);
+      const float g = exp2f_approx(k_g * vc * vc);
+      const float e = exp2f_approx(k_s * vc);
+      const float s = fmaf(c_g, g, __fdividef(0.5f, 1.0f + e));
+      m[i] = mm * (1.0f - s);
+      rho[i] = fmaf(rho[i], p.r, s);
+      th[i] = fmaf(fmaf(p.a, s, th[i]) - p.th0, 0.95f, p.th0);
+      u[i] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // 128B swizzle needs 1024 B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  // barrier map (8 bytes each)
+  auto bar_raw = [&](int s) { return bar_base + 8u * s; };
+  auto bar_split = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
+  auto bar_tfull = [&](int a) { return bar_base + 8u * (3 * TC_STAGES + a); };
+  auto bar_tempty = [&](int a) { return bar_base + 8u * (3 * TC_STAGES + TC_ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * TC_STAGES + 2 * TC_ACC);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 8 * (3 * TC_STAGES + 2 * TC_ACC));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = p.K / TC_BK;
+  const int64_t total_tiles = p.n_tiles * p.m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), TC_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < TC_ACC; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), TC_EPI_WARPS); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_x);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ======================================================================== TMA producer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0; bool ok = true;
+      for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+        const int m_t = (int)(t % p.m_tiles);
+        const int64_t n_t = t / p.m_tiles;
+        for (int kb = 0; kb < nk; ++kb) {
+          if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
+          const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+          mbar_expect_tx(bar_raw(s), 2 * TC_TILE_BYTES);
+          tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, m_t * TC_BM);
+          tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, (int)(n_t * TC_BN));
+          if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      int s = 0, a = 0; uint32_t ph = 0, aph = 0; bool ok = true;
+      for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+        if (!(ok = mbar_wait(bar_tempty(a), aph ^ 1u, p.err))) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * TC_BN);
+        for (int kb = 0; kb < nk; ++kb) {
+          if (!(ok = mbar_wait(bar_split(s), ph, p.err))) break;
+          tc_fence_after();
+          const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+          const uint64_t w_hi = umma_desc_sw128(st), w_lo = umma_desc_sw128(st + TC_TILE_BYTES);
+          const uint64_t x_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+          for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+            const uint64_t adv = (uint64_t)(k8 * 2);            // 8 tf32 = 32 B = 2 x 16 B along the swizzled row
+            umma_tf32(tmem_d, w_lo + adv, x_hi + adv, (kb | k8) ? 1u : 0u);
+            umma_tf32(tmem_d, w_hi + adv, x_lo + adv, 1u);
+            umma_tf32(tmem_d, w_hi + adv, x_hi + adv, 1u);
+          }
+          umma_commit(bar_empty(s));                             // frees the smem stage when these MMAs retire
+          if (kb == nk - 1) umma_commit(bar_tfull(a));           // accumulator complete
+          if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (++a == TC_ACC) { a = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp < TC_EPI_WARP0) {
+    // ======================================================================== splitter: raw -> (hi, lo)
+    const int tid = threadIdx.x - TC_SPLIT_WARP0 * 32;            // 0..127
+    int s = 0; uint32_t ph = 0; bool ok = true;
+    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      for (int kb = 0; kb < nk; ++kb) {
+        if (!(ok = mbar_wait(bar_raw(s), ph, p.err))) break;
+        uint8_t* st = smem_gen + s * TC_STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {                          // 0: W tile, 1: X tile
+          float4* hi = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
+#pragma unroll
+          for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (TC_SPLIT_WARPS * 32); ++i) {
+            const int e = tid + i * TC_SPLIT_WARPS * 32;
+            const float4 v = hi[e];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            hi[e] = h; lo[e] = l;
+          }
+        }
+        fence_proxy_async();                                      // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(bar_split(s));
+        if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ======================================================================== epilogue
+    const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+    const int half = (warp - TC_EPI_WARP0) >> 2;                  // which 64 columns of the 128-column tile
+    int a = 0; uint32_t aph = 0; bool ok = true;
+    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      const int m_t = (int)(t % p.m_tiles);
+      const int64_t n_t = t / p.m_tiles;
+      const int c = m_t * TC_BM + q * 32 + lane;                  // this thread's output channel
+      const bool cv = c < p.N;
+      const int cc = cv ? c : 0;
+      const float bia = p.bias ? p.bias[cc] : 0.0f;
+      const float sc = p.scale ? p.scale[cc] : 1.0f;
+      const float sh = p.shift ? p.shift[cc] : 0.0f;
+      NeuronParams np{0.9f, 0.01f, 0.5f, 1.0f};
+      if (p.act == ACT_LIF) { np.d = p.nparams[cc]; np.a = p.nparams[p.N + cc]; np.r = p.nparams[2 * p.N + cc]; np.th0 = p.nparams[3 * p.N + cc]; }
+      if (!(ok = mbar_wait(bar_tfull(a), aph, p.err))) break;
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col0 = half * 64 + ch * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + col0), v);
+        const int64_t r0 = n_t * TC_BN + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float y = v[j] + bia;
+          y = fmaf(y, sc, sh);
+          if (p.residual && cv && r0 + j < p.R) y += p.residual[(r0 + j) * p.ldr + c];
+          if (p.act == ACT_LEAKY) y = act_leaky(y);
+          else if (p.act == ACT_GELU) y = act_gelu(y);
+          v[j] = y;
+        }
+        if (p.act == ACT_LIF) {
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = v[j0 + j];
+            lif_chain_vec<8>(u, np, p.T);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j0 + j] = u[j];
+          }
+        }
+        if (p.group == 32) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (r0 + j < p.R) mx = fmaxf(mx, v[j]);
+          if (cv && r0 < p.R) p.Y[(r0 >> 5) * p.ldc + c] = mx;
+        } else if (cv) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (r0 + j < p.R) p.Y[(r0 + j) * p.ldc + c] = v[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(a));
+      if (++a == TC_ACC) { a = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, K] (row stride ld floats) -> boxes of [box_rows, 32] with 128B swizzle, OOB rows/cols read as 0
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled entry point unavailable"); return -2; }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d ld=%lld", (int)r, (long long)rows, K, (long long)ld); return -2; }
+  return 0;
+}
+
+static int* tc_err_flag() {       // one device word per process, zero-initialised
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+bool gemm_tc_supported(const GemmArgs& g, int amode) {
+  if (amode != A_PLAIN) return false;
+  if (g.K % TC_BK != 0 || g.K < TC_BK) return false;
+  if (g.R < 1024) return false;                                   // small row counts (decoder heads) stay on the SIMT engine
+  if ((g.lda % 4) != 0 || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return false;
+  if (g.group != 0 && g.group != 32) return false;
+  if (g.R >= ((int64_t)1 << 31) || g.N > (1 << 20)) return false;
+  return true;
+}
+
+int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
+  SAPCU_REQUIRE(gemm_tc_supported(g, amode), "gemm_tc: unsupported problem");
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_done = true;
+  }
+  int* err = tc_err_flag();
+  SAPCU_REQUIRE(err != nullptr, "gemm_tc: cannot allocate the watchdog flag");
+  CUtensorMap mw, mx;
+  int rc = make_map(&mw, g.W, g.N, g.K, g.K, TC_BM);
+  if (rc) return rc;
+  rc = make_map(&mx, g.A, g.R, g.K, g.lda, TC_BN);
+  if (rc) return rc;
+  TcParams p;
+  p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
+  p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.group = g.group;
+  p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, TC_BN); p.err = err;
+  const int64_t total = p.n_tiles * p.m_tiles;
+  const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mw, mx, p);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+// watchdog status (0 = fine); synchronises the stream
+int gemm_tc_check(cudaStream_t st) {
+  int* err = tc_err_flag();
+  if (!err) return 0;
+  int h = 0;
+  SAPCU_CUDA_CHECK(cudaMemcpyAsync(&h, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SAPCU_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h) { cudaMemset(err, 0, sizeof(int)); set_error("gemm_tc: pipeline watchdog fired (mbarrier protocol stall)"); return -2; }
+  return 0;
+}
+
 }  // namespace sapcu

@@ -7,4 +7,6 @@ namespace sapcu {
 // everything else stays on the fp32 SIMT engine.
 bool gemm_tc_supported(const GemmArgs& g, int amode);
 int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st);
+// pipeline watchdog status of every launch_gemm_tc since the last check (0 = fine); synchronises the stream
+int gemm_tc_check(cudaStream_t st);
 }  // namespace sapcu

@@ -23,6 +23,8 @@ int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32
 int launch_attn_out(bool precise, const float* logits, const float* pos, const float* V, int64_t ldv,
                     const int32_t* idx, int ldi, int kk, int Mpts, int64_t P, int D, float sqrt_hd, float* out,
                     cudaStream_t st);
+int launch_attn_in(const float* Q, const float* Kf, int64_t ldq, const float* pos, const int32_t* idx, int ldi, int kk,
+                   int Mpts, int64_t E, int D, float* out, cudaStream_t st);
 int launch_group_max(const float* X, int64_t S, int M, int Tt, int C, float* out, cudaStream_t st);
 int launch_fn_head(const float* H, int K, int64_t S, const float* W, const float* b, const float* lnw,
                    const float* lnb, float* out, cudaStream_t st);
@@ -30,6 +32,8 @@ int launch_fn_head(const float* H, int K, int64_t S, const float* W, const float
 int launch_fd_block0(const float* xyz, const int32_t* idx, int ldi, int Mpts, int64_t P, int nscales, const int* ks,
                      const float* const* W, const float* const* scale, const float* const* shift, float* out,
                      cudaStream_t st);
+int launch_edge_gather_max(const float* PQ, int C, const int32_t* idx, int ldi, int kk, int Mpts, int64_t P,
+                           const float* scale, const float* shift, float* out, cudaStream_t st);
 int launch_neuron_unroll(bool eif, bool precise, const float* U, int64_t ldu, int64_t rows, int C, int T,
                          const float* np, const float* ep, int all_steps, float* out, int64_t ldo, cudaStream_t st);
 int launch_temporal_lif(bool precise, const float* pool, int64_t S, int Tt, int C, const float* wsm, const float* np,

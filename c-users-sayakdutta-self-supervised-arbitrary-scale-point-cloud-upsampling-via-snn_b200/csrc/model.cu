@@ -167,6 +167,18 @@ void build_fd(Builder& B) {
   for (int b = 0; b < 3; ++b) {
     const std::string p = "encoder.conv_blocks." + std::to_string(b);
     B.layer(f.conv[b], p + ".0", p + ".1", cout[b], 2 * cin[b], false);
+    if (auto* w = B.get(p + ".0.weight", (size_t)cout[b] * 2 * cin[b])) {
+      // W = [Wa | Wb] acts on cat(x_j - x_i, x_j):  rows [0,Cout) = Wa + Wb (applied to x_j), rows [Cout,2Cout) = Wa (to x_i)
+      std::vector<float> wf((size_t)2 * cout[b] * cin[b]);
+      for (int o = 0; o < cout[b]; ++o)
+        for (int i = 0; i < cin[b]; ++i) {
+          const float wa = (*w)[(size_t)o * 2 * cin[b] + i], wb = (*w)[(size_t)o * 2 * cin[b] + cin[b] + i];
+          wf[(size_t)o * cin[b] + i] = wa + wb;
+          wf[((size_t)cout[b] + o) * cin[b] + i] = wa;
+        }
+      f.convf[b].N = 2 * cout[b]; f.convf[b].K = cin[b];
+      B.put(wf.data(), wf.size(), &f.convf[b].W);
+    }
   }
   B.layer(f.msc, "encoder.multi_scale_conv.0", "encoder.multi_scale_conv.1", f.emb, 960, false);
   B.neuron(f.snn_fc, {"encoder.snn_fc"}, f.emb, false);

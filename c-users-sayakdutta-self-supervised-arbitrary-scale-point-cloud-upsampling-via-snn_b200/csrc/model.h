@@ -31,6 +31,7 @@ struct FnNet {
 struct FdNet {
   int k = 0, emb = 0, T = 0, heads = 0, nscales = 0; int kscales[8] = {0};
   Layer first[8], fusion, conv[3], msc;
+  Layer convf[3];              // factorised EdgeConv weights [(Wa+Wb) ; Wa] : [2*Cout, Cin] (tensor-core mode)
   Neuron blk[4], snn_fc;
   const float* tw = nullptr;   // softmax(temporal weights) [T]
   Layer fc_in, rb_fc0[2], rb_fc1[2], rb_res[2], to_qkv, to_out, fc_hidden, fc_dist;

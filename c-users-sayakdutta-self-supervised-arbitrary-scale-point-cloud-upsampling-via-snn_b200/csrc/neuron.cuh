@@ -25,6 +25,12 @@ struct EifParams {      // per channel, clamped
   float thrh;  // theta_rh in [0.1, 2]
 };
 
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // PRECISE=true : libdevice expf (<= 1 ulp) -- the fp32 parity mode
 // PRECISE=false: ex2.approx based __expf     -- the tensor-core mode
 template <bool PRECISE>

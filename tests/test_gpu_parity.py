@@ -178,6 +178,25 @@ def test_gemm_engine_fp32(lib):
         assert (y.cpu() - ref).abs().max() < 2e-5 * math.sqrt(K)
 
 
+def test_gemm_engine_tensor_core(lib):
+    """tcgen05 engine (3xTF32 split, TMA-fed, TMEM accumulators): fp32-grade products, ragged tiles, N < 128."""
+    g = torch.Generator().manual_seed(2)
+    for R, K, Nn in ((4096, 64, 128), (5000, 512, 512), (2048, 960, 768), (1500, 192, 640), (3000, 256, 64), (1024, 128, 384),
+                     (40000, 128, 128)):
+        x = torch.randn(R, K, generator=g)
+        w = torch.randn(Nn, K, generator=g) / math.sqrt(K)
+        b = torch.randn(Nn, generator=g)
+        y = torch.full((R, Nn), float("nan"), dtype=torch.float32, device=DEV)
+        dx, dw, db = x.to(DEV), w.to(DEV), b.to(DEV)
+        N.check(lib.sapcu_gemm(N.ptr(dx), R, K, N.ptr(dw), Nn, N.ptr(db), N.ptr(y), N.MODE_TC, None), "gemm tc %s" % ((R, K, Nn),))
+        torch.cuda.synchronize()
+        ref = (x.double() @ w.double().t() + b.double()).float()
+        err = (y.cpu() - ref).abs().max().item()
+        assert err < 2e-5, ((R, K, Nn), err)
+    # shapes the engine does not take are refused, not mis-computed
+    assert lib.sapcu_gemm(N.ptr(dx), 100, 128, N.ptr(dw), 128, None, N.ptr(y), N.MODE_TC, None) == -1
+
+
 # ----------------------------------------------------------------------------------------- models
 def _angle_deg(a, b):
     cos = (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
@@ -188,12 +207,14 @@ def _agree(a, b):
     return float(((a > HARD) == (b > HARD)).mean())
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
 @pytest.mark.parametrize("stress", [False, True], ids=["default_init", "stress_init"])
-def test_fn_forward_parity(lib, sphere, golden, stress):
+def test_fn_forward_parity(lib, sphere, golden, stress, mode):
     cloud, seeds = sphere
     tag = "stress" if stress else "default"
     mfn, _, sd_fn, _ = _models(stress)
-    B = 8
+    mfn.set_mode(mode)
+    B = 16 if mode == "tc" else 8      # >= 1024 point rows so that the point-level layers also run on the tensor-core engine
     idx = oracle_c.knn(cloud, seeds[:B], 100)
     p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx))
     taps = {}
@@ -230,13 +251,15 @@ def test_fn_forward_parity(lib, sphere, golden, stress):
     np.testing.assert_allclose(tap("gmax"), taps["gmax"].numpy(), rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
 @pytest.mark.parametrize("stress", [False, True], ids=["default_init", "stress_init"])
-def test_fd_forward_parity(lib, sphere, golden, stress):
+def test_fd_forward_parity(lib, sphere, golden, stress, mode):
     tag = "stress" if stress else "default"
     _, mfd, _, sd_fd = _models(stress)
+    mfd.set_mode(mode)
     g = golden.models
     cloud, seeds = sphere
-    B = 8
+    B = 16 if mode == "tc" else 8      # >= 1024 point rows: the factorised EdgeConv contractions run on the tensor-core engine
     idx = oracle_c.knn(cloud, seeds[:B], 100)
     rng = np.random.default_rng(9)
     nrm = rng.normal(size=(B, 3)).astype(np.float32)
@@ -260,7 +283,7 @@ def test_fd_forward_parity(lib, sphere, golden, stress):
     # (2) free-running: own feature-space kNN; near-ties may pick other neighbours -> reported, bounded
     got = mfd(p.to(DEV)).cpu().numpy()
     rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
-    print("fd %s: teacher-forced max rel %.2e, free-running max rel %.2e" % (tag, rel_tf.max(), rel.max()))
+    print("fd %s/%s: teacher-forced max rel %.2e, free-running max rel %.2e" % (tag, mode, rel_tf.max(), rel.max()))
     assert rel.max() < 5e-3
     assert (got >= 0).all()
 
@@ -332,3 +355,21 @@ def test_pipeline_golden_and_invariants(lib, sphere, golden):
     gen2.seeds_per_pass = None
     filtered = gen2.upsample(np.expand_dims(cloud, 0), seeds=seeds[:256])
     assert 0 < filtered.shape[0] <= 256
+
+
+def test_pipeline_tensor_core_mode(lib, sphere, golden):
+    """The whole path in tensor-core mode against the reference-generated golden points (deviation reported)."""
+    from sapcu_b200.generation import Generator3D6
+    cloud, _ = sphere
+    mfn, mfd, _, _ = _models(True)
+    mfn.set_mode("tc"), mfd.set_mode("tc")
+    gen = Generator3D6(mfn, mfd, DEV, k_neighbors=100, remove_outliers=False)
+    g = golden.pipeline
+    d_c, d_s = torch.from_numpy(cloud).to(DEV), torch.from_numpy(g["seeds"]).to(DEV)
+    out, idx, n, d = gen.displace_device(d_c, d_s, return_parts=True)
+    torch.cuda.synchronize()
+    ang = _angle_deg(n.cpu().numpy(), g["normals"]).max()
+    rel = (np.abs(d.cpu().numpy() - g["dist"]) / np.abs(g["dist"])).max()
+    print("tensor-core mode vs reference: max normal angle %.4f deg, max rel distance err %.2e" % (ang, rel))
+    assert ang < 0.1 and rel < 5e-3
+    assert np.abs(out.cpu().numpy() - g["points"]).max() < 5e-3 * np.abs(g["dist"]).max()
