@@ -1,8 +1,8 @@
 // tcgen05 tensor-core GEMM engine (SAPCU_MODE_TC):  Y[R,N] = epi( X[R,K] * W[N,K]^T ), fp32 in / fp32 out.
 //
 // fp32-faithful products on the 5th-gen tensor cores by the 3xTF32 split
-//     x = x_hi + x_lo,  w = w_hi + w_lo   (hi = top 19 bits, lo = x - hi, exact in fp32)
-//     x*w ~= w_hi*x_hi + w_hi*x_lo + w_lo*x_hi        (the dropped w_lo*x_lo term is <= 2^-20 relative)
+//     x = x_hi + x_lo,  w = w_hi + w_lo   (hi = x rounded to tf32, lo = x - hi, exact in fp32)
+//     x*w ~= w_hi*x_hi + w_hi*x_lo + w_lo*x_hi        (the dropped w_lo*x_lo term is <= 2^-22 relative)
 // accumulated in fp32 in TMEM.  This keeps the "fp32 parity mode" tolerances while moving every large
 // contraction off the FFMA pipe.
 //
@@ -103,6 +103,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// round-to-nearest fp32 -> tf32 (low 13 mantissa bits cleared): an unbiased hi part, |lo| <= 2^-11 |x|
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 // K-major, 128-byte swizzled operand tile (rows of 32 fp32 = 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -270,10 +277,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             const int e = tid + i * TC_SPLIT_WARPS * 32;
             const float4 v = hi[e];
             float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            h.x = tf32_rna(v.x); l.x = v.x - h.x;
+            h.y = tf32_rna(v.y); l.y = v.y - h.y;
+            h.z = tf32_rna(v.z); l.z = v.z - h.z;
+            h.w = tf32_rna(v.w); l.w = v.w - h.w;
             hi[e] = h; lo[e] = l;
           }
         }
