@@ -38,44 +38,107 @@ __global__ void pointwise3_lif_kernel(const float* __restrict__ xyz, const int32
   out[e] = lif_chain<PRECISE>(y, p, T);
 }
 
+// fc_delta on edge offsets + BN + LIF^T for a tile of EPB edges x 128 channels per CTA: the per-edge index
+// arithmetic is done once per edge (not per element), the per-channel parameters live in registers and the
+// T-step recurrence runs on 8 interleaved edges per thread (MUFU-bound instead of latency-bound).
+constexpr int EPB = 64;
+template <bool PRECISE>
+__global__ void __launch_bounds__(128)
+edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts,
+                    int E, int C, const float* __restrict__ W, const float* __restrict__ bias,
+                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ np,
+                    int T, float* __restrict__ out) {
+  __shared__ float pd[EPB][3];
+  const int e0 = blockIdx.x * EPB;
+  for (int i = threadIdx.x; i < EPB; i += blockDim.x) {
+    const int e = e0 + i;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (e < E) {
+      const int pt = e / kk;
+      const int j = e - pt * kk;
+      const int nb = (pt / Mpts) * Mpts + idx[(int64_t)pt * ldi + j];
+      d0 = __fsub_rn(xyz[3 * (int64_t)pt], xyz[3 * (int64_t)nb]);
+      d1 = __fsub_rn(xyz[3 * (int64_t)pt + 1], xyz[3 * (int64_t)nb + 1]);
+      d2 = __fsub_rn(xyz[3 * (int64_t)pt + 2], xyz[3 * (int64_t)nb + 2]);
+    }
+    pd[i][0] = d0; pd[i][1] = d1; pd[i][2] = d2;
+  }
+  __syncthreads();
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  const float w0 = W[3 * c], w1 = W[3 * c + 1], w2 = W[3 * c + 2];
+  const float bi = bias[c], sc = scale[c], sh = shift[c];
+  const NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
+  float* o = out + (int64_t)e0 * C + c;
+  const int n = (E - e0) < EPB ? (E - e0) : EPB;
+#pragma unroll 1
+  for (int g = 0; g < EPB; g += 8) {
+    if (g >= n) break;
+    float u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(w2, pd[g + j][2], fmaf(w1, pd[g + j][1], __fmul_rn(w0, pd[g + j][0])));
+      y = __fadd_rn(y, bi);
+      u[j] = __fadd_rn(__fmul_rn(y, sc), sh);
+    }
+    lif_chain_vec<8, PRECISE>(u, p, T);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (g + j < n) o[(int64_t)(g + j) * C] = u[j];
+  }
+}
+
 constexpr int ATT_KMAX = 32;
 
-template <bool PRECISE>
-__global__ void attn_out_kernel(const float* __restrict__ logits, const float* __restrict__ pos,
-                                const float* __restrict__ V, int64_t ldv, const int32_t* __restrict__ idx, int ldi,
-                                int kk, int Mpts, int64_t P, int D, float sqrt_hd, float* __restrict__ out) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= P * D) return;
-  const int64_t pt = e / D;
-  const int c = (int)(e - pt * D);
-  const int64_t patch0 = (pt / Mpts) * Mpts;
-  float a[ATT_KMAX];
-  float mx = -INFINITY;
+// softmax over the k neighbours + weighted sum.  CTA = 128 channels x APB points; KK is the compile-time
+// neighbour count (12/18/24 for the yaml model, 32 = generic upper bound with run-time kk).
+constexpr int APB = 8;
+template <bool PRECISE, int KK>
+__global__ void __launch_bounds__(128)
+attn_out_kernel(const float* __restrict__ logits, const float* __restrict__ pos, const float* __restrict__ V,
+                int64_t ldv, const int32_t* __restrict__ idx, int ldi, int kk_rt, int Mpts, int P, int D,
+                float sqrt_hd, float* __restrict__ out) {
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= D) return;
+  const int kk = (KK == 32) ? kk_rt : KK;
+  const float inv_s = 1.0f / sqrt_hd;
+  for (int pi = 0; pi < APB; ++pi) {
+    const int pt = blockIdx.x * APB + pi;
+    if (pt >= P) return;
+    const int patch0 = (pt / Mpts) * Mpts;
+    const float* lg = logits + (int64_t)pt * kk * D + c;
+    const float* ps = pos + (int64_t)pt * kk * D + c;
+    float a[KK];
+    float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < ATT_KMAX; ++j) {
-    if (j < kk) {
-      a[j] = __fdiv_rn(logits[(pt * kk + j) * D + c], sqrt_hd);
-      mx = fmaxf(mx, a[j]);
+    for (int j = 0; j < KK; ++j) {
+      if (j < kk) {
+        const float l = lg[(int64_t)j * D];
+        a[j] = PRECISE ? __fdiv_rn(l, sqrt_hd) : l * inv_s;
+        mx = fmaxf(mx, a[j]);
+      }
     }
-  }
-  float sum = 0.0f;
+    float sum = 0.0f;
 #pragma unroll
-  for (int j = 0; j < ATT_KMAX; ++j) {
-    if (j < kk) {
-      a[j] = sapcu_exp<PRECISE>(__fsub_rn(a[j], mx));
-      sum = __fadd_rn(sum, a[j]);
+    for (int j = 0; j < KK; ++j) {
+      if (j < kk) {
+        a[j] = PRECISE ? expf(__fsub_rn(a[j], mx)) : exp2f_approx((a[j] - mx) * 1.4426950408889634f);
+        sum = __fadd_rn(sum, a[j]);
+      }
     }
-  }
-  float res = 0.0f;
+    const float inv_sum = 1.0f / sum;
+    float res = 0.0f;
 #pragma unroll
-  for (int j = 0; j < ATT_KMAX; ++j) {
-    if (j < kk) {
-      const int64_t nb = patch0 + idx[pt * ldi + j];
-      const float vp = __fadd_rn(V[nb * ldv + c], pos[(pt * kk + j) * D + c]);
-      res = __fadd_rn(res, __fmul_rn(__fdiv_rn(a[j], sum), vp));
+    for (int j = 0; j < KK; ++j) {
+      if (j < kk) {
+        const int nb = patch0 + idx[(int64_t)pt * ldi + j];
+        const float vp = __fadd_rn(V[(int64_t)nb * ldv + c], ps[(int64_t)j * D]);
+        if (PRECISE) res = __fadd_rn(res, __fmul_rn(__fdiv_rn(a[j], sum), vp));
+        else res = fmaf(a[j] * inv_sum, vp, res);
+      }
     }
+    out[(int64_t)pt * D + c] = res;
   }
-  out[e] = res;
 }
 
 // fn attention input materialised for the tensor-core engine: out[e,c] = (q[pt,c] - k[nb,c]) + pos[e,c]
@@ -156,11 +219,13 @@ int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32
                           int64_t rows, int C, const float* W, const float* bias, const float* scale,
                           const float* shift, const float* np, int T, float* out, cudaStream_t st) {
   if (rows == 0) return 0;
-  const unsigned grid = (unsigned)ceil_div(rows * C, 256);
   if (edge) {
-    if (precise) pointwise3_lif_kernel<true, true><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
-    else         pointwise3_lif_kernel<true, false><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
+    SAPCU_REQUIRE(rows < ((int64_t)1 << 31), "pointwise3_lif: too many edges for 32-bit indexing");
+    dim3 grid((unsigned)ceil_div(rows, EPB), (unsigned)ceil_div(C, 128));
+    if (precise) edge_pos_lif_kernel<true><<<grid, 128, 0, st>>>(xyz, idx, kk, ldi, Mpts, (int)rows, C, W, bias, scale, shift, np, T, out);
+    else         edge_pos_lif_kernel<false><<<grid, 128, 0, st>>>(xyz, idx, kk, ldi, Mpts, (int)rows, C, W, bias, scale, shift, np, T, out);
   } else {
+    const unsigned grid = (unsigned)ceil_div(rows * C, 256);
     if (precise) pointwise3_lif_kernel<false, true><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
     else         pointwise3_lif_kernel<false, false><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
   }
@@ -172,10 +237,16 @@ int launch_attn_out(bool precise, const float* logits, const float* pos, const f
                     const int32_t* idx, int ldi, int kk, int Mpts, int64_t P, int D, float sqrt_hd, float* out,
                     cudaStream_t st) {
   SAPCU_REQUIRE(kk <= ATT_KMAX, "attn_out: k=%d > %d", kk, ATT_KMAX);
+  SAPCU_REQUIRE(P < ((int64_t)1 << 31), "attn_out: too many points for 32-bit indexing");
   if (P == 0) return 0;
-  const unsigned grid = (unsigned)ceil_div(P * D, 256);
-  if (precise) attn_out_kernel<true><<<grid, 256, 0, st>>>(logits, pos, V, ldv, idx, ldi, kk, Mpts, P, D, sqrt_hd, out);
-  else         attn_out_kernel<false><<<grid, 256, 0, st>>>(logits, pos, V, ldv, idx, ldi, kk, Mpts, P, D, sqrt_hd, out);
+  dim3 grid((unsigned)ceil_div(P, APB), (unsigned)ceil_div(D, 128));
+#define SAPCU_AO(PR, KK) attn_out_kernel<PR, KK><<<grid, 128, 0, st>>>(logits, pos, V, ldv, idx, ldi, kk, Mpts, (int)P, D, sqrt_hd, out)
+  if (precise) {
+    if (kk == 12) SAPCU_AO(true, 12); else if (kk == 18) SAPCU_AO(true, 18); else if (kk == 24) SAPCU_AO(true, 24); else SAPCU_AO(true, 32);
+  } else {
+    if (kk == 12) SAPCU_AO(false, 12); else if (kk == 18) SAPCU_AO(false, 18); else if (kk == 24) SAPCU_AO(false, 24); else SAPCU_AO(false, 32);
+  }
+#undef SAPCU_AO
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

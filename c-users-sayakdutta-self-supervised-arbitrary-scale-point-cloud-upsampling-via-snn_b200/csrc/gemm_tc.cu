@@ -152,34 +152,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// LIF^T on NV independent accumulators of one channel (interleaved for ILP); fast-math flavour.
-template <int NV>
-__device__ __forceinline__ void lif_chain_vec(float (&u)[NV], const NeuronParams& p, int T) {
-  float m[NV], th[NV], rho[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) { m[i] = 0.0f; th[i] = p.th0; rho[i] = 0.0f; }
-  const float c_g = 0.5f / 2.5066282746310002f;        // 0.5 / sqrt(2 pi)
-  const float k_g = -0.5f * 1.4426950408889634f;       // exp(-v^2/2) = 2^(k_g v^2)
-  const float k_s = -10.0f * 1.4426950408889634f;      // exp(-10 v)  = 2^(k_s v)
-#pragma unroll 1
-  for (int t = 0; t < T; ++t) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float x = (rho[i] <= 0.0f) ? u[i] : 0.0f;
-      const float mm = fmaf(m[i] * p.d, 1.0f - rho[i], x);
-      const float vc = fminf(fmaxf(mm - th[i], -10.0f), 10.0f);
-      const float g = exp2f_approx(k_g * vc * vc);
-      const float e = exp2f_approx(k_s * vc);
-      const float s = fmaf(c_g, g, __fdividef(0.5f, 1.0f + e));
-      m[i] = mm * (1.0f - s);
-      rho[i] = fmaf(rho[i], p.r, s);
-      th[i] = fmaf(fmaf(p.a, s, th[i]) - p.th0, 0.95f, p.th0);
-      u[i] = s;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ kernel
+template <int ACT, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -304,43 +278,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const float sc = p.scale ? p.scale[cc] : 1.0f;
       const float sh = p.shift ? p.shift[cc] : 0.0f;
       NeuronParams np{0.9f, 0.01f, 0.5f, 1.0f};
-      if (p.act == ACT_LIF) { np.d = p.nparams[cc]; np.a = p.nparams[p.N + cc]; np.r = p.nparams[2 * p.N + cc]; np.th0 = p.nparams[3 * p.N + cc]; }
+      if (ACT == ACT_LIF) { np.d = p.nparams[cc]; np.a = p.nparams[p.N + cc]; np.r = p.nparams[2 * p.N + cc]; np.th0 = p.nparams[3 * p.N + cc]; }
       if (!(ok = mbar_wait(bar_tfull(a), aph, p.err))) break;
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         const int col0 = half * 64 + ch * 32;
         float v[32];
+        __syncwarp();                                             // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + col0), v);
         const int64_t r0 = n_t * TC_BN + col0;
+        const int nrows = (int)((p.R - r0) < 32 ? (p.R - r0) : 32);     // <= 0 for tiles past the end
+        if (cv && nrows > 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float y = v[j] + bia;
-          y = fmaf(y, sc, sh);
-          if (p.residual && cv && r0 + j < p.R) y += p.residual[(r0 + j) * p.ldr + c];
-          if (p.act == ACT_LEAKY) y = act_leaky(y);
-          else if (p.act == ACT_GELU) y = act_gelu(y);
-          v[j] = y;
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] + bia, sc, sh);
+        if (RES) {
+          const float* rp = p.residual + r0 * p.ldr + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { if (j < nrows) v[j] += *rp; rp += p.ldr; }
         }
-        if (p.act == ACT_LIF) {
+        if (ACT == ACT_LEAKY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = act_leaky(v[j]);
+        }
+        if (ACT == ACT_LIF) {
 #pragma unroll
           for (int j0 = 0; j0 < 32; j0 += 8) {
             float u[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) u[j] = v[j0 + j];
-            lif_chain_vec<8>(u, np, p.T);
+            lif_chain_vec_fast<8>(u, np, p.T);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j0 + j] = u[j];
           }
         }
-        if (p.group == 32) {
-          float mx = -INFINITY;
+        float* yp = p.Y + r0 * p.ldc + c;
+        if (nrows == 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (r0 + j < p.R) mx = fmaxf(mx, v[j]);
-          if (cv && r0 < p.R) p.Y[(r0 >> 5) * p.ldc + c] = mx;
-        } else if (cv) {
+          for (int j = 0; j < 32; ++j) { *yp = v[j]; yp += p.ldc; }
+        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (r0 + j < p.R) p.Y[(r0 + j) * p.ldc + c] = v[j];
+          for (int j = 0; j < 32; ++j) { if (j < nrows) *yp = v[j]; yp += p.ldc; }
+        }
         }
       }
       tc_fence_before();
@@ -402,7 +381,9 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if (g.K % TC_BK != 0 || g.K < TC_BK) return false;
   if (g.R < 1024) return false;                                   // small row counts (decoder heads) stay on the SIMT engine
   if ((g.lda % 4) != 0 || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return false;
-  if (g.group != 0 && g.group != 32) return false;
+  if (g.group != 0) return false;                                  // row-group max stays on the SIMT engine
+  if (g.act == ACT_GELU) return false;                             // decoder MLPs (rows = patches) stay on the SIMT engine
+  if (g.residual && g.act != ACT_NONE) return false;
   if (g.R >= ((int64_t)1 << 31) || g.N > (1 << 20)) return false;
   return true;
 }
@@ -411,7 +392,10 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   SAPCU_REQUIRE(gemm_tc_supported(g, amode), "gemm_tc: unsupported problem");
   static bool attr_done = false;
   if (!attr_done) {
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_LIF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_LEAKY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     attr_done = true;
   }
   int* err = tc_err_flag();
@@ -427,7 +411,12 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, TC_BN); p.err = err;
   const int64_t total = p.n_tiles * p.m_tiles;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mw, mx, p);
+#define SAPCU_TC_LAUNCH(A, RS) gemm_tc_kernel<A, RS><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mw, mx, p)
+  if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, false);
+  else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, false);
+  else if (g.residual) SAPCU_TC_LAUNCH(ACT_NONE, true);
+  else SAPCU_TC_LAUNCH(ACT_NONE, false);
+#undef SAPCU_TC_LAUNCH
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

@@ -106,6 +106,51 @@ __device__ __forceinline__ float lif_chain(float u, const NeuronParams& p, int T
   return s;
 }
 
+// LIF^T on NV independent accumulators of one channel (interleaved for ILP); fast-math flavour.
+template <int NV>
+__device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronParams& p, int T) {
+  float m[NV], th[NV], rho[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { m[i] = 0.0f; th[i] = p.th0; rho[i] = 0.0f; }
+  const float c_g = 0.5f / 2.5066282746310002f;        // 0.5 / sqrt(2 pi)
+  const float k_g = -0.5f * 1.4426950408889634f;       // exp(-v^2/2) = 2^(k_g v^2)
+  const float k_s = -10.0f * 1.4426950408889634f;      // exp(-10 v)  = 2^(k_s v)
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float x = (rho[i] <= 0.0f) ? u[i] : 0.0f;
+      const float mm = fmaf(m[i] * p.d, 1.0f - rho[i], x);
+      const float vc = fminf(fmaxf(mm - th[i], -10.0f), 10.0f);
+      const float g = exp2f_approx(k_g * vc * vc);
+      const float e = exp2f_approx(k_s * vc);
+      const float s = fmaf(c_g, g, __fdividef(0.5f, 1.0f + e));
+      m[i] = mm * (1.0f - s);
+      rho[i] = fmaf(rho[i], p.r, s);
+      th[i] = fmaf(fmaf(p.a, s, th[i]) - p.th0, 0.95f, p.th0);
+      u[i] = s;
+    }
+  }
+}
+
+// PRECISE: the reference-faithful step per element; otherwise the fast-math interleaved form above
+template <int NV, bool PRECISE>
+__device__ __forceinline__ void lif_chain_vec(float (&u)[NV], const NeuronParams& p, int T) {
+  if (PRECISE) {
+    NeuronState st[NV];
+    EifParams e{1.0f, 1.0f};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) st[i] = neuron_init(p);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) u[i] = neuron_step<false, true>(u[i], st[i], p, e);
+    }
+  } else {
+    lif_chain_vec_fast<NV>(u, p, T);
+  }
+}
+
 __device__ __forceinline__ float act_leaky(float x) { return x >= 0.0f ? x : 0.2f * x; }
 __device__ __forceinline__ float act_gelu(float x) {   // exact (erf) GELU, torch default
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
