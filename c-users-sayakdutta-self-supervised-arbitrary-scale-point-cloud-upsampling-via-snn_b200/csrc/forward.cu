@@ -104,7 +104,7 @@ struct G {
   int layer(const Layer& L, const float* X, int64_t lda, int64_t R, float* Y, int64_t ldc, int act,
             const Neuron* nr = nullptr, int T = 0, const float* res = nullptr, int64_t ldr = 0) const {
     GemmArgs g;
-    g.A = X; g.lda = lda; g.R = R; g.K = L.K; g.W = L.W; g.N = L.N; g.bias = L.bias; g.scale = L.scale; g.shift = L.shift;
+    g.A = X; g.lda = lda; g.R = R; g.K = L.K; g.W = L.W; g.Whi = L.Whi; g.Wlo = L.Wlo; g.N = L.N; g.bias = L.bias; g.scale = L.scale; g.shift = L.shift;
     g.act = act; g.T = T; g.nparams = nr ? nr->np : nullptr; g.residual = res; g.ldr = ldr; g.Y = Y; g.ldc = ldc;
     return run(g, A_PLAIN);
   }

@@ -31,6 +31,7 @@ struct GemmArgs {
   const float* Q = nullptr; const float* Kf = nullptr; int64_t ldq = 0;   // A_ATTNIN
   // B operand: W[N,K] row-major
   const float* W = nullptr; int N = 0;
+  const float* Whi = nullptr; const float* Wlo = nullptr;   // optional pre-split tf32 (hi, lo) copies for the tensor-core engine
   // epilogue
   const float* bias = nullptr; const float* scale = nullptr; const float* shift = nullptr;
   int act = ACT_NONE; int T = 0; const float* nparams = nullptr;   // nparams: [4][N] = d,a,r,th0

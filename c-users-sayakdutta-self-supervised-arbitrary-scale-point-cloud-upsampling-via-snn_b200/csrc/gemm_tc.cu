@@ -25,6 +25,7 @@
 // Roofline: tensor pipe (tf32: 2048 MAC/clk/SM, x3 passes); the LIF epilogue is MUFU bound (3 MUFU per
 // element-step, 16/clk/SM) and overlaps the MMA stream.
 #include <cuda.h>
+#include <stdlib.h>
 #include "gemm_tc.h"
 #include "neuron.cuh"
 
@@ -35,9 +36,8 @@ constexpr int TC_BN = 128;        // activation rows per tile (UMMA N)
 constexpr int TC_BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 3;
 constexpr int TC_ACC = 4;         // TMEM accumulator buffers: 4 x 128 columns = all 512
-constexpr int TC_THREADS = 448;
 constexpr int TC_SPLIT_WARP0 = 2, TC_SPLIT_WARPS = 4;
-constexpr int TC_EPI_WARP0 = 6, TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARP0 = 6;                                // epilogue warps: 8 or 16 (template parameter EPI)
 constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB (BM == BN)
 constexpr uint32_t TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // W_hi, W_lo, X_hi, X_lo
 constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -51,6 +51,8 @@ struct TcParams {
   float* Y; int64_t ldc;
   int group;                  // 0 or 32
   int m_tiles; int64_t n_tiles;
+  int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
+  int raw_hi;                 // 1: leave the raw X tile as the hi operand (tensor core ignores the low 13 bits), lo by truncation
   int* err;
 };
 
@@ -153,9 +155,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int ACT, bool RES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+template <int ACT, bool RES, int EPI>
+__global__ void __launch_bounds__((TC_EPI_WARP0 + EPI) * 32, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
+               const __grid_constant__ CUtensorMap map_x, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // 128B swizzle needs 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -175,9 +178,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), TC_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
-    for (int a = 0; a < TC_ACC; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), TC_EPI_WARPS); }
+    for (int a = 0; a < TC_ACC; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), EPI); }
     fence_barrier_init();
     tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_wlo);
     tma_prefetch_desc(&map_x);
   }
   if (warp == 1) {
@@ -199,8 +203,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         for (int kb = 0; kb < nk; ++kb) {
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), 2 * TC_TILE_BYTES);
+          mbar_expect_tx(bar_raw(s), (p.split_w ? 2 : 3) * TC_TILE_BYTES);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, m_t * TC_BM);
+          if (!p.split_w) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, m_t * TC_BM);
           tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, (int)(n_t * TC_BN));
           if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
         }
@@ -243,19 +248,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (!(ok = mbar_wait(bar_raw(s), ph, p.err))) break;
         uint8_t* st = smem_gen + s * TC_STAGE_BYTES;
 #pragma unroll
-        for (int op = 0; op < 2; ++op) {                          // 0: W tile, 1: X tile
+        for (int op = 0; op < 2; ++op) {                          // 0: W tile (only when it arrives raw), 1: X tile
+          if (op == 0 && !p.split_w) continue;
           float4* hi = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES);
           float4* lo = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
+          if (p.raw_hi) {
 #pragma unroll
-          for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (TC_SPLIT_WARPS * 32); ++i) {
-            const int e = tid + i * TC_SPLIT_WARPS * 32;
-            const float4 v = hi[e];
-            float4 h, l;
-            h.x = tf32_rna(v.x); l.x = v.x - h.x;
-            h.y = tf32_rna(v.y); l.y = v.y - h.y;
-            h.z = tf32_rna(v.z); l.z = v.z - h.z;
-            h.w = tf32_rna(v.w); l.w = v.w - h.w;
-            hi[e] = h; lo[e] = l;
+            for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (TC_SPLIT_WARPS * 32); ++i) {
+              const int e = tid + i * TC_SPLIT_WARPS * 32;
+              const float4 v = hi[e];
+              float4 l;
+              l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+              l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+              l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+              l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+              lo[e] = l;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (TC_SPLIT_WARPS * 32); ++i) {
+              const int e = tid + i * TC_SPLIT_WARPS * 32;
+              const float4 v = hi[e];
+              float4 h, l;
+              h.x = tf32_rna(v.x); l.x = v.x - h.x;
+              h.y = tf32_rna(v.y); l.y = v.y - h.y;
+              h.z = tf32_rna(v.z); l.z = v.z - h.z;
+              h.w = tf32_rna(v.w); l.w = v.w - h.w;
+              hi[e] = h; lo[e] = l;
+            }
           }
         }
         fence_proxy_async();                                      // generic-proxy writes -> visible to the tensor core
@@ -266,7 +286,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   } else {
     // ======================================================================== epilogue
     const int q = warp & 3;                                       // TMEM lane quarter this warp may access
-    const int half = (warp - TC_EPI_WARP0) >> 2;                  // which 64 columns of the 128-column tile
+    constexpr int CHUNKS = 16 / EPI;                              // 32-column chunks per warp: 2 (8 warps) or 1 (16 warps)
+    const int part = (warp - TC_EPI_WARP0) >> 2;                  // which slice of the 128-column tile
     int a = 0; uint32_t aph = 0; bool ok = true;
     for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
       const int m_t = (int)(t % p.m_tiles);
@@ -282,8 +303,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if (!(ok = mbar_wait(bar_tfull(a), aph, p.err))) break;
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const int col0 = half * 64 + ch * 32;
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        const int col0 = (part * CHUNKS + ch) * 32;
         float v[32];
         __syncwarp();                                             // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + col0), v);
@@ -392,16 +413,27 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   SAPCU_REQUIRE(gemm_tc_supported(g, amode), "gemm_tc: unsupported problem");
   static bool attr_done = false;
   if (!attr_done) {
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_LIF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_LEAKY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+#define SAPCU_TC_ATTR(A, RS)                                                                                                         \
+  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));  \
+  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES))
+    SAPCU_TC_ATTR(ACT_LIF, false); SAPCU_TC_ATTR(ACT_LEAKY, false); SAPCU_TC_ATTR(ACT_NONE, true); SAPCU_TC_ATTR(ACT_NONE, false);
+#undef SAPCU_TC_ATTR
     attr_done = true;
   }
   int* err = tc_err_flag();
   SAPCU_REQUIRE(err != nullptr, "gemm_tc: cannot allocate the watchdog flag");
-  CUtensorMap mw, mx;
-  int rc = make_map(&mw, g.W, g.N, g.K, g.K, TC_BM);
+  static int epi_warps = 0, raw_hi = 0;
+  if (!epi_warps) {
+    const char* e = getenv("SAPCU_TC_EPI");
+    epi_warps = (e && atoi(e) == 8) ? 8 : 16;
+    const char* r = getenv("SAPCU_TC_RAWHI");
+    raw_hi = (r && atoi(r) == 1) ? 1 : 0;
+  }
+  const bool presplit = g.Whi != nullptr && g.Wlo != nullptr;
+  CUtensorMap mw, mwlo, mx;
+  int rc = make_map(&mw, presplit ? g.Whi : g.W, g.N, g.K, g.K, TC_BM);
+  if (rc) return rc;
+  rc = make_map(&mwlo, presplit ? g.Wlo : g.W, g.N, g.K, g.K, TC_BM);
   if (rc) return rc;
   rc = make_map(&mx, g.A, g.R, g.K, g.lda, TC_BN);
   if (rc) return rc;
@@ -409,9 +441,14 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.group = g.group;
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, TC_BN); p.err = err;
+  p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi;
   const int64_t total = p.n_tiles * p.m_tiles;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-#define SAPCU_TC_LAUNCH(A, RS) gemm_tc_kernel<A, RS><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mw, mx, p)
+#define SAPCU_TC_LAUNCH(A, RS)                                                                                   \
+  do {                                                                                                           \
+    if (epi_warps == 8) gemm_tc_kernel<A, RS, 8><<<grid, (TC_EPI_WARP0 + 8) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p);   \
+    else gemm_tc_kernel<A, RS, 16><<<grid, (TC_EPI_WARP0 + 16) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p);              \
+  } while (0)
   if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, false);
   else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, false);
   else if (g.residual) SAPCU_TC_LAUNCH(ACT_NONE, true);

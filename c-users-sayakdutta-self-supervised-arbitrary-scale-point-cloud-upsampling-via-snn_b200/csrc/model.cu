@@ -36,10 +36,23 @@ struct Builder {
     fixes.push_back({dst, off});
     return off;
   }
+  // weight matrix + its tf32 (hi, lo) split for the tensor-core engine: hi = w rounded to 10 mantissa bits
+  // (round-to-nearest, ties away), lo = w - hi (exact in fp32)
+  void put_w(Layer& L, const float* w, size_t n) {
+    put(w, n, &L.W);
+    std::vector<float> hi(n), lo(n);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t b; memcpy(&b, &w[i], 4);
+      if ((b & 0x7F800000u) != 0x7F800000u) b = (b + 0x1000u) & 0xFFFFE000u;
+      float h; memcpy(&h, &b, 4);
+      hi[i] = h; lo[i] = w[i] - h;
+    }
+    put(hi.data(), n, &L.Whi); put(lo.data(), n, &L.Wlo);
+  }
   // conv/linear `wname`.weight [N,K(,1,1)], optional .bias; optional BatchNorm `bnname`
   void layer(Layer& L, const std::string& wname, const std::string& bnname, int N, int K, bool bias) {
     L.N = N; L.K = K;
-    if (auto* w = get(wname + ".weight", (size_t)N * K)) put(w->data(), w->size(), &L.W);
+    if (auto* w = get(wname + ".weight", (size_t)N * K)) put_w(L, w->data(), w->size());
     if (bias) { if (auto* b = get(wname + ".bias", N)) put(b->data(), N, &L.bias); }
     if (!bnname.empty()) {
       auto* g = get(bnname + ".weight", N); auto* b = get(bnname + ".bias", N);
@@ -73,7 +86,7 @@ struct Builder {
         sh[q * N_each + i] = (*b)[i] - (*mu)[i] * sc[q * N_each + i];
       }
     }
-    put(W.data(), W.size(), &L.W); put(bi.data(), bi.size(), &L.bias);
+    put_w(L, W.data(), W.size()); put(bi.data(), bi.size(), &L.bias);
     put(sc.data(), sc.size(), &L.scale); put(sh.data(), sh.size(), &L.shift);
   }
   static float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -177,7 +190,7 @@ void build_fd(Builder& B) {
           wf[((size_t)cout[b] + o) * cin[b] + i] = wa;
         }
       f.convf[b].N = 2 * cout[b]; f.convf[b].K = cin[b];
-      B.put(wf.data(), wf.size(), &f.convf[b].W);
+      B.put_w(f.convf[b], wf.data(), wf.size());
     }
   }
   B.layer(f.msc, "encoder.multi_scale_conv.0", "encoder.multi_scale_conv.1", f.emb, 960, false);

@@ -10,7 +10,7 @@
 namespace sapcu {
 
 struct Layer {     // 1x1 conv / Linear (+ folded eval BatchNorm):  y = (x W^T + bias) * scale + shift
-  const float* W = nullptr; const float* bias = nullptr; const float* scale = nullptr; const float* shift = nullptr;
+  const float* W = nullptr; const float* Whi = nullptr; const float* Wlo = nullptr; const float* bias = nullptr; const float* scale = nullptr; const float* shift = nullptr;
   int N = 0, K = 0;
 };
 struct Neuron {    // clamped per-channel parameters: np = [4][C] (d, a, r, th0); ep = [2][C] (dT, th_rh) for EIF

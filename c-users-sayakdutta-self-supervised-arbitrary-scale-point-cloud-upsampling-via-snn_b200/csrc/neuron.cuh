@@ -31,6 +31,12 @@ __device__ __forceinline__ float exp2f_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // PRECISE=true : libdevice expf (<= 1 ulp) -- the fp32 parity mode
 // PRECISE=false: ex2.approx based __expf     -- the tensor-core mode
 template <bool PRECISE>
@@ -107,27 +113,43 @@ __device__ __forceinline__ float lif_chain(float u, const NeuronParams& p, int T
 }
 
 // LIF^T on NV independent accumulators of one channel (interleaved for ILP); fast-math flavour.
+// Algebraically identical to neuron_step, re-associated for the FMA pipe (12 FP + 3 MUFU per element-step):
+//   * the soft spike is > 0, so the refractory gate is open at step 0 only: later steps take no input
+//     (the +-10 clamp of the reference only matters below 1e-22 and is dropped here);
+//   * m*d*(1-rho) = md - md*rho ; m*(1-s) = mm - mm*s ; 0.5*sigmoid(10v) = 1/(2 + 2*exp(-10v));
+//   * th' = th0 + (th + a*s - th0)*0.95 = 0.95*th + (0.95*a*s + 0.05*th0).
 template <int NV>
 __device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronParams& p, int T) {
   float m[NV], th[NV], rho[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) { m[i] = 0.0f; th[i] = p.th0; rho[i] = 0.0f; }
   const float c_g = 0.5f / 2.5066282746310002f;        // 0.5 / sqrt(2 pi)
   const float k_g = -0.5f * 1.4426950408889634f;       // exp(-v^2/2) = 2^(k_g v^2)
   const float k_s = -10.0f * 1.4426950408889634f;      // exp(-10 v)  = 2^(k_s v)
+  const float a95 = 0.95f * p.a, c05 = 0.05f * p.th0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {                        // step 0: m = u, th = th0, rho = 0
+    const float mm = u[i];
+    const float v = mm - p.th0;
+    const float g = exp2f_approx((k_g * v) * v);
+    const float e = exp2f_approx(k_s * v);
+    const float s = fmaf(c_g, g, rcp_approx(fmaf(2.0f, e, 2.0f)));
+    m[i] = fmaf(-mm, s, mm);
+    rho[i] = s;
+    th[i] = fmaf(0.95f, p.th0, fmaf(a95, s, c05));
+    u[i] = s;
+  }
 #pragma unroll 1
-  for (int t = 0; t < T; ++t) {
+  for (int t = 1; t < T; ++t) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float x = (rho[i] <= 0.0f) ? u[i] : 0.0f;
-      const float mm = fmaf(m[i] * p.d, 1.0f - rho[i], x);
-      const float vc = fminf(fmaxf(mm - th[i], -10.0f), 10.0f);
-      const float g = exp2f_approx(k_g * vc * vc);
-      const float e = exp2f_approx(k_s * vc);
-      const float s = fmaf(c_g, g, __fdividef(0.5f, 1.0f + e));
-      m[i] = mm * (1.0f - s);
+      const float md = m[i] * p.d;
+      const float mm = fmaf(-md, rho[i], md);
+      const float v = mm - th[i];
+      const float g = exp2f_approx((k_g * v) * v);
+      const float e = exp2f_approx(k_s * v);
+      const float s = fmaf(c_g, g, rcp_approx(fmaf(2.0f, e, 2.0f)));
+      m[i] = fmaf(-mm, s, mm);
       rho[i] = fmaf(rho[i], p.r, s);
-      th[i] = fmaf(fmaf(p.a, s, th[i]) - p.th0, 0.95f, p.th0);
+      th[i] = fmaf(0.95f, th[i], fmaf(a95, s, c05));
       u[i] = s;
     }
   }
