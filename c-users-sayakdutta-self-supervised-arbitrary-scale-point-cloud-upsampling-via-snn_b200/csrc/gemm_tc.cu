@@ -32,15 +32,13 @@
 namespace sapcu {
 
 constexpr int TC_BM = 128;        // output channels per tile (UMMA M)
-constexpr int TC_BN = 128;        // activation rows per tile (UMMA N)
 constexpr int TC_BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
-constexpr int TC_ACC = 4;         // TMEM accumulator buffers: 4 x 128 columns = all 512
+// BN = activation rows per tile (UMMA N) is a template parameter: 128 (3 smem stages, 4 TMEM accumulators)
+// or 256 (2 stages, 2 accumulators; 25 % fewer operand bytes per FLOP)
 constexpr int TC_SPLIT_WARP0 = 2, TC_SPLIT_WARPS = 4;
 constexpr int TC_EPI_WARP0 = 6;                                // epilogue warps: 8 or 16 (template parameter EPI)
-constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB (BM == BN)
-constexpr uint32_t TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // W_hi, W_lo, X_hi, X_lo
-constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB weight tile
+constexpr size_t TC_SMEM_BYTES = (size_t)3 * 4 * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // same for both BN
 constexpr long long TC_WATCHDOG_CLOCKS = 6000000000LL;         // ~3 s at 1.9 GHz
 
 struct TcParams {
@@ -123,15 +121,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t tc_idesc(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -155,10 +155,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int ACT, bool RES, int EPI>
+template <int ACT, bool RES, int EPI, int TC_BN>
 __global__ void __launch_bounds__((TC_EPI_WARP0 + EPI) * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+  constexpr int TC_STAGES = (TC_BN == 128) ? 3 : 2;
+  constexpr int TC_ACC = 512 / TC_BN;
+  constexpr uint32_t X_BYTES = TC_BN * TC_BK * 4;
+  constexpr uint32_t TC_STAGE_BYTES = 2 * TC_TILE_BYTES + 2 * X_BYTES;       // W_hi, W_lo, X_hi, X_lo
+  constexpr uint32_t IDESC = tc_idesc(TC_BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // 128B swizzle needs 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -203,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         for (int kb = 0; kb < nk; ++kb) {
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), (p.split_w ? 2 : 3) * TC_TILE_BYTES);
+          mbar_expect_tx(bar_raw(s), (p.split_w ? 1 : 2) * TC_TILE_BYTES + X_BYTES);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, m_t * TC_BM);
           if (!p.split_w) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, m_t * TC_BM);
           tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, (int)(n_t * TC_BN));
@@ -224,13 +229,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           tc_fence_after();
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
           const uint64_t w_hi = umma_desc_sw128(st), w_lo = umma_desc_sw128(st + TC_TILE_BYTES);
-          const uint64_t x_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+          const uint64_t x_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 2 * TC_TILE_BYTES + X_BYTES);
 #pragma unroll
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
             const uint64_t adv = (uint64_t)(k8 * 2);            // 8 tf32 = 32 B = 2 x 16 B along the swizzled row
-            umma_tf32(tmem_d, w_lo + adv, x_hi + adv, (kb | k8) ? 1u : 0u);
-            umma_tf32(tmem_d, w_hi + adv, x_lo + adv, 1u);
-            umma_tf32(tmem_d, w_hi + adv, x_hi + adv, 1u);
+            umma_tf32(tmem_d, w_lo + adv, x_hi + adv, IDESC, (kb | k8) ? 1u : 0u);
+            umma_tf32(tmem_d, w_hi + adv, x_lo + adv, IDESC, 1u);
+            umma_tf32(tmem_d, w_hi + adv, x_hi + adv, IDESC, 1u);
           }
           umma_commit(bar_empty(s));                             // frees the smem stage when these MMAs retire
           if (kb == nk - 1) umma_commit(bar_tfull(a));           // accumulator complete
@@ -250,11 +255,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll
         for (int op = 0; op < 2; ++op) {                          // 0: W tile (only when it arrives raw), 1: X tile
           if (op == 0 && !p.split_w) continue;
+          const uint32_t bytes = op ? X_BYTES : TC_TILE_BYTES;
           float4* hi = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES + bytes);
+          const int iters = (int)(bytes / 16) / (TC_SPLIT_WARPS * 32);
           if (p.raw_hi) {
 #pragma unroll
-            for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (TC_SPLIT_WARPS * 32); ++i) {
+            for (int i = 0; i < iters; ++i) {
               const int e = tid + i * TC_SPLIT_WARPS * 32;
               const float4 v = hi[e];
               float4 l;
@@ -266,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (TC_SPLIT_WARPS * 32); ++i) {
+            for (int i = 0; i < iters; ++i) {
               const int e = tid + i * TC_SPLIT_WARPS * 32;
               const float4 v = hi[e];
               float4 h, l;
@@ -286,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   } else {
     // ======================================================================== epilogue
     const int q = warp & 3;                                       // TMEM lane quarter this warp may access
-    constexpr int CHUNKS = 16 / EPI;                              // 32-column chunks per warp: 2 (8 warps) or 1 (16 warps)
+    constexpr int CHUNKS = (TC_BN / 32) / (EPI / 4);              // 32-column chunks per warp
     const int part = (warp - TC_EPI_WARP0) >> 2;                  // which slice of the 128-column tile
     int a = 0; uint32_t aph = 0; bool ok = true;
     for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
@@ -413,21 +420,23 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   SAPCU_REQUIRE(gemm_tc_supported(g, amode), "gemm_tc: unsupported problem");
   static bool attr_done = false;
   if (!attr_done) {
-#define SAPCU_TC_ATTR(A, RS)                                                                                                         \
-  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));  \
-  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES))
+#define SAPCU_TC_ATTR1(A, RS, E, B) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES))
+#define SAPCU_TC_ATTR(A, RS) SAPCU_TC_ATTR1(A, RS, 8, 128); SAPCU_TC_ATTR1(A, RS, 8, 256); SAPCU_TC_ATTR1(A, RS, 16, 128); SAPCU_TC_ATTR1(A, RS, 16, 256)
     SAPCU_TC_ATTR(ACT_LIF, false); SAPCU_TC_ATTR(ACT_LEAKY, false); SAPCU_TC_ATTR(ACT_NONE, true); SAPCU_TC_ATTR(ACT_NONE, false);
 #undef SAPCU_TC_ATTR
+#undef SAPCU_TC_ATTR1
     attr_done = true;
   }
   int* err = tc_err_flag();
   SAPCU_REQUIRE(err != nullptr, "gemm_tc: cannot allocate the watchdog flag");
-  static int epi_warps = 0, raw_hi = 0;
+  static int epi_warps = 0, raw_hi = 0, bn = 0;
   if (!epi_warps) {
     const char* e = getenv("SAPCU_TC_EPI");
     epi_warps = (e && atoi(e) == 8) ? 8 : 16;
     const char* r = getenv("SAPCU_TC_RAWHI");
     raw_hi = (r && atoi(r) == 1) ? 1 : 0;
+    const char* b = getenv("SAPCU_TC_BN");
+    bn = (b && atoi(b) == 128) ? 128 : 256;
   }
   const bool presplit = g.Whi != nullptr && g.Wlo != nullptr;
   CUtensorMap mw, mwlo, mx;
@@ -435,25 +444,29 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   if (rc) return rc;
   rc = make_map(&mwlo, presplit ? g.Wlo : g.W, g.N, g.K, g.K, TC_BM);
   if (rc) return rc;
-  rc = make_map(&mx, g.A, g.R, g.K, g.lda, TC_BN);
+  rc = make_map(&mx, g.A, g.R, g.K, g.lda, bn);
   if (rc) return rc;
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.group = g.group;
-  p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, TC_BN); p.err = err;
+  p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, bn); p.err = err;
   p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi;
   const int64_t total = p.n_tiles * p.m_tiles;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-#define SAPCU_TC_LAUNCH(A, RS)                                                                                   \
-  do {                                                                                                           \
-    if (epi_warps == 8) gemm_tc_kernel<A, RS, 8><<<grid, (TC_EPI_WARP0 + 8) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p);   \
-    else gemm_tc_kernel<A, RS, 16><<<grid, (TC_EPI_WARP0 + 16) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p);              \
+#define SAPCU_TC_LAUNCH1(A, RS, E, B) gemm_tc_kernel<A, RS, E, B><<<grid, (TC_EPI_WARP0 + E) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
+#define SAPCU_TC_LAUNCH(A, RS)                                                  \
+  do {                                                                          \
+    if (epi_warps == 8 && bn == 128) SAPCU_TC_LAUNCH1(A, RS, 8, 128);            \
+    else if (epi_warps == 8) SAPCU_TC_LAUNCH1(A, RS, 8, 256);                    \
+    else if (bn == 128) SAPCU_TC_LAUNCH1(A, RS, 16, 128);                        \
+    else SAPCU_TC_LAUNCH1(A, RS, 16, 256);                                       \
   } while (0)
   if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, false);
   else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, false);
   else if (g.residual) SAPCU_TC_LAUNCH(ACT_NONE, true);
   else SAPCU_TC_LAUNCH(ACT_NONE, false);
 #undef SAPCU_TC_LAUNCH
+#undef SAPCU_TC_LAUNCH1
   SAPCU_LAUNCH_CHECK();
   return 0;
 }
