@@ -81,6 +81,83 @@ int launch_edge_gather_max(const float* PQ, int C, const int32_t* idx, int ldi, 
   return 0;
 }
 
+// Fused tail of a factorised EdgeConv block (tensor-core mode): for one patch and a slab of 128 channels,
+//   u[i,c] = max_j LeakyReLU(scale_c (P[nb_ij,c] - Q[i,c]) + shift_c)   (P rows staged in shared memory)
+// followed by the block's T-step EIF/LIF recurrence, every step's spike written into the [point, t, 960] spike
+// tensor.  Replaces edge_gather_max + neuron_unroll and their HBM round trip.
+constexpr int EGU_PTS = 4;     // points processed together per thread (ILP for the recurrence)
+template <bool EIF>
+__global__ void __launch_bounds__(128)
+edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __restrict__ idx, int kk, int Mpts,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ np, const float* __restrict__ ep, int T,
+                          float* __restrict__ U, float* __restrict__ spk, int64_t ldspk_row, int ldo) {
+  extern __shared__ float egs[];
+  float* Ps = egs;                                        // [Mpts][128]
+  int* nbs = reinterpret_cast<int*>(egs + Mpts * 128);    // [Mpts][kk]
+  const int64_t patch0 = (int64_t)blockIdx.x * Mpts;
+  const int c = blockIdx.y * 128 + threadIdx.x;           // C is a multiple of 128
+  for (int m = 0; m < Mpts; ++m) Ps[m * 128 + threadIdx.x] = PQ[(patch0 + m) * 2 * C + c];
+  for (int e = threadIdx.x; e < Mpts * kk; e += 128) nbs[e] = idx[patch0 * kk + e];
+  __syncthreads();
+  const float sc = scale[c], sh = shift[c];
+  const NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
+  EifParams q{1.0f, 1.0f};
+  if (EIF) { q.dT = ep[c]; q.thrh = ep[C + c]; }
+  const FastNeuronK k = fast_neuron_k(p, q);
+  for (int i0 = 0; i0 < Mpts; i0 += EGU_PTS) {
+    float u[EGU_PTS], m[EGU_PTS], th[EGU_PTS], rho[EGU_PTS];
+#pragma unroll
+    for (int a = 0; a < EGU_PTS; ++a) {
+      const int i = min(i0 + a, Mpts - 1);
+      const float qv = PQ[(patch0 + i) * 2 * C + C + c];
+      float mx = -INFINITY;
+      for (int j = 0; j < kk; ++j) mx = fmaxf(mx, Ps[nbs[i * kk + j] * 128 + threadIdx.x]);
+      // LeakyReLU(scale*(P-Q)+shift) is monotone in P for scale >= 0 and antitone otherwise: take max or min of P
+      if (sc < 0.0f) {
+        float mn = INFINITY;
+        for (int j = 0; j < kk; ++j) mn = fminf(mn, Ps[nbs[i * kk + j] * 128 + threadIdx.x]);
+        mx = mn;
+      }
+      u[a] = act_leaky(fmaf(mx - qv, sc, sh));
+      if (i0 + a < Mpts) U[(patch0 + i) * C + c] = u[a];
+    }
+    float s[EGU_PTS];
+#pragma unroll
+    for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, true>(u[a], m[a], th[a], rho[a], k);
+#pragma unroll
+    for (int a = 0; a < EGU_PTS; ++a)
+      if (i0 + a < Mpts) spk[(patch0 + i0 + a) * ldspk_row + c] = s[a];
+    for (int t = 1; t < T; ++t) {
+#pragma unroll
+      for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, false>(0.0f, m[a], th[a], rho[a], k);
+#pragma unroll
+      for (int a = 0; a < EGU_PTS; ++a)
+        if (i0 + a < Mpts) spk[(patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c] = s[a];
+    }
+  }
+}
+
+int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* idx, int kk, int Mpts, int64_t S,
+                              const float* scale, const float* shift, const float* np, const float* ep, int T, float* U,
+                              float* spk, int64_t ldspk_row, int ldo, cudaStream_t st) {
+  SAPCU_REQUIRE(C % 128 == 0, "edge_gather_unroll: C=%d must be a multiple of 128", C);
+  if (S == 0) return 0;
+  const size_t smem = sizeof(float) * ((size_t)Mpts * 128 + (size_t)Mpts * kk);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_gather_unroll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_gather_unroll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_done = true;
+  }
+  SAPCU_REQUIRE(smem <= 160 * 1024, "edge_gather_unroll: patch too large for shared memory");
+  dim3 grid((unsigned)S, (unsigned)(C / 128));
+  if (eif) edge_gather_unroll_kernel<true><<<grid, 128, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
+  else     edge_gather_unroll_kernel<false><<<grid, 128, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
 // out[row*(T*ldo) + t*ldo + c] = spike at step t of channel c for input U[row*ldu + c]   (all_steps)
 // out[row*ldo + c]             = spike at step T-1                                        (!all_steps)
 template <bool EIF, bool PRECISE>

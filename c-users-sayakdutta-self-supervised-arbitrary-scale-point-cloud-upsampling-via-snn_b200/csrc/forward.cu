@@ -189,7 +189,9 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
       // factorised EdgeConv: one per-POINT contraction [P, Cin] x [2 Cout, Cin]^T, then gather / BN / LeakyReLU / max_k
       Layer L = f.convf[b];
       SAPCU_TRY(g.layer(L, p.SPK + off_in[b], ldspk, P, p.PQ, 2 * cout[b], ACT_NONE));
-      SAPCU_TRY(launch_edge_gather_max(p.PQ, cout[b], idx, p.k, p.k, M, P, f.conv[b].scale, f.conv[b].shift, U[b], st));
+      SAPCU_TRY(launch_edge_gather_unroll(b == 0, p.PQ, cout[b], idx, p.k, M, s, f.conv[b].scale, f.conv[b].shift,
+                                          f.blk[b + 1].np, f.blk[b + 1].ep, T, U[b], p.SPK + off_out[b], ldspk, 960, st));
+      continue;
     } else {
       GemmArgs a;
       a.R = P * p.k; a.K = 2 * cin[b]; a.idx = idx; a.ldi = p.k; a.kk = p.k; a.Mpts = M;

@@ -50,6 +50,7 @@ struct TcParams {
   int group;                  // 0 or 32
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
+  int l2_prefetch;            // k-blocks of look-ahead for the activation L2 prefetch (0 = off)
   int raw_hi;                 // 1: leave the raw X tile as the hi operand (tensor core ignores the low 13 bits), lo by truncation
   int* err;
 };
@@ -95,6 +96,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -206,6 +211,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const int m_t = (int)(t % p.m_tiles);
         const int64_t n_t = t / p.m_tiles;
         for (int kb = 0; kb < nk; ++kb) {
+          if (p.l2_prefetch > 0) {
+            // pull the activation tile `l2_prefetch` k-blocks ahead (possibly in this CTA's next tile) into L2
+            int kp = kb + p.l2_prefetch; int64_t tp = t;
+            if (kp >= nk) { kp -= nk; tp += gridDim.x; }
+            if (kp < nk && tp < total_tiles) tma_prefetch_l2_2d(&map_x, kp * TC_BK, (int)((tp / p.m_tiles) * TC_BN));
+          }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
           mbar_expect_tx(bar_raw(s), (p.split_w ? 1 : 2) * TC_TILE_BYTES + X_BYTES);
@@ -429,7 +440,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   }
   int* err = tc_err_flag();
   SAPCU_REQUIRE(err != nullptr, "gemm_tc: cannot allocate the watchdog flag");
-  static int epi_warps = 0, raw_hi = 0, bn = 0;
+  static int epi_warps = 0, raw_hi = 0, bn = 0, l2pf = 0;
   if (!epi_warps) {
     const char* e = getenv("SAPCU_TC_EPI");
     epi_warps = (e && atoi(e) == 8) ? 8 : 16;
@@ -437,6 +448,8 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
     raw_hi = (r && atoi(r) == 1) ? 1 : 0;
     const char* b = getenv("SAPCU_TC_BN");
     bn = (b && atoi(b) == 128) ? 128 : 256;
+    const char* f = getenv("SAPCU_TC_L2PF");
+    l2pf = f ? atoi(f) : 4;
   }
   const bool presplit = g.Whi != nullptr && g.Wlo != nullptr;
   CUtensorMap mw, mwlo, mx;
@@ -450,7 +463,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.group = g.group;
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, bn); p.err = err;
-  p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi;
+  p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf;
   const int64_t total = p.n_tiles * p.m_tiles;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
 #define SAPCU_TC_LAUNCH1(A, RS, E, B) gemm_tc_kernel<A, RS, E, B><<<grid, (TC_EPI_WARP0 + E) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p)

@@ -34,6 +34,9 @@ int launch_fd_block0(const float* xyz, const int32_t* idx, int ldi, int Mpts, in
                      cudaStream_t st);
 int launch_edge_gather_max(const float* PQ, int C, const int32_t* idx, int ldi, int kk, int Mpts, int64_t P,
                            const float* scale, const float* shift, float* out, cudaStream_t st);
+int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* idx, int kk, int Mpts, int64_t S,
+                              const float* scale, const float* shift, const float* np, const float* ep, int T, float* U,
+                              float* spk, int64_t ldspk_row, int ldo, cudaStream_t st);
 int launch_neuron_unroll(bool eif, bool precise, const float* U, int64_t ldu, int64_t rows, int C, int T,
                          const float* np, const float* ep, int all_steps, float* out, int64_t ldo, cudaStream_t st);
 int launch_temporal_lif(bool precise, const float* pool, int64_t S, int Tt, int C, const float* wsm, const float* np,

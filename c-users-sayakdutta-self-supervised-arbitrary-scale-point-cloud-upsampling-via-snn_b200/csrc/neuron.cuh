@@ -155,6 +155,38 @@ __device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronP
   }
 }
 
+// One re-associated step (fast-math flavour of neuron_step) for kernels that need every step's spike.
+// FIRST: the step from the zero state (m = 0, th = th0, rho = 0) with input u; later steps take no input
+// (closed refractory gate).  Derived constants are passed in `k`.
+struct FastNeuronK { float d, r, a95, c05, th0, dT, thrh, inv_dT; };
+__device__ __forceinline__ FastNeuronK fast_neuron_k(const NeuronParams& p, const EifParams& e) {
+  FastNeuronK k;
+  k.d = p.d; k.r = p.r; k.a95 = 0.95f * p.a; k.c05 = 0.05f * p.th0; k.th0 = p.th0;
+  k.dT = e.dT; k.thrh = e.thrh; k.inv_dT = 1.0f / (e.dT + 1e-6f);
+  return k;
+}
+template <bool EIF, bool FIRST>
+__device__ __forceinline__ float neuron_step_fast(float u, float& m, float& th, float& rho, const FastNeuronK& k) {
+  const float c_g = 0.5f / 2.5066282746310002f, k_g = -0.5f * 1.4426950408889634f, k_s = -10.0f * 1.4426950408889634f;
+  float mm;
+  if (FIRST) {
+    mm = u;
+    if (EIF) mm += k.dT * exp2f_approx(fminf(fmaxf(-k.thrh * k.inv_dT, -5.0f), 5.0f) * 1.4426950408889634f);
+  } else {
+    const float md = m * k.d;
+    mm = fmaf(-md, rho, md);
+    if (EIF) mm += k.dT * exp2f_approx(fminf(fmaxf((m - k.thrh) * k.inv_dT, -5.0f), 5.0f) * 1.4426950408889634f);
+  }
+  const float v = mm - (FIRST ? k.th0 : th);
+  const float g = exp2f_approx((k_g * v) * v);
+  const float e = exp2f_approx(k_s * v);
+  const float s = fmaf(c_g, g, rcp_approx(fmaf(2.0f, e, 2.0f)));
+  m = fmaf(-mm, s, mm);
+  rho = FIRST ? s : fmaf(rho, k.r, s);
+  th = fmaf(0.95f, FIRST ? k.th0 : th, fmaf(k.a95, s, k.c05));
+  return s;
+}
+
 // PRECISE: the reference-faithful step per element; otherwise the fast-math interleaved form above
 template <int NV, bool PRECISE>
 __device__ __forceinline__ void lif_chain_vec(float (&u)[NV], const NeuronParams& p, int T) {
