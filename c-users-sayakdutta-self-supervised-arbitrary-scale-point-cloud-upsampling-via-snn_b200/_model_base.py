@@ -100,7 +100,7 @@ class NativeModel(nn.Module):
     def tap(self, name, S, M, dtype=torch.float32):
         """Debug view of a named intermediate of the last forward (tests only)."""
         off, rows, cols, ld = (ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64())
-        N.check(N.lib().sapcu_model_tap(self._ensure_handle(), name.encode(), S, M, ctypes.byref(off), ctypes.byref(rows),
+        N.check(N.lib().sapcu_model_tap(self._ensure_handle(), name.encode(), S, M, self.mode, ctypes.byref(off), ctypes.byref(rows),
                                         ctypes.byref(cols), ctypes.byref(ld)), "model_tap(%s)" % name)
         flat = self._ws.view(torch.float32) if dtype == torch.float32 else self._ws.view(torch.int32)
         return flat[off.value: off.value + rows.value * ld.value].view(rows.value, ld.value)[:, :cols.value]

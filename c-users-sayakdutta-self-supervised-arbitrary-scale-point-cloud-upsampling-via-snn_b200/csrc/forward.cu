@@ -129,12 +129,32 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
     SAPCU_TRY(launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias,
                                     k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, p.E1, st));
-    SAPCU_TRY(g.layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
     if (mode == SAPCU_MODE_TC) {
-      // the TMA-fed tensor-core engine reads plain row-major operands: materialise q_i - k_j + pos_ij (E1 is free)
-      SAPCU_TRY(launch_attn_in(p.QKV, p.QKV + D, 3 * D, p.E2, p.idx, p.kmax, kk, M, E, D, p.E1, st));
-      SAPCU_TRY(g.layer(k.fc_gamma, p.E1, D, E, p.E3, D, ACT_LIF, &k.snn_gamma, 4));
-    } else {
+      // the TMA-fed tensor-core engine reads plain row-major operands: the fc_delta2 epilogue also emits the attention
+      // input q_i - k_j + pos_ij (into E3), fc_gamma then maps E3 -> E1 and fc_gamma2 E1 -> E3
+      GemmArgs a;
+      const Layer& L = k.fc_delta2;
+      a.A = p.E1; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
+      a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_delta2.np;
+      a.Y = p.E2; a.ldc = D; a.Y2 = p.E3;
+      a.Q = p.QKV; a.Kf = p.QKV + D; a.ldq = 3 * D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
+      if (gemm_tc_supported(a, A_PLAIN)) {
+        SAPCU_TRY(g.run(a, A_PLAIN));
+      } else {
+        a.Y2 = nullptr;
+        SAPCU_TRY(g.run(a, A_PLAIN));
+        SAPCU_TRY(launch_attn_in(p.QKV, p.QKV + D, 3 * D, p.E2, p.idx, p.kmax, kk, M, E, D, p.E3, st));
+      }
+      SAPCU_TRY(g.layer(k.fc_gamma, p.E3, D, E, p.E1, D, ACT_LIF, &k.snn_gamma, 4));
+      SAPCU_TRY(g.layer(k.fc_gamma2, p.E1, D, E, p.E3, D, ACT_NONE));
+      const float sq = sqrtf((float)(D / f.heads));
+      SAPCU_TRY(launch_attn_out(precise, p.E3, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, sq, p.RES, st));
+      SAPCU_TRY(g.layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
+      SAPCU_TRY(g.layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
+      continue;
+    }
+    SAPCU_TRY(g.layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
+    {
       GemmArgs a;
       a.A = p.E2; a.lda = D; a.R = E; a.K = D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
       a.Q = p.QKV; a.Kf = p.QKV + D; a.ldq = 3 * D;
@@ -287,8 +307,8 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
   return 0;
 }
 
-int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, int64_t* off_floats, int64_t* rows,
-                    int64_t* cols, int64_t* ld) {
+int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, int mode, int64_t* off_floats,
+                    int64_t* rows, int64_t* cols, int64_t* ld) {
   SAPCU_REQUIRE(m && name && off_floats && rows && cols && ld && S >= 1 && M >= 1, "model_tap: bad argument");
   const std::string n(name);
   const int64_t P = S * M;
@@ -304,8 +324,9 @@ int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, in
     if (n == "trans3.snn1") return set(p.X, P, D, D);
     if (n == "trans3.snn_qkv") return set(p.QKV, P, 3 * D, 3 * D);
     if (n == "trans3.snn_delta2") return set(p.E2, E, D, D);
-    if (n == "trans3.snn_gamma") return set(p.E3, E, D, D);
-    if (n == "trans3.logits") return set(p.E1, E, D, D);
+    // tensor-core mode rotates the edge buffers (the fc_delta2 epilogue emits the attention input into E3)
+    if (n == "trans3.snn_gamma") return set(mode == SAPCU_MODE_TC ? p.E1 : p.E3, E, D, D);
+    if (n == "trans3.logits") return set(mode == SAPCU_MODE_TC ? p.E3 : p.E1, E, D, D);
     if (n == "trans3.res") return set(p.RES, P, D, D);
     if (n == "snn_final") return set(p.G, P, m->fn.emb, m->fn.emb);
     if (n == "gmax") return set(p.GM, S, m->fn.emb, m->fn.emb);

@@ -37,6 +37,7 @@ struct GemmArgs {
   int act = ACT_NONE; int T = 0; const float* nparams = nullptr;   // nparams: [4][N] = d,a,r,th0
   const float* residual = nullptr; int64_t ldr = 0;
   float* Y = nullptr; int64_t ldc = 0;
+  float* Y2 = nullptr;   // tensor-core engine only: second output (attention input q_i - k_j + Y), see gemm_tc.cu
   int group = 0;   // 0 or 32
 };
 

@@ -47,6 +47,8 @@ struct TcParams {
   int act, T; const float* nparams;
   const float* residual; int64_t ldr;
   float* Y; int64_t ldc;
+  // EXTRA == 2 (fn fc_delta2): second output Y2[e,c] = (aq[pt,c] - ak[nb,c]) + Y[e,c], the attention input q_i - k_j + pos_ij
+  const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts; float* Y2;
   int group;                  // 0 or 32
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
@@ -160,7 +162,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int ACT, bool RES, int EPI, int TC_BN>
+template <int ACT, int EXTRA, int EPI, int TC_BN>
 __global__ void __launch_bounds__((TC_EPI_WARP0 + EPI) * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                const __grid_constant__ CUtensorMap map_x, const TcParams p) {
@@ -328,10 +330,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + col0), v);
         const int64_t r0 = n_t * TC_BN + col0;
         const int nrows = (int)((p.R - r0) < 32 ? (p.R - r0) : 32);     // <= 0 for tiles past the end
+        int64_t my_pt = 0, my_nb = 0;                                   // EXTRA == 2: lane j resolves edge row r0 + j
+        if (EXTRA == 2 && lane < nrows) {
+          const int64_t e = r0 + lane;
+          my_pt = e / p.kk;
+          my_nb = (my_pt / p.Mpts) * p.Mpts + p.idx[my_pt * p.ldi + (e - my_pt * p.kk)];
+        }
         if (cv && nrows > 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] + bia, sc, sh);
-        if (RES) {
+        if (EXTRA == 1) {
           const float* rp = p.residual + r0 * p.ldr + c;
 #pragma unroll
           for (int j = 0; j < 32; ++j) { if (j < nrows) v[j] += *rp; rp += p.ldr; }
@@ -349,6 +357,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             lif_chain_vec_fast<8>(u, np, p.T);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j0 + j] = u[j];
+          }
+        }
+        if (EXTRA == 2) {                                                // N % 32 == 0 here: cv is warp-uniform
+          float* y2 = p.Y2 + r0 * p.ldc + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t ptj = __shfl_sync(0xffffffffu, my_pt, j), nbj = __shfl_sync(0xffffffffu, my_nb, j);
+            if (j < nrows) *y2 = (p.aq[ptj * p.ldq + c] - p.ak[nbj * p.ldq + c]) + v[j];
+            y2 += p.ldc;
           }
         }
         float* yp = p.Y + r0 * p.ldc + c;
@@ -423,6 +440,7 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if (g.group != 0) return false;                                  // row-group max stays on the SIMT engine
   if (g.act == ACT_GELU) return false;                             // decoder MLPs (rows = patches) stay on the SIMT engine
   if (g.residual && g.act != ACT_NONE) return false;
+  if (g.Y2 && (g.act != ACT_LIF || (g.N % 32) != 0 || !g.Q || !g.Kf || !g.idx)) return false;
   if (g.R >= ((int64_t)1 << 31) || g.N > (1 << 20)) return false;
   return true;
 }
@@ -433,7 +451,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   if (!attr_done) {
 #define SAPCU_TC_ATTR1(A, RS, E, B) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES))
 #define SAPCU_TC_ATTR(A, RS) SAPCU_TC_ATTR1(A, RS, 8, 128); SAPCU_TC_ATTR1(A, RS, 8, 256); SAPCU_TC_ATTR1(A, RS, 16, 128); SAPCU_TC_ATTR1(A, RS, 16, 256)
-    SAPCU_TC_ATTR(ACT_LIF, false); SAPCU_TC_ATTR(ACT_LEAKY, false); SAPCU_TC_ATTR(ACT_NONE, true); SAPCU_TC_ATTR(ACT_NONE, false);
+    SAPCU_TC_ATTR(ACT_LIF, 0); SAPCU_TC_ATTR(ACT_LIF, 2); SAPCU_TC_ATTR(ACT_LEAKY, 0); SAPCU_TC_ATTR(ACT_NONE, 1); SAPCU_TC_ATTR(ACT_NONE, 0);
 #undef SAPCU_TC_ATTR
 #undef SAPCU_TC_ATTR1
     attr_done = true;
@@ -445,7 +463,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
     const char* e = getenv("SAPCU_TC_EPI");
     epi_warps = (e && atoi(e) == 8) ? 8 : 16;
     const char* r = getenv("SAPCU_TC_RAWHI");
-    raw_hi = (r && atoi(r) == 1) ? 1 : 0;
+    raw_hi = (r && atoi(r) == 0) ? 0 : 1;
     const char* b = getenv("SAPCU_TC_BN");
     bn = (b && atoi(b) == 128) ? 128 : 256;
     const char* f = getenv("SAPCU_TC_L2PF");
@@ -462,6 +480,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.group = g.group;
+  p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts; p.Y2 = g.Y2;
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, bn); p.err = err;
   p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf;
   const int64_t total = p.n_tiles * p.m_tiles;
@@ -474,10 +493,11 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
     else if (bn == 128) SAPCU_TC_LAUNCH1(A, RS, 16, 128);                        \
     else SAPCU_TC_LAUNCH1(A, RS, 16, 256);                                       \
   } while (0)
-  if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, false);
-  else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, false);
-  else if (g.residual) SAPCU_TC_LAUNCH(ACT_NONE, true);
-  else SAPCU_TC_LAUNCH(ACT_NONE, false);
+  if (g.act == ACT_LIF && g.Y2) SAPCU_TC_LAUNCH(ACT_LIF, 2);
+  else if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, 0);
+  else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, 0);
+  else if (g.residual) SAPCU_TC_LAUNCH(ACT_NONE, 1);
+  else SAPCU_TC_LAUNCH(ACT_NONE, 0);
 #undef SAPCU_TC_LAUNCH
 #undef SAPCU_TC_LAUNCH1
   SAPCU_LAUNCH_CHECK();

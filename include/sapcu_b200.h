@@ -111,9 +111,9 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
                      void* d_ws, size_t ws_bytes, int mode, void* stream);
 
 /* Debug taps for the parity tests: location of a named intermediate inside the workspace of the
- * LAST chunk a forward call processed (valid when S fits one chunk).  Element (row r, col c) is at
+ * LAST chunk a forward call of the given `mode` processed (valid when S fits one chunk).  Element (row r, col c) is at
  * float offset  off + r*ld + c.  Returns SAPCU_EINVAL for an unknown name. */
-int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M,
+int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, int mode,
                     int64_t* off_floats, int64_t* rows, int64_t* cols, int64_t* ld);
 
 /* ------------------------------------------------------------------------------------
