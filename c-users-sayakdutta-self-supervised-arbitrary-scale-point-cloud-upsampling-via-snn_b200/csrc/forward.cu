@@ -7,6 +7,7 @@
 //  * fd's time loop (fd/snn_coder.py:408-480) feeds each block's conv output through a gate that is
 //    closed for t >= 1, so the graph convolutions and feature-space kNN are evaluated once (t = 0) and
 //    only the neuron recurrences + the 960 -> emb contraction + max-pool run for all T steps.
+#include <stdlib.h>
 #include "../../include/sapcu_b200.h"
 #include "gemm_simt.cuh"
 #include "gemm_tc.h"
@@ -95,7 +96,8 @@ struct G {
     int slot = -1;
     const bool prof = prof_begin(st, 2.0 * (double)g.R * g.K * g.N, &slot);
     int rc;
-    if (mode == SAPCU_MODE_TC && gemm_tc_supported(g, amode)) rc = launch_gemm_tc(g, amode, st);
+    if (mode == SAPCU_MODE_TC && gemm_tc2_supported(g, amode)) rc = launch_gemm_tc2(g, st);
+    else if (mode == SAPCU_MODE_TC && gemm_tc_supported(g, amode)) rc = launch_gemm_tc(g, amode, st);
     else rc = launch_gemm_simt(g, amode, mode == SAPCU_MODE_FP32, st);
     if (prof) prof_end(st, slot);
     return rc;
@@ -138,7 +140,8 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
       a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_delta2.np;
       a.Y = p.E2; a.ldc = D; a.Y2 = p.E3;
       a.Q = p.QKV; a.Kf = p.QKV + D; a.ldq = 3 * D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
-      if (gemm_tc_supported(a, A_PLAIN)) {
+      static const bool fuse_attn_in = getenv("SAPCU_TC_FUSE_ATTNIN") && atoi(getenv("SAPCU_TC_FUSE_ATTNIN")) == 1;
+      if (fuse_attn_in && gemm_tc_supported(a, A_PLAIN)) {
         SAPCU_TRY(g.run(a, A_PLAIN));
       } else {
         a.Y2 = nullptr;

@@ -28,138 +28,16 @@
 #include <stdlib.h>
 #include "gemm_tc.h"
 #include "neuron.cuh"
+#include "tc_ptx.cuh"
 
 namespace sapcu {
 
-constexpr int TC_BM = 128;        // output channels per tile (UMMA M)
-constexpr int TC_BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 // BN = activation rows per tile (UMMA N) is a template parameter: 128 (3 smem stages, 4 TMEM accumulators)
 // or 256 (2 stages, 2 accumulators; 25 % fewer operand bytes per FLOP)
 constexpr int TC_SPLIT_WARP0 = 2, TC_SPLIT_WARPS = 4;
 constexpr int TC_EPI_WARP0 = 6;                                // epilogue warps: 8 or 16 (template parameter EPI)
-constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB weight tile
 constexpr size_t TC_SMEM_BYTES = (size_t)3 * 4 * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // same for both BN
-constexpr long long TC_WATCHDOG_CLOCKS = 6000000000LL;         // ~3 s at 1.9 GHz
 
-struct TcParams {
-  int64_t R; int N, K;
-  const float* bias; const float* scale; const float* shift;
-  int act, T; const float* nparams;
-  const float* residual; int64_t ldr;
-  float* Y; int64_t ldc;
-  // EXTRA == 2 (fn fc_delta2): second output Y2[e,c] = (aq[pt,c] - ak[nb,c]) + Y[e,c], the attention input q_i - k_j + pos_ij
-  const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts; float* Y2;
-  int group;                  // 0 or 32
-  int m_tiles; int64_t n_tiles;
-  int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
-  int l2_prefetch;            // k-blocks of look-ahead for the activation L2 prefetch (0 = off)
-  int raw_hi;                 // 1: leave the raw X tile as the hi operand (tensor core ignores the low 13 bits), lo by truncation
-  int* err;
-};
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-// returns false after the watchdog fired (here or in another role)
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  int spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 1023) == 0) {
-      if (*reinterpret_cast<volatile int*>(err) != 0) return false;
-      if (clock64() - t0 > TC_WATCHDOG_CLOCKS) { atomicExch(err, 1); return false; }
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// round-to-nearest fp32 -> tf32 (low 13 mantissa bits cleared): an unbiased hi part, |lo| <= 2^-11 |x|
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// K-major, 128-byte swizzled operand tile (rows of 32 fp32 = 128 B, 8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address        bits [0,14)
-  d |= (uint64_t)1 << 16;                        // leading byte offset  bits [16,30) (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset   bits [32,46)
-  d |= (uint64_t)1 << 46;                        // descriptor version 1 (sm_100)
-  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = BN
-__host__ __device__ constexpr uint32_t tc_idesc(int bn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ------------------------------------------------------------------------------------------------ kernel
 template <int ACT, int EXTRA, int EPI, int TC_BN>
@@ -330,11 +208,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + col0), v);
         const int64_t r0 = n_t * TC_BN + col0;
         const int nrows = (int)((p.R - r0) < 32 ? (p.R - r0) : 32);     // <= 0 for tiles past the end
-        int64_t my_pt = 0, my_nb = 0;                                   // EXTRA == 2: lane j resolves edge row r0 + j
-        if (EXTRA == 2 && lane < nrows) {
-          const int64_t e = r0 + lane;
-          my_pt = e / p.kk;
-          my_nb = (my_pt / p.Mpts) * p.Mpts + p.idx[my_pt * p.ldi + (e - my_pt * p.kk)];
+        int my_qo = 0, my_ko = 0;                                       // EXTRA == 2: lane j resolves edge row r0 + j
+        if (EXTRA == 2 && lane < nrows) {                               // (element offsets fit 32 bits: checked on the host)
+          const int e = (int)(r0 + lane);
+          const int pt = e / p.kk;
+          const int nb = (pt / p.Mpts) * p.Mpts + p.idx[(int64_t)pt * p.ldi + (e - pt * p.kk)];
+          my_qo = pt * (int)p.ldq; my_ko = nb * (int)p.ldq;
         }
         if (cv && nrows > 0) {
 #pragma unroll
@@ -363,8 +242,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           float* y2 = p.Y2 + r0 * p.ldc + c;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int64_t ptj = __shfl_sync(0xffffffffu, my_pt, j), nbj = __shfl_sync(0xffffffffu, my_nb, j);
-            if (j < nrows) *y2 = (p.aq[ptj * p.ldq + c] - p.ak[nbj * p.ldq + c]) + v[j];
+            const int qo = __shfl_sync(0xffffffffu, my_qo, j), ko = __shfl_sync(0xffffffffu, my_ko, j);
+            if (j < nrows) *y2 = (p.aq[qo + c] - p.ak[ko + c]) + v[j];
             y2 += p.ldc;
           }
         }
@@ -409,7 +288,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D fp32 row-major [rows, K] (row stride ld floats) -> boxes of [box_rows, 32] with 128B swizzle, OOB rows/cols read as 0
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows) {
+int tc_make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled entry point unavailable"); return -2; }
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -423,7 +302,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int6
   return 0;
 }
 
-static int* tc_err_flag() {       // one device word per process, zero-initialised
+int* tc_err_flag() {       // one device word per process, zero-initialised
   static int* flag = nullptr;
   if (!flag) {
     if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
@@ -441,6 +320,7 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if (g.act == ACT_GELU) return false;                             // decoder MLPs (rows = patches) stay on the SIMT engine
   if (g.residual && g.act != ACT_NONE) return false;
   if (g.Y2 && (g.act != ACT_LIF || (g.N % 32) != 0 || !g.Q || !g.Kf || !g.idx)) return false;
+  if (g.Y2 && (g.R >= ((int64_t)1 << 31) || (g.R / (g.kk > 0 ? g.kk : 1) + 1) * g.ldq >= ((int64_t)1 << 31))) return false;
   if (g.R >= ((int64_t)1 << 31) || g.N > (1 << 20)) return false;
   return true;
 }
@@ -471,11 +351,11 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   }
   const bool presplit = g.Whi != nullptr && g.Wlo != nullptr;
   CUtensorMap mw, mwlo, mx;
-  int rc = make_map(&mw, presplit ? g.Whi : g.W, g.N, g.K, g.K, TC_BM);
+  int rc = tc_make_map(&mw, presplit ? g.Whi : g.W, g.N, g.K, g.K, TC_BM);
   if (rc) return rc;
-  rc = make_map(&mwlo, presplit ? g.Wlo : g.W, g.N, g.K, g.K, TC_BM);
+  rc = tc_make_map(&mwlo, presplit ? g.Wlo : g.W, g.N, g.K, g.K, TC_BM);
   if (rc) return rc;
-  rc = make_map(&mx, g.A, g.R, g.K, g.lda, bn);
+  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, bn);
   if (rc) return rc;
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;

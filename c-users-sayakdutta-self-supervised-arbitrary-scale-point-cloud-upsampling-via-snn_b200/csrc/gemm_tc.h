@@ -9,4 +9,7 @@ bool gemm_tc_supported(const GemmArgs& g, int amode);
 int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st);
 // pipeline watchdog status of every launch_gemm_tc since the last check (0 = fine); synchronises the stream
 int gemm_tc_check(cudaStream_t st);
+// 2-CTA (cta_group::2) variant for N % 256 == 0 problems (gemm_tc2.cu)
+bool gemm_tc2_supported(const GemmArgs& g, int amode);
+int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st);
 }  // namespace sapcu

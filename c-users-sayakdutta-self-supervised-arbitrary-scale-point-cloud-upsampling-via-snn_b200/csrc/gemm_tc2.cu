@@ -1,0 +1,305 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 3xTF32 GEMM engine, used when N (output channels) % 256 == 0.
+//
+// A CTA pair (thread-block cluster of 2, same TPC) computes a 256-channel x 256-row tile with ONE
+// tcgen05.mma.cta_group::2 stream issued by the leader CTA: each CTA stages only ITS 128 weight rows and ITS
+// 128 activation rows (64 KiB per stage instead of 96 KiB for the same per-SM MMA work), so the shared-memory
+// operand traffic per FLOP -- the limiter of the 1-CTA kernel (ncu: tensor pipe 57 % active, smem-bound) -- is
+// halved.  Accumulators: each CTA's TMEM holds its 128 channels x 256 rows (2 buffers of 256 columns).
+//
+// Cross-CTA protocol (all waits are watchdogged):
+//   raw[s]    local   TMA bytes of this CTA landed                       -> this CTA's splitter
+//   split[s]  LEADER  256 arrivals (128 splitter threads of each CTA; the follower arrives remotely via mapa)
+//   empty[s]  both    tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11) -> each CTA's TMA producer
+//   tfull[a]  both    multicast commit after the last k-block           -> each CTA's epilogue
+//   tempty[a] LEADER  2 x EPI arrivals (epilogue warps of both CTAs)    -> leader's MMA issuer
+// Roles per CTA: warp 0 TMA, warp 1 MMA (leader only; both CTAs allocate TMEM with cta_group::2), warps 2..5
+// splitter (lo = x - trunc_tf32(x); the raw tile is the hi operand), warps 6..21 epilogue (same code as gemm_tc.cu).
+#include <cuda.h>
+#include <stdlib.h>
+#include "gemm_tc.h"
+#include "neuron.cuh"
+#include "tc_ptx.cuh"
+
+namespace sapcu {
+
+constexpr int T2_STAGES = 3;
+constexpr int T2_ACC = 2;                       // 2 x 256 TMEM columns
+constexpr int T2_BN = 256;                      // rows per pair tile (128 staged by each CTA)
+constexpr int T2_SPLIT_WARP0 = 2, T2_SPLIT_WARPS = 4;
+constexpr int T2_EPI_WARP0 = 6, T2_EPI = 16;
+constexpr int T2_THREADS = (T2_EPI_WARP0 + T2_EPI) * 32;
+constexpr uint32_t T2_STAGE_BYTES = 4 * TC_TILE_BYTES;          // W_hi, W_lo, X(raw = hi), X_lo : 64 KiB
+constexpr size_t T2_SMEM_BYTES = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 + 256;
+// instruction descriptor: D = F32, A = B = TF32, K-major, M = 256 (pair), N = 256
+constexpr uint32_t T2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int ACT, int EXTRA>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
+                const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + T2_STAGES * T2_STAGE_BYTES;
+  auto bar_raw = [&](int s) { return bar_base + 8u * s; };
+  auto bar_split = [&](int s) { return bar_base + 8u * (T2_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (2 * T2_STAGES + s); };
+  auto bar_tfull = [&](int a) { return bar_base + 8u * (3 * T2_STAGES + a); };
+  auto bar_tempty = [&](int a) { return bar_base + 8u * (3 * T2_STAGES + T2_ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * T2_STAGES + 2 * T2_ACC);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T2_STAGES * T2_STAGE_BYTES + 8 * (3 * T2_STAGES + 2 * T2_ACC));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nk = p.K / TC_BK;
+  const int64_t total_tiles = p.n_tiles * p.m_tiles;       // m_tiles = N / 256 (channel pairs), n_tiles = ceil(R / 256)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), 2 * T2_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < T2_ACC; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 2 * T2_EPI); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_wlo); tma_prefetch_desc(&map_x);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                       // barriers of both CTAs initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ======================================================================== TMA producer (each CTA: its own halves)
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0; bool ok = true;
+      for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
+        const int m_t = (int)(t % p.m_tiles);
+        const int64_t n_t = t / p.m_tiles;
+        const int wrow = m_t * 256 + (int)rank * 128;
+        const int xrow = (int)(n_t * T2_BN) + (int)rank * 128;
+        for (int kb = 0; kb < nk; ++kb) {
+          if (p.l2_prefetch > 0) {
+            int kp = kb + p.l2_prefetch; int64_t tp = t;
+            if (kp >= nk) { kp -= nk; tp += npairs; }
+            if (kp < nk && tp < total_tiles) tma_prefetch_l2_2d(&map_x, kp * TC_BK, (int)((tp / p.m_tiles) * T2_BN) + (int)rank * 128);
+          }
+          if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
+          const uint32_t st = smem_base + s * T2_STAGE_BYTES;
+          mbar_expect_tx(bar_raw(s), 3 * TC_TILE_BYTES);
+          tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, wrow);
+          tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, wrow);
+          tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, xrow);
+          if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      int s = 0, a = 0; uint32_t ph = 0, aph = 0; bool ok = true;
+      for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
+        if (!(ok = mbar_wait(bar_tempty(a), aph ^ 1u, p.err))) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * T2_BN);
+        for (int kb = 0; kb < nk; ++kb) {
+          if (!(ok = mbar_wait(bar_split(s), ph, p.err))) break;
+          tc_fence_after();
+          const uint32_t st = smem_base + s * T2_STAGE_BYTES;
+          const uint64_t w_hi = umma_desc_sw128(st), w_lo = umma_desc_sw128(st + TC_TILE_BYTES);
+          const uint64_t x_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+          for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+            const uint64_t adv = (uint64_t)(k8 * 2);
+            umma_tf32_2cta(tmem_d, w_lo + adv, x_hi + adv, T2_IDESC, (kb | k8) ? 1u : 0u);
+            umma_tf32_2cta(tmem_d, w_hi + adv, x_lo + adv, T2_IDESC, 1u);
+            umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, T2_IDESC, 1u);
+          }
+          umma_commit_2cta(bar_empty(s));
+          if (kb == nk - 1) umma_commit_2cta(bar_tfull(a));
+          if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (++a == T2_ACC) { a = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp < T2_EPI_WARP0) {
+    // ======================================================================== splitter: X_lo = x - trunc_tf32(x)
+    const int tid = threadIdx.x - T2_SPLIT_WARP0 * 32;
+    int s = 0; uint32_t ph = 0; bool ok = true;
+    for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
+      for (int kb = 0; kb < nk; ++kb) {
+        if (!(ok = mbar_wait(bar_raw(s), ph, p.err))) break;
+        uint8_t* st = smem_gen + s * T2_STAGE_BYTES;
+        const float4* hi = reinterpret_cast<const float4*>(st + 2 * TC_TILE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (T2_SPLIT_WARPS * 32); ++i) {
+          const int e = tid + i * T2_SPLIT_WARPS * 32;
+          const float4 v = hi[e];
+          float4 l;
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          lo[e] = l;
+        }
+        fence_proxy_async();
+        if (rank == 0) mbar_arrive(bar_split(s)); else mbar_arrive_cluster(bar_split(s), 0);
+        if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ======================================================================== epilogue (this CTA's 128 channels x 256 rows)
+    const int q = warp & 3;
+    constexpr int CHUNKS = (T2_BN / 32) / (T2_EPI / 4);
+    const int part = (warp - T2_EPI_WARP0) >> 2;
+    int a = 0; uint32_t aph = 0; bool ok = true;
+    for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
+      const int m_t = (int)(t % p.m_tiles);
+      const int64_t n_t = t / p.m_tiles;
+      const int c = m_t * 256 + (int)rank * 128 + q * 32 + lane;
+      const float bia = p.bias ? p.bias[c] : 0.0f;
+      const float sc = p.scale ? p.scale[c] : 1.0f;
+      const float sh = p.shift ? p.shift[c] : 0.0f;
+      NeuronParams np{0.9f, 0.01f, 0.5f, 1.0f};
+      if (ACT == ACT_LIF) { np.d = p.nparams[c]; np.a = p.nparams[p.N + c]; np.r = p.nparams[2 * p.N + c]; np.th0 = p.nparams[3 * p.N + c]; }
+      if (!(ok = mbar_wait(bar_tfull(a), aph, p.err))) break;
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        const int col0 = (part * CHUNKS + ch) * 32;
+        float v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T2_BN + col0), v);
+        const int64_t r0 = n_t * T2_BN + col0;
+        const int nrows = (int)((p.R - r0) < 32 ? (p.R - r0) : 32);
+        if (nrows > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] + bia, sc, sh);
+          if (EXTRA == 1) {
+            const float* rp = p.residual + r0 * p.ldr + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { if (j < nrows) v[j] += *rp; rp += p.ldr; }
+          }
+          if (ACT == ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_leaky(v[j]);
+          }
+          if (ACT == ACT_LIF) {
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+              float u[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) u[j] = v[j0 + j];
+              lif_chain_vec_fast<8>(u, np, p.T);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j0 + j] = u[j];
+            }
+          }
+          float* yp = p.Y + r0 * p.ldc + c;
+          if (nrows == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { *yp = v[j]; yp += p.ldc; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { if (j < nrows) *yp = v[j]; yp += p.ldc; }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (rank == 0) mbar_arrive(bar_tempty(a)); else mbar_arrive_cluster(bar_tempty(a), 0); }
+      if (++a == T2_ACC) { a = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                       // nobody leaves while the peer may still touch its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool gemm_tc2_supported(const GemmArgs& g, int amode) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("SAPCU_TC_2CTA"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (!enabled || !gemm_tc_supported(g, amode)) return false;
+  if (g.N % 256 != 0 || g.Y2 != nullptr) return false;
+  if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
+  if (g.R < 4096) return false;
+  return true;
+}
+
+int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
+  SAPCU_REQUIRE(gemm_tc2_supported(g, A_PLAIN), "gemm_tc2: unsupported problem");
+  static bool attr_done = false;
+  if (!attr_done) {
+#define SAPCU_T2_ATTR(A, X) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
+    SAPCU_T2_ATTR(ACT_LIF, 0); SAPCU_T2_ATTR(ACT_LEAKY, 0); SAPCU_T2_ATTR(ACT_NONE, 1); SAPCU_T2_ATTR(ACT_NONE, 0);
+#undef SAPCU_T2_ATTR
+    attr_done = true;
+  }
+  int* err = tc_err_flag();
+  SAPCU_REQUIRE(err != nullptr, "gemm_tc2: cannot allocate the watchdog flag");
+  static int l2pf = -1;
+  if (l2pf < 0) { const char* f = getenv("SAPCU_TC_L2PF"); l2pf = f ? atoi(f) : 4; }
+  CUtensorMap mw, mwlo, mx;
+  int rc = tc_make_map(&mw, g.Whi, g.N, g.K, g.K, 128);
+  if (rc) return rc;
+  rc = tc_make_map(&mwlo, g.Wlo, g.N, g.K, g.K, 128);
+  if (rc) return rc;
+  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, 128);
+  if (rc) return rc;
+  TcParams p;
+  p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
+  p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.group = 0;
+  p.aq = nullptr; p.ak = nullptr; p.ldq = 0; p.idx = nullptr; p.ldi = 0; p.kk = 0; p.Mpts = 0; p.Y2 = nullptr;
+  p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, T2_BN); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf;
+  const int64_t total = p.n_tiles * p.m_tiles;
+  int pairs = (int)(total < kNumSMs / 2 ? total : kNumSMs / 2);
+  const int grid = 2 * pairs;
+#define SAPCU_T2_LAUNCH(A, X) gemm_tc2_kernel<A, X><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
+  if (g.act == ACT_LIF) SAPCU_T2_LAUNCH(ACT_LIF, 0);
+  else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH(ACT_LEAKY, 0);
+  else if (g.residual) SAPCU_T2_LAUNCH(ACT_NONE, 1);
+  else SAPCU_T2_LAUNCH(ACT_NONE, 0);
+#undef SAPCU_T2_LAUNCH
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sapcu
