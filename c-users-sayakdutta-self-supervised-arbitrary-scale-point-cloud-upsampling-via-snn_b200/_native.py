@@ -37,8 +37,12 @@ def _stale():
     return os.path.getmtime(os.path.join(_HERE, "..", "include", "sapcu_b200.h")) > t
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into libsapcu_b200.so (sm_100a; cross-compiles without a GPU)."""
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile csrc/*.cu into libsapcu_b200.so (sm_100a; cross-compiles without a GPU).
+    `extra_flags` / `out` build an experimental variant next to the default library (see SAPCU_LIB)."""
+    global _SO
+    if out is not None:
+        return _build_variant(list(extra_flags), out)
     if not force and not _stale():
         return _SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -60,6 +64,23 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", _SO] + objs
     subprocess.check_call(cmd)
     return _SO
+
+
+def _build_variant(extra, out):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    bdir = os.path.join(_HERE, "build", "variant_" + os.path.basename(out))
+    os.makedirs(bdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra
+    procs, objs = [], []
+    for src in _SOURCES:
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc] + flags + ["-c", os.path.join(_CSRC, src), "-o", obj]))
+    for p in procs:
+        if p.wait() != 0:
+            raise SapcuError("nvcc failed building variant %s" % out)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
+    return out
 
 
 _SIGS = {
@@ -109,11 +130,12 @@ def lib():
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(_SO):
+                so = os.environ.get("SAPCU_LIB", _SO)      # experiments: an alternative build of the same sources
+                if not os.path.exists(so):
                     raise SapcuError(
                         "libsapcu_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
-                        "There is no CPU fallback for the sapcu_b200 hot path." % _SO)
-                h = ctypes.CDLL(_SO)
+                        "There is no CPU fallback for the sapcu_b200 hot path." % so)
+                h = ctypes.CDLL(so)
                 for name, (res, args) in _SIGS.items():
                     fn = getattr(h, name)   # AttributeError = the .so is missing a declared symbol
                     fn.restype = res

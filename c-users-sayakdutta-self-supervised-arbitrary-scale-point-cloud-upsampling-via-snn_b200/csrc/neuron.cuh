@@ -37,6 +37,29 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// 1/x on the FMA pipe (x in [2, inf]): magic-constant seed + 3 Newton steps (relative error < 1e-7).
+// Trades one MUFU.RCP (8 issue cycles of the 16-lane MUFU pipe per warp) for 7 FMA-pipe instructions; the LIF
+// recurrence is MUFU-bound (3 MUFU vs 12 FP per element-step), so this rebalances the two pipes.
+#ifndef SAPCU_LIF_RCP
+#define SAPCU_LIF_RCP rcp_lif
+#endif
+__device__ __forceinline__ float rcp_fma(float x) {
+  float r = __uint_as_float(0x7EF311C7u - __float_as_uint(x));
+  r = r * fmaf(-x, r, 2.0f);
+  r = r * fmaf(-x, r, 2.0f);
+  r = r * fmaf(-x, r, 2.0f);
+  return r;
+}
+
+// reciprocal used by the fast LIF step; x = 2 + 2*exp2(.) may overflow to +inf (v << 0), where the answer is 0
+__device__ __forceinline__ float rcp_lif(float x) {
+#ifdef SAPCU_LIF_RCP_FMA          // measured slower on B200 (321.9 vs 315.3 ms/step): the step is issue-bound, not MUFU-bound
+  return rcp_fma(fminf(x, 1e30f));
+#else
+  return rcp_approx(x);
+#endif
+}
+
 // PRECISE=true : libdevice expf (<= 1 ulp) -- the fp32 parity mode
 // PRECISE=false: ex2.approx based __expf     -- the tensor-core mode
 template <bool PRECISE>
@@ -131,7 +154,7 @@ __device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronP
     const float v = mm - p.th0;
     const float g = exp2f_approx((k_g * v) * v);
     const float e = exp2f_approx(k_s * v);
-    const float s = fmaf(c_g, g, rcp_approx(fmaf(2.0f, e, 2.0f)));
+    const float s = fmaf(c_g, g, SAPCU_LIF_RCP(fmaf(2.0f, e, 2.0f)));
     m[i] = fmaf(-mm, s, mm);
     rho[i] = s;
     th[i] = fmaf(0.95f, p.th0, fmaf(a95, s, c05));
@@ -146,7 +169,7 @@ __device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronP
       const float v = mm - th[i];
       const float g = exp2f_approx((k_g * v) * v);
       const float e = exp2f_approx(k_s * v);
-      const float s = fmaf(c_g, g, rcp_approx(fmaf(2.0f, e, 2.0f)));
+      const float s = fmaf(c_g, g, SAPCU_LIF_RCP(fmaf(2.0f, e, 2.0f)));
       m[i] = fmaf(-mm, s, mm);
       rho[i] = fmaf(rho[i], p.r, s);
       th[i] = fmaf(0.95f, th[i], fmaf(a95, s, c05));
@@ -180,7 +203,7 @@ __device__ __forceinline__ float neuron_step_fast(float u, float& m, float& th, 
   const float v = mm - (FIRST ? k.th0 : th);
   const float g = exp2f_approx((k_g * v) * v);
   const float e = exp2f_approx(k_s * v);
-  const float s = fmaf(c_g, g, rcp_approx(fmaf(2.0f, e, 2.0f)));
+  const float s = fmaf(c_g, g, SAPCU_LIF_RCP(fmaf(2.0f, e, 2.0f)));
   m = fmaf(-mm, s, mm);
   rho = FIRST ? s : fmaf(rho, k.r, s);
   th = fmaf(0.95f, FIRST ? k.th0 : th, fmaf(k.a95, s, k.c05));
