@@ -12,7 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libsapcu_b200.so")
 _SOURCES = ["api.cu", "model.cu", "forward.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc2.cu", "knn_seed.cu", "patch_ops.cu",
-            "intra_knn.cu", "fn_kernels.cu", "fd_kernels.cu"]
+            "intra_knn.cu", "fn_kernels.cu", "fd_kernels.cu", "seedgen.cu"]
+# per-file flags: the fp64 geometry of seedgen.cu must round like the g++ build of dense.cpp (no FMA contraction)
+_FILE_FLAGS = {"seedgen.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -53,7 +55,7 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     for src in _SOURCES:
         obj = os.path.join(_HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + flags + ["-c", os.path.join(_CSRC, src), "-o", obj]
+        cmd = [nvcc] + flags + _FILE_FLAGS.get(src, []) + ["-c", os.path.join(_CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -75,7 +77,7 @@ def _build_variant(extra, out):
     for src in _SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        procs.append(subprocess.Popen([nvcc] + flags + ["-c", os.path.join(_CSRC, src), "-o", obj]))
+        procs.append(subprocess.Popen([nvcc] + flags + _FILE_FLAGS.get(src, []) + ["-c", os.path.join(_CSRC, src), "-o", obj]))
     for p in procs:
         if p.wait() != 0:
             raise SapcuError("nvcc failed building variant %s" % out)
@@ -99,6 +101,10 @@ _SIGS = {
     "sapcu_renormalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "sapcu_displace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                       ctypes.c_void_p, ctypes.c_void_p]),
+    "sapcu_seedgen_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_double, ctypes.c_int64]),
+    "sapcu_seedgen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
+                                     ctypes.c_size_t, ctypes.c_void_p]),
     "sapcu_model_create": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     "sapcu_model_set_tensor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
     "sapcu_model_finalize": (ctypes.c_int, [ctypes.c_void_p]),

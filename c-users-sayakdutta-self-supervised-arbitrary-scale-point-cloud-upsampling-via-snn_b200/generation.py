@@ -34,7 +34,7 @@ def rotation_matrix_from_vectors(vec1, vec2):
 
 class Generator3D6(object):
     def __init__(self, model1, model2, device, k_neighbors=100, dense_spacing=0.004,
-                 outlier_threshold=1.5, batch_size=400, seeds_per_pass=None, remove_outliers=True):
+                 outlier_threshold=1.5, batch_size=400, seeds_per_pass=None, remove_outliers=True, seed_source="gpu"):
         self.model1, self.model2 = model1, model2          # fn (normals), fd (distances)
         self.device = torch.device(device)
         self.k_neighbors = k_neighbors
@@ -43,6 +43,7 @@ class Generator3D6(object):
         self.batch_size = batch_size                       # kept for API compatibility; results are per-seed
         self.seeds_per_pass = seeds_per_pass               # device-side pass size (None: everything at once)
         self.remove_outliers = remove_outliers
+        self.seed_source = seed_source                     # "gpu": sapcu_seedgen; "dense": the reference's ./dense process
         self.model1.eval()
         self.model2.eval()
         self._bufs = {}
@@ -123,8 +124,28 @@ class Generator3D6(object):
         return out
 
     # ------------------------------------------------------------------ host-side steps outside the hot path
+    def gpu_seeds(self, data, cap=None, quirk_origin=True, round6=True):
+        """Seeds of dense.cpp computed on the device (csrc/seedgen.cu): same set, same order as `./dense`."""
+        import ctypes
+        L = N.lib()
+        d_cloud = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).to(self.device)
+        n = d_cloud.shape[0]
+        cap = int(cap or max(400 * n, 1 << 20))
+        while True:
+            ws = torch.empty(L.sapcu_seedgen_workspace_bytes(n, float(self.dense_spacing), cap), dtype=torch.uint8, device=self.device)
+            out = torch.empty(cap, 3, dtype=torch.float64, device=self.device)
+            cnt = ctypes.c_int64(0)
+            N.check(L.sapcu_seedgen(N.ptr(d_cloud), n, float(self.dense_spacing), int(quirk_origin), int(round6), N.ptr(out), cap,
+                                    ctypes.byref(cnt), N.ptr(ws), ws.numel(), N.stream_ptr()), "sapcu_seedgen")
+            if cnt.value <= cap:
+                return out[:cnt.value].cpu().numpy()
+            cap = int(cnt.value)
+
     def _dense_seeds(self, data):
-        """Seed generation exactly as the reference: shell out to ./dense (generation.py:113-118)."""
+        """Seed generation: on the device by default; seed_source="dense" shells out to ./dense exactly as the
+        reference does (generation.py:113-118; needs a ./test.xyz that the reference never writes)."""
+        if self.seed_source == "gpu":
+            return self.gpu_seeds(data)
         cmd = f"./dense {self.dense_spacing} {data.shape[0]}"
         print(cmd)
         os.system(cmd)

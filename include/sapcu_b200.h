@@ -81,6 +81,19 @@ int sapcu_displace(const double* d_seeds, const float* d_normals, const float* d
                    int64_t S, double* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Seed generator ("next" row 1).  Replaces the `./dense <cell> <N>` process + test.xyz/target.xyz file IPC of
+ * generation.py:113-118 (dense.cpp:175-252): voxel flood fill from the occupied cells, a voxel centre is a seed when
+ * its distance to the local triangle fan of its 10 nearest input points lies in [0.011, 0.015].  Same seeds in the
+ * same (FIFO) order as the reference binary.  quirk_origin != 0 keeps the reference's extra all-zero point in the
+ * 10-NN search (dense.cpp:193); round6 != 0 rounds coordinates to 6 decimals like the "%lf" text round trip.
+ * d_seeds: [cap,3] f64 (first min(count, cap) seeds are stored); *h_count (HOST) receives the total count.
+ * Synchronises the stream once per flood-fill level.
+ * ---------------------------------------------------------------------------------- */
+size_t sapcu_seedgen_workspace_bytes(int64_t N, double cell, int64_t cap);
+int sapcu_seedgen(const double* d_cloud, int64_t N, double cell, int quirk_origin, int round6,
+                  double* d_seeds, int64_t cap, int64_t* h_count, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Models.  A handle is built from the same hyper-parameters get_model() consumes
  * (fn/config.py:183-210, fd/config.py:89-117) and the tensors of the module's
  * state_dict (host fp32 pointers, names = state_dict keys).

@@ -374,3 +374,52 @@ def test_pipeline_tensor_core_mode(lib, sphere, golden):
     print("tensor-core mode vs reference: max normal angle %.4f deg, max rel distance err %.2e" % (ang, rel))
     assert ang < 0.1 and rel < 5e-3
     assert np.abs(out.cpu().numpy() - g["points"]).max() < 5e-3 * np.abs(g["dist"]).max()
+
+
+# ----------------------------------------------------------------------------------------- "next" row 1: seed generator
+def _gpu_seeds(cloud, cell, **kw):
+    from sapcu_b200.generation import Generator3D6
+    gen = Generator3D6.__new__(Generator3D6)
+    gen.device, gen.dense_spacing = torch.device(DEV), cell
+    return gen.gpu_seeds(cloud, **kw)
+
+
+def test_seed_generator_matches_reference_binary(lib, golden):
+    """sapcu_seedgen vs the seeds the reference's dense.cpp emits (same voxels, same FIFO order, 6-decimal rounding)."""
+    import hashlib
+    g = golden.seeds
+    cases = {"sphere256_c010": (syn.cloud(256, seed=5, shape="sphere"), 0.01),
+             "boxes2048_c008": (syn.cloud(2048, seed=3, shape="boxes"), 0.008),
+             "sphere2048_c004": (syn.cloud(2048, seed=0, shape="sphere"), 0.004)}
+    for name, (cloud, cell) in cases.items():
+        seeds = _gpu_seeds(cloud, cell)
+        m = np.rint(seeds * 1e6).astype(np.int32)
+        assert np.abs(m / 1e6 - seeds).max() < 1e-12                      # exactly the 6-decimal values
+        assert seeds.shape[0] == int(g[name + "_count"]), (name, seeds.shape[0], int(g[name + "_count"]))
+        if name in g.files:
+            assert np.array_equal(m, g[name]), name
+        else:
+            assert np.array_equal(m[:512], g[name + "_head"]) and np.array_equal(m[-512:], g[name + "_tail"])
+        digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(m).tobytes()).digest(), dtype=np.uint8)
+        assert np.array_equal(digest, g[name + "_sha256"]), name
+    # a too-small capacity reports the true count and the caller retries
+    small = _gpu_seeds(cases["sphere256_c010"][0], 0.01, cap=1000)
+    assert small.shape[0] == int(g["sphere256_c010_count"])
+    # without the reference's spurious origin point / text rounding the generator still runs (different, documented, output)
+    raw = _gpu_seeds(cases["sphere256_c010"][0], 0.01, quirk_origin=False, round6=False)
+    assert abs(raw.shape[0] - small.shape[0]) < 0.05 * small.shape[0]
+
+
+def test_seed_generator_live_reference(lib, tmp_path):
+    """When the compiled reference binary travelled with the repo (oracle/_ref/dense), compare on a fresh random cloud."""
+    import subprocess
+    from conftest import ROOT
+    dense = os.path.join(ROOT, "oracle", "_ref", "dense")
+    if not os.path.exists(dense):
+        pytest.skip("oracle/_ref/dense not built")
+    cloud = syn.cloud(1000, seed=77, shape="boxes")
+    np.savetxt(tmp_path / "test.xyz", cloud, fmt="%.17g")
+    subprocess.check_call([dense, "0.01", "1000"], cwd=tmp_path)
+    ref = np.loadtxt(tmp_path / "target.xyz").reshape(-1, 3)
+    got = _gpu_seeds(cloud, 0.01)
+    assert got.shape == ref.shape and np.array_equal(np.rint(got * 1e6), np.rint(ref * 1e6))

@@ -116,3 +116,18 @@ def test_pipeline_matches_reference(golden):
     np.testing.assert_allclose(d, g["dist"][:S], rtol=2e-5, atol=1e-7)
     # a different batch size changes torch's conv blocking: agreement is to fp32 rounding, not bitwise
     np.testing.assert_allclose(pts, g["points"][:S], rtol=0, atol=1e-5)
+
+
+def test_seed_golden_matches_reference_binary(golden, tmp_path):
+    """Fixture integrity for the seed-generator row: re-run the compiled reference (when present) on one case."""
+    import subprocess
+    import pytest
+    from conftest import ROOT
+    dense = os.path.join(ROOT, "oracle", "_ref", "dense")
+    if not os.path.exists(dense):
+        pytest.skip("oracle/_ref/dense not built (make -C oracle ref)")
+    cloud = syn.cloud(256, seed=5, shape="sphere")
+    np.savetxt(tmp_path / "test.xyz", cloud, fmt="%.17g")
+    subprocess.check_call([dense, "0.01", "256"], cwd=tmp_path)
+    ref = np.loadtxt(tmp_path / "target.xyz").reshape(-1, 3)
+    assert np.array_equal(np.rint(ref * 1e6).astype(np.int32), golden.seeds["sphere256_c010"])
