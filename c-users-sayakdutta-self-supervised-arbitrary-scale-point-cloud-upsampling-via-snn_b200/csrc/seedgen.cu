@@ -265,11 +265,19 @@ static SeedPlan seed_plan(int64_t N, double cell, int64_t cap) {
   SeedPlan p;
   p.B = (int)round(1.0 / cell);
   const int64_t B = p.B;
-  p.id_lo = -(B * B + B + 1);                       // ids produced by border arithmetic stay within [id_lo, id_hi)
-  p.id_hi = B * B * B + 2 * (B * B + B + 1);
+  // x is the top "digit" of a voxel id, so the flood fill legitimately runs past x = B when the cloud touches the +x
+  // face (the band reaches 0.015 + one cell beyond the surface); y/z overflow and negative indices alias exactly as in
+  // the reference.  Ids outside [id_lo, id_hi) cannot be produced by an expanding voxel.
+  const int64_t xpad = (int64_t)ceil(0.015 / cell) + 4;
+  p.id_lo = -(B * B + B + 1);
+  p.id_hi = (B + xpad + 1) * B * B + 2 * (B * B + B + 1);
   p.nvox = p.id_hi - p.id_lo;
-  // a level holds at most 6 children per expanding voxel; the visited band is a few times the emitted count
-  p.qcap = 6 * (cap > N ? cap : N) + 1024;
+  // a level holds 6 children per expanding voxel; a level is a thin shell of the band around the surface, bounded here
+  // by 64 B^2 voxels (a unit-box surface has <= 6 B^2 cells per layer) independently of the output capacity
+  int64_t lvl = 64 * B * B;
+  if (cap > lvl) lvl = cap;
+  if (N > lvl) lvl = N;
+  p.qcap = 6 * lvl + 1024;
   size_t o = 0;
   auto take = [&](size_t b) { size_t r = o; o = align_up(o + b, 256); return r; };
   p.off_eval = take(((size_t)p.nvox + 31) / 32 * 4);
