@@ -152,14 +152,22 @@ class Generator3D6(object):
         return np.loadtxt("target.xyz")[:, 0:3]
 
     def _outlier_filter(self, xyz):
-        """generation.py:176-183 (next-row scope: still the reference's host KDTree formulation)."""
-        from sklearn.neighbors import KDTree
-        if xyz.shape[0] < 30:
-            return xyz
-        dist, _ = KDTree(xyz).query(xyz, 30)
-        avg = np.mean(dist, axis=1)
-        keep = np.where(avg < np.mean(dist) * self.outlier_threshold)[0]
-        return xyz[keep, :]
+        """generation.py:176-183 on the device: self-kNN (k = 30) with sapcu_knn, mean neighbour distance per point,
+        keep the points below outlier_threshold x the global mean."""
+        L = N.lib()
+        S = xyz.shape[0]
+        if S < 30:
+            raise ValueError("k must be less than or equal to the number of training points")   # as sklearn does
+        st = N.stream_ptr()
+        d_pts = torch.from_numpy(np.ascontiguousarray(xyz, dtype=np.float64)).to(self.device)
+        idx = torch.empty(S, 30, dtype=torch.int32, device=self.device)
+        kws = torch.empty(L.sapcu_knn_workspace_bytes(S), dtype=torch.uint8, device=self.device)
+        N.check(L.sapcu_knn(N.ptr(d_pts), S, N.ptr(d_pts), S, 30, N.ptr(idx), N.ptr(kws), kws.numel(), st), "sapcu_knn(self)")
+        keep = torch.empty(S, dtype=torch.uint8, device=self.device)
+        ows = torch.empty(L.sapcu_outlier_workspace_bytes(S), dtype=torch.uint8, device=self.device)
+        N.check(L.sapcu_outlier_mask(N.ptr(d_pts), S, N.ptr(idx), 30, float(self.outlier_threshold), N.ptr(keep), N.ptr(ows),
+                                     ows.numel(), st), "sapcu_outlier_mask")
+        return xyz[keep.cpu().numpy().astype(bool), :]
 
 
 class SNNPointCloudGenerator(Generator3D6):

@@ -94,6 +94,22 @@ int sapcu_seedgen(const double* d_cloud, int64_t N, double cell, int quirk_origi
                   double* d_seeds, int64_t cap, int64_t* h_count, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Outlier filter ("next" row 2), generation.py:176-183: with d_idx = the k = 30 self-neighbours of every output point
+ * (sapcu_knn with cloud == seeds == points), keep[i] = mean_j |p_i - p_idx[i][j]| < threshold * (global mean).
+ * ---------------------------------------------------------------------------------- */
+size_t sapcu_outlier_workspace_bytes(int64_t S);
+int sapcu_outlier_mask(const double* d_points, int64_t S, const int32_t* d_idx, int K, double threshold,
+                       uint8_t* d_keep, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Farthest point sampling ("next" row 3), generate.py:56-74: fp32, start index `start` (the reference uses N/2),
+ * running distances initialised to 1e32, ties -> lowest index.  d_out: int32 [npoint] selected indices in order.
+ * One cooperative persistent kernel (a grid barrier per selected point); workspace: 32 bytes.
+ * ---------------------------------------------------------------------------------- */
+int sapcu_fps(const float* d_xyz, int64_t N, int64_t npoint, int64_t start, int32_t* d_out,
+              void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Models.  A handle is built from the same hyper-parameters get_model() consumes
  * (fn/config.py:183-210, fd/config.py:89-117) and the tensors of the module's
  * state_dict (host fp32 pointers, names = state_dict keys).

@@ -344,3 +344,31 @@ def pipeline(sd_fn, sd_fd, cloud, seeds, K=100, batch=256, cfg_fn=None, cfg_fd=N
             dists.append(fd_forward(sd_fd, pr, cfg_fd, schedule).numpy())
     normals, dists = np.concatenate(normals, 0), np.concatenate(dists, 0)
     return displace(seeds, normals, dists), idx, normals, dists
+
+
+# ----------------------------------------------------------------------------- "next" rows: outlier filter, FPS
+def outlier_filter(xyz, threshold=1.5, k=30):
+    """generation.py:176-183: KDTree self-query (k = 30, true distances), keep avg < threshold * global mean."""
+    from sklearn.neighbors import KDTree
+    dist, _ = KDTree(xyz).query(xyz, k)
+    avg = np.mean(dist, axis=1)
+    avgtotal = np.mean(dist)
+    return np.where(avg < avgtotal * threshold)[0]
+
+
+def fps(xyz, npoint):
+    """farthest_point_sample (generate.py:56-74) restated in numpy float32: start at N // 2, distances 1e32,
+    `dist < distance` update, arg-max (first maximum)."""
+    xyz = np.asarray(xyz, dtype=np.float32)
+    n = xyz.shape[0]
+    out = np.zeros(npoint, dtype=np.int64)
+    distance = np.full(n, 1e32, dtype=np.float32)
+    far = n // 2
+    for i in range(npoint):
+        out[i] = far
+        d = xyz - xyz[far]
+        dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        m = dist < distance
+        distance[m] = dist[m]
+        far = int(np.argmax(distance))
+    return out

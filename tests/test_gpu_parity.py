@@ -423,3 +423,36 @@ def test_seed_generator_live_reference(lib, tmp_path):
     ref = np.loadtxt(tmp_path / "target.xyz").reshape(-1, 3)
     got = _gpu_seeds(cloud, 0.01)
     assert got.shape == ref.shape and np.array_equal(np.rint(got * 1e6), np.rint(ref * 1e6))
+
+
+# ----------------------------------------------------------------------------------------- "next" rows 2, 3
+def test_outlier_filter_matches_reference(lib, golden):
+    from sapcu_b200.generation import Generator3D6
+    g = golden.post
+    gen = Generator3D6.__new__(Generator3D6)
+    gen.device, gen.outlier_threshold = torch.device(DEV), 1.5
+    kept = gen._outlier_filter(g["out_points"])
+    assert np.array_equal(kept, g["out_points"][g["out_keep"]])            # the reference pipeline's own survivors
+    # larger, structured set against the oracle
+    rng = np.random.default_rng(4)
+    pts = rng.normal(size=(20000, 3)); pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    pts[::97] *= 1.3
+    assert np.array_equal(gen._outlier_filter(pts), pts[orc.outlier_filter(pts, 1.5)])
+    with pytest.raises(ValueError):
+        gen._outlier_filter(pts[:10])
+
+
+def test_fps_matches_reference(lib, golden):
+    from sapcu_b200.generate import farthest_point_sample, normalize_pointcloud
+    g = golden.post
+    assert np.array_equal(farthest_point_sample(g["fps_xyz"], 512, DEV), g["fps_idx"])
+    grid = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(12), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    assert np.array_equal(farthest_point_sample(grid, 200, DEV), g["fps_grid_idx"])        # exact ties -> lowest index
+    # the real use: ~390k dense points down to 8,192 (generate.py:95-99), checked against the oracle on a prefix
+    rng = np.random.default_rng(8)
+    big = rng.normal(size=(390000, 3)); big = 0.5 * big / np.linalg.norm(big, axis=1, keepdims=True)
+    idx = farthest_point_sample(big, 8192, DEV)
+    assert len(set(idx.tolist())) == 8192 and idx[0] == 195000
+    assert np.array_equal(idx[:64], orc.fps(big, 64))
+    c, loc, scale = normalize_pointcloud(big)
+    assert np.allclose(c.max(0) - c.min(0), (big.max(0) - big.min(0)) / scale)

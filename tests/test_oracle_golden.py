@@ -131,3 +131,11 @@ def test_seed_golden_matches_reference_binary(golden, tmp_path):
     subprocess.check_call([dense, "0.01", "256"], cwd=tmp_path)
     ref = np.loadtxt(tmp_path / "target.xyz").reshape(-1, 3)
     assert np.array_equal(np.rint(ref * 1e6).astype(np.int32), golden.seeds["sphere256_c010"])
+
+
+def test_outlier_filter_and_fps_oracles(golden):
+    g = golden.post
+    assert np.array_equal(orc.outlier_filter(g["out_points"], 1.5), g["out_keep"])
+    assert np.array_equal(orc.fps(g["fps_xyz"], 512), g["fps_idx"])
+    grid = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(12), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    assert np.array_equal(orc.fps(grid, 200), g["fps_grid_idx"])
