@@ -456,3 +456,21 @@ def test_fps_matches_reference(lib, golden):
     assert np.array_equal(idx[:64], orc.fps(big, 64))
     c, loc, scale = normalize_pointcloud(big)
     assert np.allclose(c.max(0) - c.min(0), (big.max(0) - big.min(0)) / scale)
+
+
+def test_upsample_end_to_end_no_host_seed_process(lib, tmp_path):
+    """generate.py's per-file flow entirely on the device: seeds (seedgen) -> hot path -> outlier filter -> FPS -> .xyz"""
+    from sapcu_b200.generation import Generator3D6, SNNPointCloudGenerator
+    from sapcu_b200.generate import process_file
+    mfn, mfd, _, _ = _models(False)
+    mfn.set_mode("tc"), mfd.set_mode("tc")
+    cloud = syn.cloud(256, seed=5, shape="sphere") * 3.0 + np.array([1.0, -2.0, 0.5])     # un-normalised input file
+    np.savetxt(tmp_path / "in.xyz", cloud, fmt="%.8f")
+    gen = Generator3D6(mfn, mfd, DEV, k_neighbors=100, dense_spacing=0.02, batch_size=256)
+    process_file(str(tmp_path / "in.xyz"), str(tmp_path / "out.xyz"), gen, 1024)
+    out = np.loadtxt(tmp_path / "out.xyz")
+    assert out.shape == (1024, 3) and np.isfinite(out).all()
+    # the x4 cloud hugs the input surface (radius 1.5 around the centre), within the seed band + predicted distance
+    r = np.linalg.norm(out - np.array([1.0, -2.0, 0.5]), axis=1)
+    assert np.abs(r - 1.5).max() < 0.5
+    assert isinstance(SNNPointCloudGenerator(mfn, mfd, DEV, upsampling_ratio=4, dense_spacing=0.02).upsampling_ratio, int)
