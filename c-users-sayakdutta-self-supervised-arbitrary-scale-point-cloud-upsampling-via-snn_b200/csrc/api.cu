@@ -78,7 +78,7 @@ int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launch
 
 size_t sapcu_knn_workspace_bytes(int64_t N) {
   if (N < 0) return 0;
-  return align_up((size_t)(3 * N) * sizeof(float), 256) + 256;
+  return align_up((size_t)(4 * N) * sizeof(float), 256) + 256;     // float4 per point + one scalar
 }
 
 int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S, int K, int32_t* d_idx,
@@ -90,7 +90,7 @@ int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S
     return SAPCU_EWORKSPACE;
   }
   float* c32 = reinterpret_cast<float*>(d_ws);
-  float* rmax = reinterpret_cast<float*>(reinterpret_cast<char*>(d_ws) + align_up((size_t)(3 * N) * sizeof(float), 256));
+  float* rmax = reinterpret_cast<float*>(reinterpret_cast<char*>(d_ws) + align_up((size_t)(4 * N) * sizeof(float), 256));
   return launch_knn_seed(d_cloud, N, d_seeds, S, K, d_idx, c32, rmax, reinterpret_cast<cudaStream_t>(stream));
 }
 

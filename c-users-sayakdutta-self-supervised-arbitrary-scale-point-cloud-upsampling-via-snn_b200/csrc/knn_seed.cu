@@ -1,18 +1,18 @@
-// K1: exact brute-force seed -> input-cloud kNN (replaces sklearn KDTree.query, generation.py:127,153).
+// K1: exact brute-force seed -> input-cloud kNN (replaces sklearn KDTree.query, generation.py:127,153,178).
 //
-// One warp owns one seed.  The cloud is streamed through shared memory in fp32 tiles; each lane tests
-// one cloud point per iteration with a CONSERVATIVE fp32 filter and only survivors pay for the exact
-// fp64 squared distance ((dx*dx + dy*dy) + dz*dz, no contraction -- the KDTree's reduced distance).
-// The warp keeps the K best as a sorted list of (fp64 distance, index) in shared memory; survivors are
-// queued and merged by rank (keys are unique, ties resolved by the lowest index), so the result is the
-// exact fp64 ordering independent of how the cloud is tiled.
+// Large clouds (N >= 2^20): one THREAD owns one seed.  The cloud streams through shared memory as fp32 float4 tiles; every lane of a warp reads
+// the SAME point (one broadcast LDS.128 per 32 pair evaluations) and tests it against its own seed with a
+// CONSERVATIVE fp32 filter: 3 FADD + FMUL + 2 FFMA + FSETP per pair.  Only survivors pay for the exact fp64 squared
+// distance ((dx*dx + dy*dy) + dz*dz, no contraction -- the KDTree's reduced distance) and an O(log K) update of the
+// thread's private max-heap of (fp64 distance, index) keys; the heap is heap-sorted at the end, so the result is the
+// exact fp64 ordering with ties broken by the lowest cloud index, independent of tiling.
 //
 // Filter soundness: with p~,q~ the fp32 roundings of p,q and Rmax >= every |coordinate|,
 // |sqrt(d32) - sqrt(d)| <= 2^-22 Rmax + 2^-21 sqrt(d); a point with d <= tau therefore always has
 // d32 <= ((1+2^-20) sqrt(tau) + 2^-21 Rmax)^2 (1+2^-20) =: tau32, recomputed whenever tau changes.
 //
-// Roofline: FP32 issue (about 8 lane-ops per pair), cloud tiles come from L2; HBM traffic is only
-// S*(24 + 4K) bytes.
+// Roofline: FP32 issue (8 lane-ops per pair -> 148 SM x 128 lanes x clk / 8 = 4.65e12 pairs/s); the cloud comes from
+// L2 once per CTA (256 seeds); HBM traffic is only S*(24 + 4K) bytes.
 #include "common.cuh"
 #include "kernels.h"
 #include <float.h>
@@ -21,39 +21,135 @@
 namespace sapcu {
 
 constexpr int KNN_KMAX = 128;
-constexpr int KNN_WARPS = 8;
-constexpr int KNN_TILE = 1024;
-constexpr int KNN_QCAP = 64;
+constexpr int KNN_THREADS = 256;     // seeds per CTA
+constexpr int KNN_TILE = 2048;       // cloud points per shared-memory tile (32 KiB)
 
-__global__ void cloud_to_f32_kernel(const double* __restrict__ cloud, int64_t n3, float* __restrict__ out,
-                                    float* __restrict__ rmax) {
+// fp32 float4 copy of a [n,3] fp64 array (w = 0) and the running max |coordinate|
+__global__ void cloud_to_f32_kernel(const double* __restrict__ cloud, int64_t n, float4* __restrict__ out, float* __restrict__ rmax) {
   float m = 0.0f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x) {
-    const double v = cloud[i];
-    if (out) out[i] = (float)v;
-    m = fmaxf(m, (float)fabs(v) * 1.0000002f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = cloud[3 * i], y = cloud[3 * i + 1], z = cloud[3 * i + 2];
+    if (out) out[i] = make_float4((float)x, (float)y, (float)z, 0.0f);
+    m = fmaxf(m, (float)fmax(fmax(fabs(x), fabs(y)), fabs(z)) * 1.0000002f);
   }
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(rmax), __float_as_int(m));   // m >= 0
 }
 
-struct KnnKey { double d; int i; };
 __device__ __forceinline__ bool key_less(double da, int ia, double db, int ib) {
   return da < db || (da == db && ia < ib);
 }
 
-__global__ void __launch_bounds__(KNN_WARPS * 32)
-knn_seed_kernel(const double* __restrict__ cloud, const float* __restrict__ cloud32, int64_t N,
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_seed_kernel(const double* __restrict__ cloud, const float4* __restrict__ cloud32, int64_t N,
                 const double* __restrict__ seeds, int64_t S, int K, const float* __restrict__ rmax_p,
                 int32_t* __restrict__ out_idx) {
-  __shared__ float tx[KNN_TILE], ty[KNN_TILE], tz[KNN_TILE];
-  __shared__ double ld[KNN_WARPS][2][KNN_KMAX];
-  __shared__ int li[KNN_WARPS][2][KNN_KMAX];
-  __shared__ double qd[KNN_WARPS][KNN_QCAP];
-  __shared__ int qi[KNN_WARPS][KNN_QCAP];
+  __shared__ float4 tile[KNN_TILE];
+  const int64_t s = (int64_t)blockIdx.x * KNN_THREADS + threadIdx.x;
+  const bool active = s < S;
+  const float rmax = *rmax_p;
+  double sx = 0, sy = 0, sz = 0;
+  if (active) { sx = seeds[3 * s]; sy = seeds[3 * s + 1]; sz = seeds[3 * s + 2]; }
+  const float fx = (float)sx, fy = (float)sy, fz = (float)sz;
+
+  // private max-heap (root = current K-th best = tau); lives in local memory, touched only by filter survivors
+  double hd[KNN_KMAX]; int hi[KNN_KMAX];
+  for (int j = 0; j < K; ++j) { hd[j] = DBL_MAX; hi[j] = INT_MAX; }
+  double tau = DBL_MAX; int tau_i = INT_MAX;
+  float tau32 = FLT_MAX;
+
+  auto consider = [&](int gi) {
+    const double ex = cloud[3 * (int64_t)gi] - sx, ey = cloud[3 * (int64_t)gi + 1] - sy, ez = cloud[3 * (int64_t)gi + 2] - sz;
+    const double d = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+    if (!key_less(d, gi, tau, tau_i)) return;
+    // replace the root and sift down
+    int pos = 0;
+    while (true) {
+      const int l = 2 * pos + 1, r = l + 1;
+      if (l >= K) break;
+      int c = l;
+      if (r < K && key_less(hd[l], hi[l], hd[r], hi[r])) c = r;      // larger child
+      if (!key_less(d, gi, hd[c], hi[c])) break;
+      hd[pos] = hd[c]; hi[pos] = hi[c];
+      pos = c;
+    }
+    hd[pos] = d; hi[pos] = gi;
+    tau = hd[0]; tau_i = hi[0];
+    if (tau < DBL_MAX) {
+      const float rt = sqrtf((float)tau) * 1.000002f;   // >= (1+2^-20) sqrt(tau) incl. rounding of the cast/sqrt
+      const float b = rt + 4.76837158e-7f * rmax;       // 2^-21 Rmax
+      tau32 = b * b * 1.000002f;
+    }
+  };
+
+  for (int64_t base = 0; base < N; base += KNN_TILE) {
+    const int tn = (N - base) < KNN_TILE ? (int)(N - base) : KNN_TILE;
+    __syncthreads();
+    for (int j = threadIdx.x; j < tn; j += KNN_THREADS) tile[j] = cloud32[base + j];
+    __syncthreads();
+    if (!active) continue;
+    int j = 0;
+    for (; j + 4 <= tn; j += 4) {
+      float d32[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 p = tile[j + u];
+        const float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
+        d32[u] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      }
+      if (d32[0] <= tau32 || d32[1] <= tau32 || d32[2] <= tau32 || d32[3] <= tau32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (d32[u] <= tau32) consider((int)(base + j + u));       // tau32 only shrinks: re-testing is still sound
+      }
+    }
+    for (; j < tn; ++j) {
+      const float4 p = tile[j];
+      const float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
+      if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= tau32) consider((int)(base + j));
+    }
+  }
+  if (!active) return;
+  // heap sort: pop the maximum into the tail
+  for (int n = K; n > 1; --n) {
+    const double md = hd[0]; const int mi = hi[0];
+    const double d = hd[n - 1]; const int gi = hi[n - 1];
+    int pos = 0;
+    while (true) {
+      const int l = 2 * pos + 1, r = l + 1;
+      if (l >= n - 1) break;
+      int c = l;
+      if (r < n - 1 && key_less(hd[l], hi[l], hd[r], hi[r])) c = r;
+      if (!key_less(d, gi, hd[c], hi[c])) break;
+      hd[pos] = hd[c]; hi[pos] = hi[c];
+      pos = c;
+    }
+    hd[pos] = d; hi[pos] = gi;
+    hd[n - 1] = md; hi[n - 1] = mi;
+  }
+  for (int j = 0; j < K; ++j) out_idx[s * K + j] = hi[j];
+}
+
+// ---- small clouds: one WARP per seed.  Each lane tests one cloud point per iteration; survivors are queued and merged
+// by rank into a sorted shared-memory list 32 at a time, which amortises the exact fp64 work far better than the
+// thread-per-seed kernel when every seed still sees many survivors (K ln(N/K) of N points).
+constexpr int KNNW_WARPS = 8;
+constexpr int KNNW_TILE = 1024;
+constexpr int KNNW_QCAP = 64;
+
+
+__global__ void __launch_bounds__(KNNW_WARPS * 32)
+knn_seed_warp_kernel(const double* __restrict__ cloud, const float4* __restrict__ cloud32, int64_t N,
+                const double* __restrict__ seeds, int64_t S, int K, const float* __restrict__ rmax_p,
+                int32_t* __restrict__ out_idx) {
+  __shared__ float tx[KNNW_TILE], ty[KNNW_TILE], tz[KNNW_TILE];
+  __shared__ double ld[KNNW_WARPS][2][KNN_KMAX];
+  __shared__ int li[KNNW_WARPS][2][KNN_KMAX];
+  __shared__ double qd[KNNW_WARPS][KNNW_QCAP];
+  __shared__ int qi[KNNW_WARPS][KNNW_QCAP];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * KNN_WARPS + warp;
+  const int64_t s = (int64_t)blockIdx.x * KNNW_WARPS + warp;
   const bool active = s < S;
   const float rmax = *rmax_p;
 
@@ -99,11 +195,11 @@ knn_seed_kernel(const double* __restrict__ cloud, const float* __restrict__ clou
     __syncwarp();
   };
 
-  for (int64_t base = 0; base < N; base += KNN_TILE) {
-    const int tn = (int)min((int64_t)KNN_TILE, N - base);
+  for (int64_t base = 0; base < N; base += KNNW_TILE) {
+    const int tn = (int)min((int64_t)KNNW_TILE, N - base);
     __syncthreads();
     for (int j = threadIdx.x; j < tn; j += blockDim.x) {
-      tx[j] = cloud32[3 * (base + j)]; ty[j] = cloud32[3 * (base + j) + 1]; tz[j] = cloud32[3 * (base + j) + 2];
+      const float4 p = cloud32[base + j]; tx[j] = p.x; ty[j] = p.y; tz[j] = p.z;
     }
     __syncthreads();
     if (!active) continue;
@@ -130,7 +226,7 @@ knn_seed_kernel(const double* __restrict__ cloud, const float* __restrict__ clou
           }
           qn += __popc(bal);
           __syncwarp();
-          if (qn > KNN_QCAP - 32) flush();
+          if (qn > KNNW_QCAP - 32) flush();
         }
       }
     }
@@ -148,14 +244,18 @@ int launch_knn_seed(const double* cloud, int64_t N, const double* seeds, int64_t
   SAPCU_REQUIRE(N < (int64_t)INT32_MAX / 3, "sapcu_knn: N too large for int32 indices");
   if (S == 0) return 0;
   SAPCU_CUDA_CHECK(cudaMemsetAsync(rmax_scratch, 0, sizeof(float), st));
-  const int blocks = (int)std::min<int64_t>(ceil_div(3 * N, 256), 148 * 8);
-  cloud_to_f32_kernel<<<blocks, 256, 0, st>>>(cloud, 3 * N, cloud32_scratch, rmax_scratch);
+  const int blocks = (int)std::min<int64_t>(ceil_div(N, 256), 148 * 8);
+  cloud_to_f32_kernel<<<blocks, 256, 0, st>>>(cloud, N, reinterpret_cast<float4*>(cloud32_scratch), rmax_scratch);
   SAPCU_LAUNCH_CHECK();
-  const int sblocks = (int)std::min<int64_t>(ceil_div(3 * S, 256), 148 * 8);
-  cloud_to_f32_kernel<<<sblocks, 256, 0, st>>>(seeds, 3 * S, nullptr, rmax_scratch);
+  const int sblocks = (int)std::min<int64_t>(ceil_div(S, 256), 148 * 8);
+  cloud_to_f32_kernel<<<sblocks, 256, 0, st>>>(seeds, S, nullptr, rmax_scratch);
   SAPCU_LAUNCH_CHECK();
-  knn_seed_kernel<<<(unsigned)ceil_div(S, KNN_WARPS), KNN_WARPS * 32, 0, st>>>(cloud, cloud32_scratch, N, seeds, S, K,
-                                                                               rmax_scratch, idx);
+  if (N < (1 << 20))  // measured on B200 (N=1e5: 11 vs 30 ms; N=2e6: 165 vs 114 ms) (tools/knn_microbench.py): survivors dominate below, the scan above
+    knn_seed_warp_kernel<<<(unsigned)ceil_div(S, KNNW_WARPS), KNNW_WARPS * 32, 0, st>>>(cloud, reinterpret_cast<const float4*>(cloud32_scratch), N,
+                                                                                       seeds, S, K, rmax_scratch, idx);
+  else
+    knn_seed_kernel<<<(unsigned)ceil_div(S, KNN_THREADS), KNN_THREADS, 0, st>>>(cloud, reinterpret_cast<const float4*>(cloud32_scratch), N,
+                                                                               seeds, S, K, rmax_scratch, idx);
   SAPCU_LAUNCH_CHECK();
   return 0;
 }
