@@ -14,7 +14,7 @@ from . import _native as N
 class NativeModel(nn.Module):
     KIND = None            # N.MODEL_FN / N.MODEL_FD
     #: bytes of workspace the shim is willing to allocate per forward (chunks internally below that)
-    WORKSPACE_CAP = 24 << 30
+    WORKSPACE_CAP = int(float(__import__('os').environ.get('SAPCU_WS_CAP_GB', '24')) * (1 << 30))
 
     def __init__(self):
         super().__init__()
