@@ -214,6 +214,10 @@ def run_ours(args):
             peaks = json.load(open(pk))
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         achieved_tf = (gfl.value / max(gms.value, 1e-9)) / 1e9        # FLOP / ms -> TFLOP/s
+        traffic = None
+        tr = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if mode == "tc" and world == 1 and os.path.exists(tr):        # dram bytes of the same kernels, one ncu pass (per step)
+            traffic = json.load(open(tr)).get("traffic_bytes_per_step")
         cores = torch.get_num_threads()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -237,7 +241,8 @@ def run_ours(args):
                          if mode == "fp32" else "gemm_tc_kernel (tcgen05 3xTF32 contractions with fused BN/LIF epilogues; small-row layers on gemm_simt_kernel)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s",
-                         "traffic": None, "kernel_ms_per_step": gms.value / args.steps, "kernel_launches_per_step": gn.value / args.steps,
+                         "traffic": traffic, "traffic_note": "dram read+write bytes summed over the contraction launches of ONE step (ncu, profiles/r01_gemm_traffic.json); achieved/kernel_ms are likewise per-step sums over the family",
+                         "kernel_ms_per_step": gms.value / args.steps, "kernel_launches_per_step": gn.value / args.steps,
                          "kernel_share_of_step": gms.value / max(ms, 1e-9), "algorithmic_gflop_per_step": gfl.value / args.steps / 1e9},
             "cpu_baseline": cpu,
         }
