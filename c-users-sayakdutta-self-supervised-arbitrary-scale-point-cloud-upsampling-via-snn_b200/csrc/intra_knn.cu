@@ -41,9 +41,8 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
   for (int c0 = 0; c0 < C; c0 += cc_max) {
     const int cc = min(cc_max, C - c0);
     __syncthreads();
-    for (int e = tid; e < Mp * cc; e += IK_THREADS) {
-      const int i = e / cc, c = e - i * cc;
-      fsm[i * fs + c] = (i < M) ? base[(int64_t)i * ld + c0 + c] : 0.0f;
+    for (int i = tid / 32; i < Mp; i += IK_THREADS / 32) {        // one warp per row: coalesced, no per-element division
+      for (int c = tid & 31; c < cc; c += 32) fsm[i * fs + c] = (i < M) ? base[(int64_t)i * ld + c0 + c] : 0.0f;
     }
     __syncthreads();
     if (tid < M) {
@@ -53,13 +52,16 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
     for (int r = 0; r < 3; ++r) {
       const int b = tid + r * IK_THREADS;
       if (b < nb * nb) {
+        // block (bi, bj) owns rows {bi + nb*i} x {bj + nb*j}: consecutive lanes read consecutive rows (stride fs = odd
+        // number of words) -> conflict-free shared-memory loads
         const int bi = b / nb, bj = b - bi * nb;
-        const float* fa = fsm + (bi * 4) * fs;
-        const float* fb = fsm + (bj * 4) * fs;
+        const float* fa = fsm + bi * fs;
+        const float* fb = fsm + bj * fs;
+        const int rs = nb * fs;
         for (int c = 0; c < cc; ++c) {
           float a[4], bb[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { a[i] = fa[i * fs + c]; bb[i] = fb[i * fs + c]; }
+          for (int i = 0; i < 4; ++i) { a[i] = fa[i * rs + c]; bb[i] = fb[i * rs + c]; }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -80,7 +82,7 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int gi = bi * 4 + i, gj = bj * 4 + j;
+          const int gi = bi + nb * i, gj = bj + nb * j;
           if (gi < M && gj < M) {
             const float inner = __fmul_rn(-2.0f, acc[r][i][j]);
             sc[gi * ss + gj] = __fsub_rn(__fsub_rn(-xx[gj], inner), xx[gi]);
