@@ -52,39 +52,11 @@ __global__ void fd_block0_kernel(const Block0Args a) {
   a.out[pt * (a.nscales * 64) + threadIdx.x] = m;
 }
 
-// Factorised EdgeConv (tensor-core mode):  W cat(x_j - x_i, x_j) = (Wa+Wb) x_j - Wa x_i =: P_j - Q_i, so
-// out[i,c] = max_j LeakyReLU(scale_c (P[nb_j,c] - Q[i,c]) + shift_c).  PQ: [P, 2*C] rows = (P | Q).
-__global__ void edge_gather_max_kernel(const float* __restrict__ PQ, int C, const int32_t* __restrict__ idx, int ldi,
-                                       int kk, int Mpts, int64_t P, const float* __restrict__ scale,
-                                       const float* __restrict__ shift, float* __restrict__ out) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= P * C) return;
-  const int64_t pt = e / C;
-  const int c = (int)(e - pt * C);
-  const int64_t patch0 = (pt / Mpts) * Mpts;
-  const float qv = PQ[pt * 2 * C + C + c];
-  const float sc = scale[c], sh = shift[c];
-  float m = -INFINITY;
-  for (int j = 0; j < kk; ++j) {
-    const int64_t nb = patch0 + idx[pt * ldi + j];
-    const float y = fmaf(PQ[nb * 2 * C + c] - qv, sc, sh);
-    m = fmaxf(m, act_leaky(y));
-  }
-  out[e] = m;
-}
-
-int launch_edge_gather_max(const float* PQ, int C, const int32_t* idx, int ldi, int kk, int Mpts, int64_t P,
-                           const float* scale, const float* shift, float* out, cudaStream_t st) {
-  if (P == 0) return 0;
-  edge_gather_max_kernel<<<(unsigned)ceil_div(P * C, 256), 256, 0, st>>>(PQ, C, idx, ldi, kk, Mpts, P, scale, shift, out);
-  SAPCU_LAUNCH_CHECK();
-  return 0;
-}
-
-// Fused tail of a factorised EdgeConv block (tensor-core mode): for one patch and a slab of 128 channels,
+// Factorised EdgeConv (tensor-core mode):  W cat(x_j - x_i, x_j) = (Wa+Wb) x_j - Wa x_i =: P_j - Q_i, PQ rows = (P | Q).
+// Fused tail of such a block: for one patch and a slab of 128 channels,
 //   u[i,c] = max_j LeakyReLU(scale_c (P[nb_ij,c] - Q[i,c]) + shift_c)   (P rows staged in shared memory)
 // followed by the block's T-step EIF/LIF recurrence, every step's spike written into the [point, t, 960] spike
-// tensor.  Replaces edge_gather_max + neuron_unroll and their HBM round trip.
+// tensor (no HBM round trip between the max-pool and the recurrence).
 constexpr int EGU_PTS = 4;     // points processed together per thread (ILP for the recurrence)
 template <bool EIF>
 __global__ void __launch_bounds__(128)

@@ -29,8 +29,6 @@ struct Bump {
   }
 };
 
-struct Tap { const char* name; const void* ptr; int64_t rows, cols, ld; };
-
 struct FnPlan {
   int32_t* idx; float *F0, *FCAT, *X, *QKV, *E1, *E2, *E3, *RES, *R1, *G, *GM, *H0, *H1, *H2, *H3;
   size_t bytes; int kmax; int Dl, kl;

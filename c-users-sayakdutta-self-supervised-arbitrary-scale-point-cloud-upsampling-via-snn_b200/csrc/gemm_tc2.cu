@@ -286,7 +286,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   if (rc) return rc;
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
-  p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.group = 0;
+  p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = nullptr; p.ak = nullptr; p.ldq = 0; p.idx = nullptr; p.ldi = 0; p.kk = 0; p.Mpts = 0; p.Y2 = nullptr;
   p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, T2_BN); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf;
   const int64_t total = p.n_tiles * p.m_tiles;

@@ -32,8 +32,6 @@ int launch_fn_head(const float* H, int K, int64_t S, const float* W, const float
 int launch_fd_block0(const float* xyz, const int32_t* idx, int ldi, int Mpts, int64_t P, int nscales, const int* ks,
                      const float* const* W, const float* const* scale, const float* const* shift, float* out,
                      cudaStream_t st);
-int launch_edge_gather_max(const float* PQ, int C, const int32_t* idx, int ldi, int kk, int Mpts, int64_t P,
-                           const float* scale, const float* shift, float* out, cudaStream_t st);
 int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* idx, int kk, int Mpts, int64_t S,
                               const float* scale, const float* shift, const float* np, const float* ep, int T, float* U,
                               float* spk, int64_t ldspk_row, int ldo, cudaStream_t st);

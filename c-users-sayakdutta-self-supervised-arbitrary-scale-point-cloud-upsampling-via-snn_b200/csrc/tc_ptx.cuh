@@ -124,7 +124,6 @@ struct TcParams {
   float* Y; int64_t ldc;
   // EXTRA == 2 (fn fc_delta2): second output Y2[e,c] = (aq[pt,c] - ak[nb,c]) + Y[e,c], the attention input q_i - k_j + pos_ij
   const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts; float* Y2;
-  int group;                  // 0 or 32
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
   int l2_prefetch;            // k-blocks of look-ahead for the activation L2 prefetch (0 = off)
