@@ -227,10 +227,11 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if mode == "fp32" else "tf32x3", "data": "synthetic",
+            "dtype": {"fp32": "f32", "tc": "tf32x3", "tf32": "tf32"}[mode], "data": "synthetic",
             "config": {"workload": "configs[1]: 2,048-pt sphere cloud x4 -> 8,192 seeds per GPU, K=100, fn.yaml+fd.yaml "
-                                   "random-init weights, %s" % ("fp32 parity mode (FFMA contractions)" if mode == "fp32" else
-                                                              "fp32 parity mode (3xTF32 tcgen05 contractions, fp32 accumulate)"),
+                                   "random-init weights, %s" % {"fp32": "fp32 parity mode (FFMA contractions)",
+                                                              "tc": "fp32 parity mode (3xTF32 tcgen05 contractions, fp32 accumulate)",
+                                                              "tf32": "fast mode (single-pass TF32 tcgen05 contractions; deviation in profiles/)"}[mode],
                        "seeds_total": S_total, "l2": "256 MiB flush buffer written between timed steps",
                        "collective": "one all-gather of [S,3] f64 per step" if world > 1 else "none"},
             "clocks": sampler.summary(),
@@ -257,7 +258,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="tc", choices=["fp32", "tc"])
+    ap.add_argument("--mode", default="tc", choices=["fp32", "tc", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -76,8 +76,9 @@ class NativeModel(nn.Module):
         return super().train(False)
 
     def set_mode(self, mode):
-        """'fp32' (parity mode) or 'tc' (tcgen05 tensor-core contractions)."""
-        self.mode = {"fp32": N.MODE_FP32, "tc": N.MODE_TC}[mode] if isinstance(mode, str) else int(mode)
+        """'fp32' (FFMA, reference-faithful arithmetic), 'tc' (tcgen05 3xTF32, parity-grade) or 'tf32' (tcgen05
+        single-pass TF32, the fast mode whose deviation is reported separately)."""
+        self.mode = {"fp32": N.MODE_FP32, "tc": N.MODE_TC, "tf32": N.MODE_TF32}[mode] if isinstance(mode, str) else int(mode)
         return self
 
     # ------------------------------------------------------------------ helpers for subclasses

@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 MODEL_FN, MODEL_FD = 0, 1
-MODE_FP32, MODE_TC = 0, 1
+MODE_FP32, MODE_TC, MODE_TF32 = 0, 1, 2
 
 _lock = threading.Lock()
 _lib = None

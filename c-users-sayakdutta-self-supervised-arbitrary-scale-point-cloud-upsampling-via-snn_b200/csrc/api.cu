@@ -133,7 +133,8 @@ int sapcu_gemm(const float* d_x, int64_t R, int K, const float* d_w, int N, cons
   GemmArgs g;
   g.A = d_x; g.lda = K; g.R = R; g.K = K; g.W = d_w; g.N = N; g.bias = d_bias; g.Y = d_y; g.ldc = N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (mode == SAPCU_MODE_TC) {
+  if (mode == SAPCU_MODE_TC || mode == SAPCU_MODE_TF32) {
+    g.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
     if (!gemm_tc_supported(g, A_PLAIN)) { set_error("gemm: shape R=%lld K=%d N=%d not supported by the tensor-core engine", (long long)R, K, N); return SAPCU_EINVAL; }
     int rc = launch_gemm_tc(g, A_PLAIN, st);
     return rc ? rc : gemm_tc_check(st);

@@ -92,7 +92,10 @@ constexpr int ATT_KMAX = 32;
 
 // softmax over the k neighbours + weighted sum.  CTA = 128 channels x APB points; KK is the compile-time
 // neighbour count (12/18/24 for the yaml model, 32 = generic upper bound with run-time kk).
-constexpr int APB = 8;
+#ifndef SAPCU_APB
+#define SAPCU_APB 8
+#endif
+constexpr int APB = SAPCU_APB;
 template <bool PRECISE, int KK>
 __global__ void __launch_bounds__(128)
 attn_out_kernel(const float* __restrict__ logits, const float* __restrict__ pos, const float* __restrict__ V,
@@ -141,31 +144,42 @@ attn_out_kernel(const float* __restrict__ logits, const float* __restrict__ pos,
   }
 }
 
-// fn attention input materialised for the tensor-core engine: out[e,c] = (q[pt,c] - k[nb,c]) + pos[e,c]
-__global__ void attn_in_kernel(const float* __restrict__ Q, const float* __restrict__ Kf, int64_t ldq,
-                               const float* __restrict__ pos, const int32_t* __restrict__ idx, int ldi, int kk,
-                               int Mpts, int64_t E, int D, float* __restrict__ out) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // over E * D/4 float4s
+// fn attention input materialised for the tensor-core engine: out[e,c] = (q[pt,c] - k[nb,c]) + pos[e,c].
+// One CTA = AIN_EDGES consecutive edges x D/4 float4 columns; a thread walks its column over the CTA's edges with
+// incremental (pt, j) bookkeeping (one 32-bit division per thread instead of three 64-bit ones per element).
+constexpr int AIN_EDGES = 16;
+__global__ void __launch_bounds__(128)
+attn_in_kernel(const float* __restrict__ Q, const float* __restrict__ Kf, int ldq, const float* __restrict__ pos,
+               const int32_t* __restrict__ idx, int ldi, int kk, int Mpts, int E, int D, float* __restrict__ out) {
   const int D4 = D >> 2;
-  if (i >= E * D4) return;
-  const int64_t e = i / D4;
-  const int c4 = (int)(i - e * D4);
-  const int64_t pt = e / kk;
-  const int64_t nb = (pt / Mpts) * Mpts + idx[pt * ldi + (e - pt * kk)];
-  const float4 q = reinterpret_cast<const float4*>(Q + pt * ldq)[c4];
-  const float4 k = reinterpret_cast<const float4*>(Kf + nb * ldq)[c4];
-  const float4 x = reinterpret_cast<const float4*>(pos + e * D)[c4];
-  float4 o;
-  o.x = __fadd_rn(__fsub_rn(q.x, k.x), x.x); o.y = __fadd_rn(__fsub_rn(q.y, k.y), x.y);
-  o.z = __fadd_rn(__fsub_rn(q.z, k.z), x.z); o.w = __fadd_rn(__fsub_rn(q.w, k.w), x.w);
-  reinterpret_cast<float4*>(out + e * D)[c4] = o;
+  const int c4 = threadIdx.x % D4;
+  const int lane_e = threadIdx.x / D4;               // blockDim.x / D4 edges are processed side by side
+  const int estep = blockDim.x / D4;
+  const int e_begin = blockIdx.x * AIN_EDGES;
+  const int e_end = min(e_begin + AIN_EDGES, E);
+  int e = e_begin + lane_e;
+  if (e >= e_end) return;
+  int pt = e / kk, j = e - pt * kk;
+  for (; e < e_end; e += estep) {
+    const int nb = (pt / Mpts) * Mpts + idx[(int64_t)pt * ldi + j];
+    const float4 q = reinterpret_cast<const float4*>(Q + (int64_t)pt * ldq)[c4];
+    const float4 k = reinterpret_cast<const float4*>(Kf + (int64_t)nb * ldq)[c4];
+    const float4 x = reinterpret_cast<const float4*>(pos + (int64_t)e * D)[c4];
+    float4 o;
+    o.x = __fadd_rn(__fsub_rn(q.x, k.x), x.x); o.y = __fadd_rn(__fsub_rn(q.y, k.y), x.y);
+    o.z = __fadd_rn(__fsub_rn(q.z, k.z), x.z); o.w = __fadd_rn(__fsub_rn(q.w, k.w), x.w);
+    reinterpret_cast<float4*>(out + (int64_t)e * D)[c4] = o;
+    j += estep;
+    while (j >= kk) { j -= kk; ++pt; }
+  }
 }
 
 int launch_attn_in(const float* Q, const float* Kf, int64_t ldq, const float* pos, const int32_t* idx, int ldi, int kk,
                    int Mpts, int64_t E, int D, float* out, cudaStream_t st) {
-  SAPCU_REQUIRE((D & 3) == 0 && (ldq & 3) == 0, "attn_in: D and ldq must be multiples of 4");
+  SAPCU_REQUIRE((D & 3) == 0 && (ldq & 3) == 0 && D <= 512 && (128 % (D >> 2)) == 0, "attn_in: unsupported D=%d", D);
+  SAPCU_REQUIRE(E < ((int64_t)1 << 31) && ldq < (1 << 30), "attn_in: sizes must fit 32 bits");
   if (E == 0) return 0;
-  attn_in_kernel<<<(unsigned)ceil_div(E * (D >> 2), 256), 256, 0, st>>>(Q, Kf, ldq, pos, idx, ldi, kk, Mpts, E, D, out);
+  attn_in_kernel<<<(unsigned)ceil_div(E, AIN_EDGES), 128, 0, st>>>(Q, Kf, (int)ldq, pos, idx, ldi, kk, Mpts, (int)E, D, out);
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

@@ -94,8 +94,9 @@ struct G {
     int slot = -1;
     const bool prof = prof_begin(st, 2.0 * (double)g.R * g.K * g.N, &slot);
     int rc;
-    if (mode == SAPCU_MODE_TC && gemm_tc2_supported(g, amode)) rc = launch_gemm_tc2(g, st);
-    else if (mode == SAPCU_MODE_TC && gemm_tc_supported(g, amode)) rc = launch_gemm_tc(g, amode, st);
+    g.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+    if (mode != SAPCU_MODE_FP32 && gemm_tc2_supported(g, amode)) rc = launch_gemm_tc2(g, st);
+    else if (mode != SAPCU_MODE_FP32 && gemm_tc_supported(g, amode)) rc = launch_gemm_tc(g, amode, st);
     else rc = launch_gemm_simt(g, amode, mode == SAPCU_MODE_FP32, st);
     if (prof) prof_end(st, slot);
     return rc;
@@ -129,7 +130,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
     SAPCU_TRY(launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias,
                                     k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, p.E1, st));
-    if (mode == SAPCU_MODE_TC) {
+    if (mode != SAPCU_MODE_FP32) {
       // the TMA-fed tensor-core engine reads plain row-major operands: the fc_delta2 epilogue also emits the attention
       // input q_i - k_j + pos_ij (into E3), fc_gamma then maps E3 -> E1 and fc_gamma2 E1 -> E3
       GemmArgs a;
@@ -206,7 +207,7 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
       SAPCU_TRY(launch_intra_knn(p.SPK + off_in[b], ldspk, s, M, cin[b], p.k, p.idxf, st));
       idx = p.idxf;
     }
-    if (mode == SAPCU_MODE_TC) {
+    if (mode != SAPCU_MODE_FP32) {
       // factorised EdgeConv: one per-POINT contraction [P, Cin] x [2 Cout, Cin]^T, then gather / BN / LeakyReLU / max_k
       Layer L = f.convf[b];
       SAPCU_TRY(g.layer(L, p.SPK + off_in[b], ldspk, P, p.PQ, 2 * cout[b], ACT_NONE));
@@ -255,7 +256,7 @@ int check_common(const sapcu_model* m, int kind, const float* patches, int64_t S
   if (!m->finalized) { set_error("forward: model not finalized"); return SAPCU_ESTATE; }
   SAPCU_REQUIRE(S >= 0 && M >= 1 && M <= 128, "forward: need S >= 0 and 1 <= M <= 128 (got S=%lld M=%d)", (long long)S, M);
   SAPCU_REQUIRE(S == 0 || (patches && out && ws), "forward: null pointer");
-  SAPCU_REQUIRE(mode == SAPCU_MODE_FP32 || mode == SAPCU_MODE_TC, "forward: unknown mode %d", mode);
+  SAPCU_REQUIRE(mode == SAPCU_MODE_FP32 || mode == SAPCU_MODE_TC || mode == SAPCU_MODE_TF32, "forward: unknown mode %d", mode);
   return 0;
 }
 
@@ -283,7 +284,7 @@ int sapcu_fn_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
     const FnPlan p = fn_plan(m->fn, s, M, d_ws);
     SAPCU_TRY(fn_chunk(m->fn, d_patches + s0 * M * 3, s, M, d_normals + s0 * 3, p, mode, st));
   }
-  if (mode == SAPCU_MODE_TC) SAPCU_TRY(gemm_tc_check(st));
+  if (mode != SAPCU_MODE_FP32) SAPCU_TRY(gemm_tc_check(st));
   return 0;
 }
 
@@ -292,7 +293,7 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
   SAPCU_TRY(check_common(m, SAPCU_MODEL_FD, d_patches, S, M, d_dist, d_ws, mode));
   if (S == 0) return 0;
   const int k = m->fd.k < M ? m->fd.k : M;
-  SAPCU_REQUIRE(k == 32 || mode == SAPCU_MODE_TC, "fd_forward(fp32): the fused EdgeConv max-pool is built for min(k, M) == 32 (got %d)", k);
+  SAPCU_REQUIRE(k == 32 || mode != SAPCU_MODE_FP32, "fd_forward(fp32): the fused EdgeConv max-pool is built for min(k, M) == 32 (got %d)", k);
   const int64_t chunk = pick_chunk(m, S, M, ws_bytes);
   if (chunk < 1) { set_error("fd_forward: workspace of %zu bytes cannot hold one patch (need %zu)", ws_bytes, sapcu_model_workspace_bytes(m, 1, M)); return SAPCU_EWORKSPACE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -304,7 +305,7 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
       for (int b = 0; b < 3; ++b) forced[b] = d_forced_idx + ((int64_t)b * S + s0) * M * k;
     SAPCU_TRY(fd_chunk(m->fd, d_patches + s0 * M * 3, s, M, d_dist + s0, forced, p, mode, st));
   }
-  if (mode == SAPCU_MODE_TC) SAPCU_TRY(gemm_tc_check(st));
+  if (mode != SAPCU_MODE_FP32) SAPCU_TRY(gemm_tc_check(st));
   return 0;
 }
 
@@ -326,8 +327,8 @@ int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, in
     if (n == "trans3.snn_qkv") return set(p.QKV, P, 3 * D, 3 * D);
     if (n == "trans3.snn_delta2") return set(p.E2, E, D, D);
     // tensor-core mode rotates the edge buffers (the fc_delta2 epilogue emits the attention input into E3)
-    if (n == "trans3.snn_gamma") return set(mode == SAPCU_MODE_TC ? p.E1 : p.E3, E, D, D);
-    if (n == "trans3.logits") return set(mode == SAPCU_MODE_TC ? p.E3 : p.E1, E, D, D);
+    if (n == "trans3.snn_gamma") return set(mode != SAPCU_MODE_FP32 ? p.E1 : p.E3, E, D, D);
+    if (n == "trans3.logits") return set(mode != SAPCU_MODE_FP32 ? p.E3 : p.E1, E, D, D);
     if (n == "trans3.res") return set(p.RES, P, D, D);
     if (n == "snn_final") return set(p.G, P, m->fn.emb, m->fn.emb);
     if (n == "gmax") return set(p.GM, S, m->fn.emb, m->fn.emb);

@@ -37,6 +37,7 @@ struct GemmArgs {
   int act = ACT_NONE; int T = 0; const float* nparams = nullptr;   // nparams: [4][N] = d,a,r,th0
   const float* residual = nullptr; int64_t ldr = 0;
   float* Y = nullptr; int64_t ldc = 0;
+  int tc_passes = 3;     // tensor-core engine only: 3 = 3xTF32 split, 1 = single-pass TF32
   float* Y2 = nullptr;   // tensor-core engine only: second output (attention input q_i - k_j + Y), see gemm_tc.cu
   int group = 0;   // 0 or 32
 };

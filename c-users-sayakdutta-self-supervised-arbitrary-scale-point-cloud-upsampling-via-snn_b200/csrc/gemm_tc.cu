@@ -99,9 +99,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), (p.split_w ? 1 : 2) * TC_TILE_BYTES + X_BYTES);
+          mbar_expect_tx(bar_raw(s), ((p.split_w || p.passes == 1) ? 1 : 2) * TC_TILE_BYTES + X_BYTES);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, m_t * TC_BM);
-          if (!p.split_w) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, m_t * TC_BM);
+          if (!p.split_w && p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, m_t * TC_BM);
           tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, (int)(n_t * TC_BN));
           if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
         }
@@ -124,9 +124,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
             const uint64_t adv = (uint64_t)(k8 * 2);            // 8 tf32 = 32 B = 2 x 16 B along the swizzled row
-            umma_tf32(tmem_d, w_lo + adv, x_hi + adv, IDESC, (kb | k8) ? 1u : 0u);
-            umma_tf32(tmem_d, w_hi + adv, x_lo + adv, IDESC, 1u);
-            umma_tf32(tmem_d, w_hi + adv, x_hi + adv, IDESC, 1u);
+            if (p.passes == 3) {
+              umma_tf32(tmem_d, w_lo + adv, x_hi + adv, IDESC, (kb | k8) ? 1u : 0u);
+              umma_tf32(tmem_d, w_hi + adv, x_lo + adv, IDESC, 1u);
+              umma_tf32(tmem_d, w_hi + adv, x_hi + adv, IDESC, 1u);
+            } else {
+              umma_tf32(tmem_d, w_hi + adv, x_hi + adv, IDESC, (kb | k8) ? 1u : 0u);
+            }
           }
           umma_commit(bar_empty(s));                             // frees the smem stage when these MMAs retire
           if (kb == nk - 1) umma_commit(bar_tfull(a));           // accumulator complete
@@ -145,6 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         uint8_t* st = smem_gen + s * TC_STAGE_BYTES;
 #pragma unroll
         for (int op = 0; op < 2; ++op) {                          // 0: W tile (only when it arrives raw), 1: X tile
+          if (p.passes == 1) continue;                            // single-pass TF32: the raw tiles are the operands
           if (op == 0 && !p.split_w) continue;
           const uint32_t bytes = op ? X_BYTES : TC_TILE_BYTES;
           float4* hi = reinterpret_cast<float4*>(st + op * 2 * TC_TILE_BYTES);
@@ -362,7 +367,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts; p.Y2 = g.Y2;
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, bn); p.err = err;
-  p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf;
+  p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
 #define SAPCU_TC_LAUNCH1(A, RS, E, B) gemm_tc_kernel<A, RS, E, B><<<grid, (TC_EPI_WARP0 + E) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p)

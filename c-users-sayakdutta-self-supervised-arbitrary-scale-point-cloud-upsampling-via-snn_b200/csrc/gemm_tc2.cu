@@ -119,9 +119,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), 3 * TC_TILE_BYTES);
+          mbar_expect_tx(bar_raw(s), (p.passes == 3 ? 3 : 2) * TC_TILE_BYTES);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, wrow);
-          tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, wrow);
+          if (p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, wrow);
           tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, xrow);
           if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
         }
@@ -144,9 +144,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 #pragma unroll
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
             const uint64_t adv = (uint64_t)(k8 * 2);
-            umma_tf32_2cta(tmem_d, w_lo + adv, x_hi + adv, T2_IDESC, (kb | k8) ? 1u : 0u);
-            umma_tf32_2cta(tmem_d, w_hi + adv, x_lo + adv, T2_IDESC, 1u);
-            umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, T2_IDESC, 1u);
+            if (p.passes == 3) {
+              umma_tf32_2cta(tmem_d, w_lo + adv, x_hi + adv, T2_IDESC, (kb | k8) ? 1u : 0u);
+              umma_tf32_2cta(tmem_d, w_hi + adv, x_lo + adv, T2_IDESC, 1u);
+              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, T2_IDESC, 1u);
+            } else {
+              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, T2_IDESC, (kb | k8) ? 1u : 0u);
+            }
           }
           umma_commit_2cta(bar_empty(s));
           if (kb == nk - 1) umma_commit_2cta(bar_tfull(a));
@@ -167,6 +171,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         float4* lo = reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES);
 #pragma unroll
         for (int i = 0; i < (int)(TC_TILE_BYTES / 16) / (T2_SPLIT_WARPS * 32); ++i) {
+          if (p.passes == 1) break;                               // single-pass TF32: nothing to split
           const int e = tid + i * T2_SPLIT_WARPS * 32;
           const float4 v = hi[e];
           float4 l;
@@ -288,7 +293,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = nullptr; p.ak = nullptr; p.ldq = 0; p.idx = nullptr; p.ldi = 0; p.kk = 0; p.Mpts = 0; p.Y2 = nullptr;
-  p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, T2_BN); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf;
+  p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, T2_BN); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;
   int pairs = (int)(total < kNumSMs / 2 ? total : kNumSMs / 2);
   const int grid = 2 * pairs;

@@ -126,6 +126,7 @@ struct TcParams {
   const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts; float* Y2;
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
+  int passes;                 // 3: w_lo*x_hi + w_hi*x_lo + w_hi*x_hi (fp32-grade); 1: w_hi*x_hi only (plain TF32)
   int l2_prefetch;            // k-blocks of look-ahead for the activation L2 prefetch (0 = off)
   int raw_hi;                 // 1: leave the raw X tile as the hi operand (tensor core ignores the low 13 bits), lo by truncation
   int* err;

@@ -39,8 +39,10 @@ extern "C" {
 
 /* arithmetic modes of the dense contractions */
 #define SAPCU_MODE_FP32     0   /* fp32 FFMA everywhere: the "fp32 parity mode" */
-#define SAPCU_MODE_TC       1   /* tcgen05 tensor-core GEMMs (bf16 operands, fp32 accumulate) for the
-                                   per-edge contractions; everything else as in FP32 mode */
+#define SAPCU_MODE_TC       1   /* tcgen05 tensor-core contractions, 3xTF32 split (fp32-grade products, fp32 accumulate):
+                                   meets the fp32-parity tolerances; the benchmarked mode */
+#define SAPCU_MODE_TF32     2   /* tcgen05 single-pass TF32 contractions (10-bit mantissa operands): the fast
+                                   tensor-core mode, deviation reported separately */
 
 const char* sapcu_last_error(void);
 int         sapcu_abi_version(void);

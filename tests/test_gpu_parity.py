@@ -474,3 +474,31 @@ def test_upsample_end_to_end_no_host_seed_process(lib, tmp_path):
     r = np.linalg.norm(out - np.array([1.0, -2.0, 0.5]), axis=1)
     assert np.abs(r - 1.5).max() < 0.5
     assert isinstance(SNNPointCloudGenerator(mfn, mfd, DEV, upsampling_ratio=4, dense_spacing=0.02).upsampling_ratio, int)
+
+
+def test_tf32_fast_mode_deviation(lib, sphere, golden):
+    """Single-pass TF32 contractions (SAPCU_MODE_TF32): NOT a parity mode -- its deviation from the fp32 oracle is
+    measured, printed (and archived by tools/tf32_deviation.py) and only sanity-bounded here."""
+    cloud, seeds = sphere
+    B = 16
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx))
+    out = {}
+    for stress in (False, True):
+        mfn, mfd, sd_fn, sd_fd = _models(stress)
+        mfn.set_mode("tf32"), mfd.set_mode("tf32")
+        with torch.no_grad():
+            n_ref = orc.fn_forward(sd_fn, p).numpy()
+            taps = {}
+            d_ref = orc.fd_forward(sd_fd, p, schedule="dce", taps=taps).numpy()
+        n = mfn(p.to(DEV)).cpu().numpy()
+        forced = torch.stack([gi.to(torch.int32) for gi in taps["graph_idx"]], 0)
+        d_tf = mfd(p.to(DEV), forced_idx=forced).cpu().numpy()
+        d_fr = mfd(p.to(DEV)).cpu().numpy()
+        tag = "stress" if stress else "default"
+        out[tag] = dict(angle_deg=float(_angle_deg(n, n_ref).max()),
+                        dist_rel_teacher_forced=float((np.abs(d_tf - d_ref) / np.maximum(np.abs(d_ref), 1e-6)).max()),
+                        dist_rel_free_running=float((np.abs(d_fr - d_ref) / np.maximum(np.abs(d_ref), 1e-6)).max()))
+    print("tf32 fast-mode deviation vs fp32 oracle:", out)
+    for v in out.values():
+        assert v["angle_deg"] < 5.0 and v["dist_rel_teacher_forced"] < 0.1
