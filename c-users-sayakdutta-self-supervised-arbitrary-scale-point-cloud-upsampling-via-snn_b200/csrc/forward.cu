@@ -148,9 +148,24 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
         SAPCU_TRY(launch_attn_in(p.QKV, p.QKV + D, 3 * D, p.E2, p.idx, p.kmax, kk, M, E, D, p.E3, st));
       }
       SAPCU_TRY(g.layer(k.fc_gamma, p.E3, D, E, p.E1, D, ACT_LIF, &k.snn_gamma, 4));
-      SAPCU_TRY(g.layer(k.fc_gamma2, p.E1, D, E, p.E3, D, ACT_NONE));
       const float sq = sqrtf((float)(D / f.heads));
-      SAPCU_TRY(launch_attn_out(precise, p.E3, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, sq, p.RES, st));
+      {
+        // fc_gamma2 with the attention tail fused into its epilogue (2-CTA kernel, k in {12,18,24}); otherwise logits -> E3
+        GemmArgs a;
+        const Layer& L = k.fc_gamma2;
+        a.A = p.E1; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
+        a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_NONE;
+        a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
+        a.at_pos = p.E2; a.at_v = p.QKV + 2 * D; a.at_ldv = 3 * D; a.at_sqrt = sq;
+        a.Y = p.RES; a.ldc = D;
+        a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+        if (gemm_tc2_supported(a, A_PLAIN)) {
+          SAPCU_TRY(g.run(a, A_PLAIN));
+        } else {
+          SAPCU_TRY(g.layer(k.fc_gamma2, p.E1, D, E, p.E3, D, ACT_NONE));
+          SAPCU_TRY(launch_attn_out(precise, p.E3, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, sq, p.RES, st));
+        }
+      }
       SAPCU_TRY(g.layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
       SAPCU_TRY(g.layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
       continue;

@@ -30,8 +30,6 @@ constexpr int T2_EPI_WARP0 = 6, T2_EPI = 16;
 constexpr int T2_THREADS = (T2_EPI_WARP0 + T2_EPI) * 32;
 constexpr uint32_t T2_STAGE_BYTES = 4 * TC_TILE_BYTES;          // W_hi, W_lo, X(raw = hi), X_lo : 64 KiB
 constexpr size_t T2_SMEM_BYTES = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 + 256;
-// instruction descriptor: D = F32, A = B = TF32, K-major, M = 256 (pair), N = 256
-constexpr uint32_t T2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -65,7 +63,7 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives
                : "memory");
 }
 
-template <int ACT, int EXTRA>
+template <int ACT, int EXTRA, int KK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                 const __grid_constant__ CUtensorMap map_x, const TcParams p) {
@@ -85,7 +83,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   const uint32_t rank = cluster_ctarank();                 // 0 = leader
   const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nk = p.K / TC_BK;
-  const int64_t total_tiles = p.n_tiles * p.m_tiles;       // m_tiles = N / 256 (channel pairs), n_tiles = ceil(R / 256)
+  const int64_t total_tiles = p.n_tiles * p.m_tiles;       // m_tiles = N / 256 (channel pairs), n_tiles = ceil(R / tile_rows)
+  const int TR = p.tile_rows, HALF = TR >> 1;              // rows per pair tile (<= 256) / staged by each CTA
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < T2_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), 2 * T2_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
@@ -110,16 +110,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         const int m_t = (int)(t % p.m_tiles);
         const int64_t n_t = t / p.m_tiles;
         const int wrow = m_t * 256 + (int)rank * 128;
-        const int xrow = (int)(n_t * T2_BN) + (int)rank * 128;
+        const int xrow = (int)(n_t * TR) + (int)rank * HALF;
         for (int kb = 0; kb < nk; ++kb) {
           if (p.l2_prefetch > 0) {
             int kp = kb + p.l2_prefetch; int64_t tp = t;
             if (kp >= nk) { kp -= nk; tp += npairs; }
-            if (kp < nk && tp < total_tiles) tma_prefetch_l2_2d(&map_x, kp * TC_BK, (int)((tp / p.m_tiles) * T2_BN) + (int)rank * 128);
+            if (kp < nk && tp < total_tiles) tma_prefetch_l2_2d(&map_x, kp * TC_BK, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), (p.passes == 3 ? 3 : 2) * TC_TILE_BYTES);
+          mbar_expect_tx(bar_raw(s), (p.passes == 3 ? 2 : 1) * TC_TILE_BYTES + (uint32_t)HALF * 128u);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, wrow);
           if (p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, wrow);
           tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, xrow);
@@ -145,11 +145,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
             const uint64_t adv = (uint64_t)(k8 * 2);
             if (p.passes == 3) {
-              umma_tf32_2cta(tmem_d, w_lo + adv, x_hi + adv, T2_IDESC, (kb | k8) ? 1u : 0u);
-              umma_tf32_2cta(tmem_d, w_hi + adv, x_lo + adv, T2_IDESC, 1u);
-              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, T2_IDESC, 1u);
+              umma_tf32_2cta(tmem_d, w_lo + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
+              umma_tf32_2cta(tmem_d, w_hi + adv, x_lo + adv, idesc, 1u);
+              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
             } else {
-              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, T2_IDESC, (kb | k8) ? 1u : 0u);
+              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
             }
           }
           umma_commit_2cta(bar_empty(s));
@@ -203,6 +203,41 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
       if (ACT == ACT_LIF) { np.d = p.nparams[c]; np.a = p.nparams[p.N + c]; np.r = p.nparams[2 * p.N + c]; np.th0 = p.nparams[3 * p.N + c]; }
       if (!(ok = mbar_wait(bar_tfull(a), aph, p.err))) break;
       tc_fence_after();
+      if (EXTRA == 3) {
+        // fused attention tail: this tile holds TR / KK whole points; a warp takes every `parts`-th point, one
+        // channel per lane: logits -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j])
+        const int npts = TR / KK;
+        const int parts = (npts % 4 == 0) ? 4 : ((npts % 2 == 0) ? 2 : 1);
+        const int64_t P_total = p.R / KK;
+        const float inv_s = 1.0f / p.at_sqrt;
+        if (part < parts) {
+          for (int pp = part; pp < npts; pp += parts) {
+            const int64_t pt = n_t * npts + pp;
+            if (pt >= P_total) break;                      // warp-uniform
+            float av[KK];
+            __syncwarp();
+            tmem_ld_cols<KK>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T2_BN + pp * KK), av);
+            const int64_t patch0 = (pt / p.Mpts) * p.Mpts;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) { av[j] = fmaf(av[j] + bia, sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx((av[j] - mx) * 1.4426950408889634f); sum += av[j]; }
+            const float inv_sum = 1.0f / sum;
+            const float* ps = p.at_pos + (pt * KK) * (int64_t)p.N + c;
+            const int32_t* ip = p.idx + pt * p.ldi;
+            float res = 0.0f;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) {
+              const int64_t nb = patch0 + ip[j];
+              const float vp = p.at_v[nb * p.at_ldv + c] + ps[(int64_t)j * p.N];
+              res = fmaf(av[j] * inv_sum, vp, res);
+            }
+            p.Y[pt * p.ldc + c] = res;
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int ch = 0; ch < CHUNKS; ++ch) {
         const int col0 = (part * CHUNKS + ch) * 32;
@@ -244,6 +279,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (rank == 0) mbar_arrive(bar_tempty(a)); else mbar_arrive_cluster(bar_tempty(a), 0); }
@@ -259,13 +295,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static int fused_tile_rows(int kk) {        // largest multiple of lcm(kk, 16) not above 256, for the instantiated kk
+  if (kk == 12 || kk == 24) return 240;
+  if (kk == 18) return 144;
+  return 0;
+}
+
 bool gemm_tc2_supported(const GemmArgs& g, int amode) {
-  static int enabled = -1;
+  static int enabled = -1, fuse = -1;
   if (enabled < 0) { const char* e = getenv("SAPCU_TC_2CTA"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
-  if (!enabled || !gemm_tc_supported(g, amode)) return false;
+  if (fuse < 0) { const char* e = getenv("SAPCU_TC_FUSE_ATTNOUT"); fuse = (e && atoi(e) == 0) ? 0 : 1; }
+  GemmArgs base = g;
+  base.at_pos = nullptr;
+  if (!enabled || !gemm_tc_supported(base, amode)) return false;
   if (g.N % 256 != 0 || g.Y2 != nullptr) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
   if (g.R < 4096) return false;
+  if (g.at_pos) {
+    if (!fuse || g.act != ACT_NONE || g.residual || !g.at_v || !g.idx || fused_tile_rows(g.kk) == 0) return false;
+    if (g.R % g.kk != 0) return false;
+  }
   return true;
 }
 
@@ -273,8 +322,9 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   SAPCU_REQUIRE(gemm_tc2_supported(g, A_PLAIN), "gemm_tc2: unsupported problem");
   static bool attr_done = false;
   if (!attr_done) {
-#define SAPCU_T2_ATTR(A, X) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR(ACT_LIF, 0); SAPCU_T2_ATTR(ACT_LEAKY, 0); SAPCU_T2_ATTR(ACT_NONE, 1); SAPCU_T2_ATTR(ACT_NONE, 0);
+#define SAPCU_T2_ATTR(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
+    SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
+    SAPCU_T2_ATTR(ACT_NONE, 3, 12); SAPCU_T2_ATTR(ACT_NONE, 3, 18); SAPCU_T2_ATTR(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR
     attr_done = true;
   }
@@ -282,26 +332,31 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   SAPCU_REQUIRE(err != nullptr, "gemm_tc2: cannot allocate the watchdog flag");
   static int l2pf = -1;
   if (l2pf < 0) { const char* f = getenv("SAPCU_TC_L2PF"); l2pf = f ? atoi(f) : 4; }
+  const int tile_rows = g.at_pos ? fused_tile_rows(g.kk) : T2_BN;
   CUtensorMap mw, mwlo, mx;
   int rc = tc_make_map(&mw, g.Whi, g.N, g.K, g.K, 128);
   if (rc) return rc;
   rc = tc_make_map(&mwlo, g.Wlo, g.N, g.K, g.K, 128);
   if (rc) return rc;
-  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, 128);
+  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, tile_rows / 2);
   if (rc) return rc;
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
-  p.aq = nullptr; p.ak = nullptr; p.ldq = 0; p.idx = nullptr; p.ldi = 0; p.kk = 0; p.Mpts = 0; p.Y2 = nullptr;
-  p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, T2_BN); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
+  p.aq = nullptr; p.ak = nullptr; p.ldq = 0; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts; p.Y2 = nullptr;
+  p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
+  p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;
   int pairs = (int)(total < kNumSMs / 2 ? total : kNumSMs / 2);
   const int grid = 2 * pairs;
-#define SAPCU_T2_LAUNCH(A, X) gemm_tc2_kernel<A, X><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
-  if (g.act == ACT_LIF) SAPCU_T2_LAUNCH(ACT_LIF, 0);
-  else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH(ACT_LEAKY, 0);
-  else if (g.residual) SAPCU_T2_LAUNCH(ACT_NONE, 1);
-  else SAPCU_T2_LAUNCH(ACT_NONE, 0);
+#define SAPCU_T2_LAUNCH(A, X, KQ) gemm_tc2_kernel<A, X, KQ><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
+  if (g.at_pos) {
+    if (g.kk == 12) SAPCU_T2_LAUNCH(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH(ACT_NONE, 3, 24);
+  }
+  else if (g.act == ACT_LIF) SAPCU_T2_LAUNCH(ACT_LIF, 0, 1);
+  else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH(ACT_LEAKY, 0, 1);
+  else if (g.residual) SAPCU_T2_LAUNCH(ACT_NONE, 1, 1);
+  else SAPCU_T2_LAUNCH(ACT_NONE, 0, 1);
 #undef SAPCU_T2_LAUNCH
   SAPCU_LAUNCH_CHECK();
   return 0;

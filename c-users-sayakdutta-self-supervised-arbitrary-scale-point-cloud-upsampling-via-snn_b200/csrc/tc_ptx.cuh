@@ -98,6 +98,51 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// tcgen05.ld.32x32b.xN for N in {1,2,4,8,16}: N consecutive columns of this thread's lane into dst[0..N)
+template <int NCOL> __device__ __forceinline__ void tmem_ld_piece(uint32_t taddr, float* dst);
+template <> __device__ __forceinline__ void tmem_ld_piece<1>(uint32_t taddr, float* dst) {
+  uint32_t r0;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
+  dst[0] = __uint_as_float(r0);
+}
+template <> __device__ __forceinline__ void tmem_ld_piece<2>(uint32_t taddr, float* dst) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+  dst[0] = __uint_as_float(r0); dst[1] = __uint_as_float(r1);
+}
+template <> __device__ __forceinline__ void tmem_ld_piece<4>(uint32_t taddr, float* dst) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = __uint_as_float(r[i]);
+}
+template <> __device__ __forceinline__ void tmem_ld_piece<8>(uint32_t taddr, float* dst) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = __uint_as_float(r[i]);
+}
+template <> __device__ __forceinline__ void tmem_ld_piece<16>(uint32_t taddr, float* dst) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dst[i] = __uint_as_float(r[i]);
+}
+// KK columns (KK <= 31) as a sum of power-of-two pieces, then one tcgen05.wait::ld
+template <int KK> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[KK]) {
+  int o = 0;
+  if (KK & 16) { tmem_ld_piece<16>(taddr + o, v + o); o += 16; }
+  if (KK & 8) { tmem_ld_piece<8>(taddr + o, v + o); o += 8; }
+  if (KK & 4) { tmem_ld_piece<4>(taddr + o, v + o); o += 4; }
+  if (KK & 2) { tmem_ld_piece<2>(taddr + o, v + o); o += 2; }
+  if (KK & 1) { tmem_ld_piece<1>(taddr + o, v + o); o += 1; }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -124,6 +169,10 @@ struct TcParams {
   float* Y; int64_t ldc;
   // EXTRA == 2 (fn fc_delta2): second output Y2[e,c] = (aq[pt,c] - ak[nb,c]) + Y[e,c], the attention input q_i - k_j + pos_ij
   const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts; float* Y2;
+  // EXTRA == 3 (fn fc_gamma2, 2-CTA kernel): the epilogue applies softmax over the kk edges of a point to the logits
+  // (/ at_sqrt) and writes Y[pt,c] = sum_j a_j (at_v[nb_j,c] + at_pos[e_j,c]) instead of the logits
+  const float* at_pos; const float* at_v; int64_t at_ldv; float at_sqrt;
+  int tile_rows;              // activation rows per tile (UMMA N); a multiple of kk when EXTRA == 3
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
   int passes;                 // 3: w_lo*x_hi + w_hi*x_lo + w_hi*x_hi (fp32-grade); 1: w_hi*x_hi only (plain TF32)
