@@ -131,23 +131,30 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     SAPCU_TRY(launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias,
                                     k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, p.E1, st));
     if (mode != SAPCU_MODE_FP32) {
-      // the TMA-fed tensor-core engine reads plain row-major operands: the fc_delta2 epilogue also emits the attention
-      // input q_i - k_j + pos_ij (into E3), fc_gamma then maps E3 -> E1 and fc_gamma2 E1 -> E3
-      GemmArgs a;
-      const Layer& L = k.fc_delta2;
-      a.A = p.E1; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
-      a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_delta2.np;
-      a.Y = p.E2; a.ldc = D; a.Y2 = p.E3;
-      a.Q = p.QKV; a.Kf = p.QKV + D; a.ldq = 3 * D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
-      static const bool fuse_attn_in = getenv("SAPCU_TC_FUSE_ATTNIN") && atoi(getenv("SAPCU_TC_FUSE_ATTNIN")) == 1;
-      if (fuse_attn_in && gemm_tc_supported(a, A_PLAIN)) {
-        SAPCU_TRY(g.run(a, A_PLAIN));
-      } else {
-        a.Y2 = nullptr;
-        SAPCU_TRY(g.run(a, A_PLAIN));
-        SAPCU_TRY(launch_attn_in(p.QKV, p.QKV + D, 3 * D, p.E2, p.idx, p.kmax, kk, M, E, D, p.E3, st));
+      // tensor-core schedule.  fc_gamma's first layer is linear, so W(q_i - k_j + pos_ij) = W q_i - W k_j + W pos_ij:
+      // the edge contraction runs on pos (E2) alone and its epilogue adds the two per-POINT products (gathered through
+      // the graph) before BN + LIF -- the [E, D] attention input is never materialised.  E3 holds [W q | W k] ([P, 2D]).
+      SAPCU_TRY(g.layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
+      {
+        GemmArgs a;
+        const Layer& L = k.fc_gamma;
+        a.A = p.E2; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
+        a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_gamma.np;
+        a.Y = p.E1; a.ldc = D;
+        float* QK = p.E3;
+        a.Q = QK; a.Kf = QK + D; a.ldq = 2 * D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M; a.edge_bias = true;
+        static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
+        if (factorise && kk >= 2 && gemm_tc_supported(a, A_PLAIN)) {
+          Layer Lw = L;
+          Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;
+          SAPCU_TRY(g.layer(Lw, p.QKV, 3 * D, P, QK, 2 * D, ACT_NONE));
+          SAPCU_TRY(g.layer(Lw, p.QKV + D, 3 * D, P, QK + D, 2 * D, ACT_NONE));
+          SAPCU_TRY(g.run(a, A_PLAIN));
+        } else {
+          SAPCU_TRY(launch_attn_in(p.QKV, p.QKV + D, 3 * D, p.E2, p.idx, p.kmax, kk, M, E, D, p.E3, st));
+          SAPCU_TRY(g.layer(k.fc_gamma, p.E3, D, E, p.E1, D, ACT_LIF, &k.snn_gamma, 4));
+        }
       }
-      SAPCU_TRY(g.layer(k.fc_gamma, p.E3, D, E, p.E1, D, ACT_LIF, &k.snn_gamma, 4));
       const float sq = sqrtf((float)(D / f.heads));
       {
         // fc_gamma2 with the attention tail fused into its epilogue (2-CTA kernel, k in {12,18,24}); otherwise logits -> E3
@@ -343,7 +350,10 @@ int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, in
     if (n == "trans3.snn_delta2") return set(p.E2, E, D, D);
     // tensor-core mode rotates the edge buffers (the fc_delta2 epilogue emits the attention input into E3)
     if (n == "trans3.snn_gamma") return set(mode != SAPCU_MODE_FP32 ? p.E1 : p.E3, E, D, D);
-    if (n == "trans3.logits") return set(mode != SAPCU_MODE_FP32 ? p.E3 : p.E1, E, D, D);
+    if (n == "trans3.logits") {   // the tensor-core modes fuse the softmax into the fc_gamma2 epilogue: no logits buffer
+      SAPCU_REQUIRE(mode == SAPCU_MODE_FP32, "model_tap: 'trans3.logits' is only materialised in SAPCU_MODE_FP32");
+      return set(p.E1, E, D, D);
+    }
     if (n == "trans3.res") return set(p.RES, P, D, D);
     if (n == "snn_final") return set(p.G, P, m->fn.emb, m->fn.emb);
     if (n == "gmax") return set(p.GM, S, m->fn.emb, m->fn.emb);

@@ -34,8 +34,11 @@ namespace sapcu {
 
 // BN = activation rows per tile (UMMA N) is a template parameter: 128 (3 smem stages, 4 TMEM accumulators)
 // or 256 (2 stages, 2 accumulators; 25 % fewer operand bytes per FLOP)
-constexpr int TC_SPLIT_WARP0 = 2, TC_SPLIT_WARPS = 4;
-constexpr int TC_EPI_WARP0 = 6;                                // epilogue warps: 8 or 16 (template parameter EPI)
+#ifndef SAPCU_TC_SPLIT_WARPS
+#define SAPCU_TC_SPLIT_WARPS 2     // 2 + 2 + 16 warps = 640 threads: 96 registers per thread for the epilogue
+#endif
+constexpr int TC_SPLIT_WARP0 = 2, TC_SPLIT_WARPS = SAPCU_TC_SPLIT_WARPS;
+constexpr int TC_EPI_WARP0 = TC_SPLIT_WARP0 + TC_SPLIT_WARPS;                                // epilogue warps: 8 or 16 (template parameter EPI)
 constexpr size_t TC_SMEM_BYTES = (size_t)3 * 4 * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // same for both BN
 
 
@@ -141,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
   } else if (warp < TC_EPI_WARP0) {
     // ======================================================================== splitter: raw -> (hi, lo)
-    const int tid = threadIdx.x - TC_SPLIT_WARP0 * 32;            // 0..127
+    const int tid = threadIdx.x - TC_SPLIT_WARP0 * 32;
     int s = 0; uint32_t ph = 0; bool ok = true;
     for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
       for (int kb = 0; kb < nk; ++kb) {
@@ -205,6 +208,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if (ACT == ACT_LIF) { np.d = p.nparams[cc]; np.a = p.nparams[p.N + cc]; np.r = p.nparams[2 * p.N + cc]; np.th0 = p.nparams[3 * p.N + cc]; }
       if (!(ok = mbar_wait(bar_tfull(a), aph, p.err))) break;
       tc_fence_after();
+      if (ACT == ACT_LIF) {
+        // 8 columns at a time with the next piece's TMEM load in flight (see gemm_tc2.cu): keeps all 8 recurrences
+        // interleaved instead of 32 live accumulators forcing ptxas to serialise them
+        const int colw = part * CHUNKS * 32;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + colw);
+        float nxt[8];
+        __syncwarp();
+        tmem_ld_piece<8>(tbase, nxt);
+        int my_qo = 0, my_ko = 0, nx_qo = 0, nx_ko = 0;          // EXTRA == 2: this / the next 32-row group's offsets
+        float qv[8], kv[8];
+        if (EXTRA == 2) {                                         // edge bias W q_i - W k_j: operands of piece 0
+          edge_lane_offsets(p, n_t * TC_BN + colw, lane, my_qo, my_ko);
+          edge_fetch8(p, my_qo, my_ko, 0, c, qv, kv);
+        }
+#pragma unroll 1
+        for (int pc = 0; pc < CHUNKS * 4; ++pc) {
+          float u[8];
+          tmem_wait_ld8(nxt);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = nxt[j];
+          if (pc + 1 < CHUNKS * 4) tmem_ld_piece<8>(tbase + (uint32_t)((pc + 1) * 8), nxt);
+          const int64_t r0 = n_t * TC_BN + colw + pc * 8;
+          const int nrows = (int)((p.R - r0) < 8 ? (p.R - r0) : 8);
+          if (EXTRA == 2) {                                       // fold this piece's bias in, fetch the next one under the LIF
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] += qv[j] - kv[j];
+            if ((pc & 3) == 0 && pc + 4 < CHUNKS * 4) edge_lane_offsets(p, n_t * TC_BN + colw + (pc + 4) * 8, lane, nx_qo, nx_ko);
+            if (pc + 1 < CHUNKS * 4) {
+              if (((pc + 1) & 3) == 0) { my_qo = nx_qo; my_ko = nx_ko; }
+              edge_fetch8(p, my_qo, my_ko, (pc + 1) & 3, c, qv, kv);
+            }
+          }
+          if (cv && nrows > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j] + bia, sc, sh);
+            lif_chain_vec_fast<8>(u, np, p.T);
+            float* yp = p.Y + r0 * p.ldc + c;
+            if (nrows == 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { *yp = u[j]; yp += p.ldc; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { if (j < nrows) *yp = u[j]; yp += p.ldc; }
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int ch = 0; ch < CHUNKS; ++ch) {
         const int col0 = (part * CHUNKS + ch) * 32;
@@ -213,13 +263,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + col0), v);
         const int64_t r0 = n_t * TC_BN + col0;
         const int nrows = (int)((p.R - r0) < 32 ? (p.R - r0) : 32);     // <= 0 for tiles past the end
-        int my_qo = 0, my_ko = 0;                                       // EXTRA == 2: lane j resolves edge row r0 + j
-        if (EXTRA == 2 && lane < nrows) {                               // (element offsets fit 32 bits: checked on the host)
-          const int e = (int)(r0 + lane);
-          const int pt = e / p.kk;
-          const int nb = (pt / p.Mpts) * p.Mpts + p.idx[(int64_t)pt * p.ldi + (e - pt * p.kk)];
-          my_qo = pt * (int)p.ldq; my_ko = nb * (int)p.ldq;
-        }
         if (cv && nrows > 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] + bia, sc, sh);
@@ -243,15 +286,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             for (int j = 0; j < 8; ++j) v[j0 + j] = u[j];
           }
         }
-        if (EXTRA == 2) {                                                // N % 32 == 0 here: cv is warp-uniform
-          float* y2 = p.Y2 + r0 * p.ldc + c;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int qo = __shfl_sync(0xffffffffu, my_qo, j), ko = __shfl_sync(0xffffffffu, my_ko, j);
-            if (j < nrows) *y2 = (p.aq[qo + c] - p.ak[ko + c]) + v[j];
-            y2 += p.ldc;
-          }
-        }
         float* yp = p.Y + r0 * p.ldc + c;
         if (nrows == 32) {
 #pragma unroll
@@ -261,6 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           for (int j = 0; j < 32; ++j) { if (j < nrows) *yp = v[j]; yp += p.ldc; }
         }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -325,8 +360,8 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if (g.act == ACT_GELU) return false;                             // decoder MLPs (rows = patches) stay on the SIMT engine
   if (g.residual && g.act != ACT_NONE) return false;
   if (g.at_pos) return false;                                      // fused attention epilogue: 2-CTA kernel only
-  if (g.Y2 && (g.act != ACT_LIF || (g.N % 32) != 0 || !g.Q || !g.Kf || !g.idx)) return false;
-  if (g.Y2 && (g.R >= ((int64_t)1 << 31) || (g.R / (g.kk > 0 ? g.kk : 1) + 1) * g.ldq >= ((int64_t)1 << 31))) return false;
+  if (g.edge_bias && (g.act != ACT_LIF || (g.N % 128) != 0 || !g.Q || !g.Kf || !g.idx || g.kk < 1 || g.Mpts < 1)) return false;
+  if (g.edge_bias && (g.R / g.kk + g.Mpts) * g.ldq >= ((int64_t)1 << 31)) return false;     // 32-bit gather offsets
   if (g.R >= ((int64_t)1 << 31) || g.N > (1 << 20)) return false;
   return true;
 }
@@ -366,7 +401,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
-  p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts; p.Y2 = g.Y2;
+  p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, bn); p.err = err;
   p.at_pos = nullptr; p.at_v = nullptr; p.at_ldv = 0; p.at_sqrt = 1.0f; p.tile_rows = bn;
   p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
@@ -380,7 +415,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
     else if (bn == 128) SAPCU_TC_LAUNCH1(A, RS, 16, 128);                        \
     else SAPCU_TC_LAUNCH1(A, RS, 16, 256);                                       \
   } while (0)
-  if (g.act == ACT_LIF && g.Y2) SAPCU_TC_LAUNCH(ACT_LIF, 2);
+  if (g.act == ACT_LIF && g.edge_bias) SAPCU_TC_LAUNCH(ACT_LIF, 2);
   else if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, 0);
   else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, 0);
   else if (g.residual) SAPCU_TC_LAUNCH(ACT_NONE, 1);

@@ -25,8 +25,11 @@ namespace sapcu {
 constexpr int T2_STAGES = 3;
 constexpr int T2_ACC = 2;                       // 2 x 256 TMEM columns
 constexpr int T2_BN = 256;                      // rows per pair tile (128 staged by each CTA)
-constexpr int T2_SPLIT_WARP0 = 2, T2_SPLIT_WARPS = 4;
-constexpr int T2_EPI_WARP0 = 6, T2_EPI = 16;
+#ifndef SAPCU_T2_SPLIT_WARPS
+#define SAPCU_T2_SPLIT_WARPS 2     // 2 + 2 + 16 warps = 640 threads: 96 registers per thread for the epilogue
+#endif
+constexpr int T2_SPLIT_WARP0 = 2, T2_SPLIT_WARPS = SAPCU_T2_SPLIT_WARPS;
+constexpr int T2_EPI_WARP0 = T2_SPLIT_WARP0 + T2_SPLIT_WARPS, T2_EPI = 16;
 constexpr int T2_THREADS = (T2_EPI_WARP0 + T2_EPI) * 32;
 constexpr uint32_t T2_STAGE_BYTES = 4 * TC_TILE_BYTES;          // W_hi, W_lo, X(raw = hi), X_lo : 64 KiB
 constexpr size_t T2_SMEM_BYTES = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 + 256;
@@ -237,6 +240,52 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             p.Y[pt * p.ldc + c] = res;
           }
         }
+      } else if (ACT == ACT_LIF) {
+        // 8 columns (= rows of Y) at a time: 24 state + 24 temporary registers leave ptxas room to interleave all 8
+        // recurrences (with 32 accumulators live it serialised half of them); the next piece is loaded under the math
+        const int colw = part * CHUNKS * 32;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T2_BN + colw);
+        float nxt[8];
+        __syncwarp();
+        tmem_ld_piece<8>(tbase, nxt);
+        int my_qo = 0, my_ko = 0, nx_qo = 0, nx_ko = 0;          // EXTRA == 2: this / the next 32-row group's offsets
+        float qv[8], kv[8];
+        if (EXTRA == 2) {                                         // edge bias W q_i - W k_j: operands of piece 0
+          edge_lane_offsets(p, n_t * T2_BN + colw, lane, my_qo, my_ko);
+          edge_fetch8(p, my_qo, my_ko, 0, c, qv, kv);
+        }
+#pragma unroll 1
+        for (int pc = 0; pc < CHUNKS * 4; ++pc) {
+          float u[8];
+          tmem_wait_ld8(nxt);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = nxt[j];
+          if (pc + 1 < CHUNKS * 4) tmem_ld_piece<8>(tbase + (uint32_t)((pc + 1) * 8), nxt);
+          const int64_t r0 = n_t * T2_BN + colw + pc * 8;
+          const int nrows = (int)((p.R - r0) < 8 ? (p.R - r0) : 8);
+          if (EXTRA == 2) {                                       // fold this piece's bias in, fetch the next one under the LIF
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] += qv[j] - kv[j];
+            if ((pc & 3) == 0 && pc + 4 < CHUNKS * 4) edge_lane_offsets(p, n_t * T2_BN + colw + (pc + 4) * 8, lane, nx_qo, nx_ko);
+            if (pc + 1 < CHUNKS * 4) {
+              if (((pc + 1) & 3) == 0) { my_qo = nx_qo; my_ko = nx_ko; }
+              edge_fetch8(p, my_qo, my_ko, (pc + 1) & 3, c, qv, kv);
+            }
+          }
+          if (nrows > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j] + bia, sc, sh);
+            lif_chain_vec_fast<8>(u, np, p.T);
+            float* yp = p.Y + r0 * p.ldc + c;
+            if (nrows == 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { *yp = u[j]; yp += p.ldc; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { if (j < nrows) *yp = u[j]; yp += p.ldc; }
+            }
+          }
+        }
       } else {
 #pragma unroll 1
       for (int ch = 0; ch < CHUNKS; ++ch) {
@@ -257,17 +306,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           if (ACT == ACT_LEAKY) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = act_leaky(v[j]);
-          }
-          if (ACT == ACT_LIF) {
-#pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 8) {
-              float u[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) u[j] = v[j0 + j];
-              lif_chain_vec_fast<8>(u, np, p.T);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j0 + j] = u[j];
-            }
           }
           float* yp = p.Y + r0 * p.ldc + c;
           if (nrows == 32) {
@@ -308,7 +346,7 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   GemmArgs base = g;
   base.at_pos = nullptr;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
-  if (g.N % 256 != 0 || g.Y2 != nullptr) return false;
+  if (g.N % 256 != 0) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
   if (g.R < 4096) return false;
   if (g.at_pos) {
@@ -323,7 +361,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
 #define SAPCU_T2_ATTR(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
+    SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LIF, 2, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
     SAPCU_T2_ATTR(ACT_NONE, 3, 12); SAPCU_T2_ATTR(ACT_NONE, 3, 18); SAPCU_T2_ATTR(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR
     attr_done = true;
@@ -343,7 +381,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
-  p.aq = nullptr; p.ak = nullptr; p.ldq = 0; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts; p.Y2 = nullptr;
+  p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
   p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
   p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;
@@ -353,6 +391,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   if (g.at_pos) {
     if (g.kk == 12) SAPCU_T2_LAUNCH(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH(ACT_NONE, 3, 24);
   }
+  else if (g.act == ACT_LIF && g.edge_bias) SAPCU_T2_LAUNCH(ACT_LIF, 2, 1);
   else if (g.act == ACT_LIF) SAPCU_T2_LAUNCH(ACT_LIF, 0, 1);
   else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH(ACT_LEAKY, 0, 1);
   else if (g.residual) SAPCU_T2_LAUNCH(ACT_NONE, 1, 1);

@@ -31,6 +31,19 @@ __device__ __forceinline__ float exp2f_approx(float x) {
   return y;
 }
 
+// ordered flavours: `volatile` keeps their relative program order, which pins the phase-major MUFU schedule of
+// lif_chain_vec_fast (ptxas otherwise re-serialises half of the elements)
+__device__ __forceinline__ float exp2f_approx_ord(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx_ord(float x) {
+  float y;
+  asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -162,15 +175,27 @@ __device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronP
   }
 #pragma unroll 1
   for (int t = 1; t < T; ++t) {
+    // phase-major over the NV elements: all EX2s are issued back to back, then all RCPs, so the MUFU pipe always
+    // has independent work queued instead of one element's EX2 -> FFMA -> RCP -> FFMA dependency chain
+    float mm[NV], g[NV], e[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float md = m[i] * p.d;
-      const float mm = fmaf(-md, rho[i], md);
-      const float v = mm - th[i];
-      const float g = exp2f_approx((k_g * v) * v);
-      const float e = exp2f_approx(k_s * v);
-      const float s = fmaf(c_g, g, SAPCU_LIF_RCP(fmaf(2.0f, e, 2.0f)));
-      m[i] = fmaf(-mm, s, mm);
+      mm[i] = fmaf(-md, rho[i], md);
+      const float v = mm[i] - th[i];
+      g[i] = (k_g * v) * v;
+      e[i] = k_s * v;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) e[i] = exp2f_approx_ord(e[i]);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) g[i] = exp2f_approx_ord(g[i]);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) e[i] = rcp_approx_ord(fmaf(2.0f, e[i], 2.0f));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float s = fmaf(c_g, g[i], e[i]);
+      m[i] = fmaf(-mm[i], s, mm[i]);
       rho[i] = fmaf(rho[i], p.r, s);
       th[i] = fmaf(0.95f, th[i], fmaf(a95, s, c05));
       u[i] = s;

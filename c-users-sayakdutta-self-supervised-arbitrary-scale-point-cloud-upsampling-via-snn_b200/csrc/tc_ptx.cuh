@@ -132,6 +132,12 @@ template <> __device__ __forceinline__ void tmem_ld_piece<16>(uint32_t taddr, fl
 #pragma unroll
   for (int i = 0; i < 16; ++i) dst[i] = __uint_as_float(r[i]);
 }
+// tcgen05.wait::ld that also "produces" the 8 registers of a pending tmem_ld_piece<8>, so no use of them can be
+// scheduled ahead of the wait (lets the load of the next piece fly under the arithmetic on the current one)
+__device__ __forceinline__ void tmem_wait_ld8(float (&x)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(x[0]), "+f"(x[1]), "+f"(x[2]), "+f"(x[3]), "+f"(x[4]), "+f"(x[5]), "+f"(x[6]), "+f"(x[7])::"memory");
+}
 // KK columns (KK <= 31) as a sum of power-of-two pieces, then one tcgen05.wait::ld
 template <int KK> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[KK]) {
   int o = 0;
@@ -167,8 +173,9 @@ struct TcParams {
   int act, T; const float* nparams;
   const float* residual; int64_t ldr;
   float* Y; int64_t ldc;
-  // EXTRA == 2 (fn fc_delta2): second output Y2[e,c] = (aq[pt,c] - ak[nb,c]) + Y[e,c], the attention input q_i - k_j + pos_ij
-  const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts; float* Y2;
+  // EXTRA == 2 (fn fc_gamma on the factorised attention input): row e = pt*kk + j of the activation is pos_ij only, and
+  // the epilogue adds aq[pt,c] - ak[nb,c] (= W q_i - W k_j, per-POINT products) to the accumulator before the affine
+  const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts;
   // EXTRA == 3 (fn fc_gamma2, 2-CTA kernel): the epilogue applies softmax over the kk edges of a point to the logits
   // (/ at_sqrt) and writes Y[pt,c] = sum_j a_j (at_v[nb_j,c] + at_pos[e_j,c]) instead of the logits
   const float* at_pos; const float* at_v; int64_t at_ldv; float at_sqrt;
@@ -180,6 +187,31 @@ struct TcParams {
   int raw_hi;                 // 1: leave the raw X tile as the hi operand (tensor core ignores the low 13 bits), lo by truncation
   int* err;
 };
+
+// Edge bias operands (EXTRA == 2).  The row -> (point, neighbour) resolution is the same for every lane of a warp, so it
+// is done once per 32 rows with lane L resolving row e0 + L (rows past the end re-use the last row; offsets fit 32 bits,
+// checked on the host): qo = pt * ldq, ko = nb * ldq.
+__device__ __forceinline__ void edge_lane_offsets(const TcParams& p, int64_t e0, int lane, int& qo, int& ko) {
+  int64_t e64 = e0 + lane;
+  if (e64 > p.R - 1) e64 = p.R - 1;
+  const uint32_t e = (uint32_t)e64;
+  const uint32_t pt = e / (uint32_t)p.kk, j = e - pt * (uint32_t)p.kk;
+  const uint32_t patch0 = (pt / (uint32_t)p.Mpts) * (uint32_t)p.Mpts;
+  const int nb = (int)patch0 + p.idx[(int64_t)pt * p.ldi + j];
+  qo = (int)pt * (int)p.ldq; ko = nb * (int)p.ldq;
+}
+// qv[r] = aq[pt_r, c], kv[r] = ak[nb_r, c] for rows 8*sub .. 8*sub+7 of the warp's current 32-row group: 16 independent
+// loads, consumed by the caller only after its arithmetic on the previous piece (which hides their latency)
+__device__ __forceinline__ void edge_fetch8(const TcParams& p, int my_qo, int my_ko, int sub, int c, float (&qv)[8], float (&kv)[8]) {
+  const float* aq = p.aq + c;
+  const float* ak = p.ak + c;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int qo = __shfl_sync(0xffffffffu, my_qo, sub * 8 + r), ko = __shfl_sync(0xffffffffu, my_ko, sub * 8 + r);
+    qv[r] = aq[qo]; kv[r] = ak[ko];
+  }
+}
+
 
 // host helpers (gemm_tc.cu)
 int tc_make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows);
