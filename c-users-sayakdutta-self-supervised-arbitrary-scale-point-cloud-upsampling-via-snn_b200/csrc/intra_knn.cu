@@ -6,21 +6,32 @@
 // over the channels in ascending order), then each row's top-k is extracted by a warp with the
 // deterministic tie-break "larger score first, then lower index".  Works for xyz (C=3) and for the
 // feature-space graphs of fd blocks 1..3 (C=64/128/256, rows `ld` floats apart).
-// Roofline: shared-memory / FP32 bound; HBM traffic M*C*4 B in, M*k*4 B out per patch.
+//   * <f_i, f_j> is bitwise symmetric (same products, same order), so only the 4x4 register blocks on or above the
+//     diagonal are accumulated (325 of 625 for M = 100) and each feeds both score[i][j] and score[j][i];
+//   * top-k: scores become order-preserving 32-bit keys; per extraction one REDUX.MAX finds the best key in the warp and
+//     one REDUX.MIN the lowest index holding it -- ~20 instructions instead of a 5-round shuffle tournament.
+// Roofline: shared-memory / issue bound; HBM traffic M*C*4 B in, M*k*4 B out per patch.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace sapcu {
 
-constexpr int IK_THREADS = 256;
+constexpr int IK_THREADS = 352;
+constexpr int IK_ROUNDS = 2;  // upper-triangular 4x4 blocks per thread: nb(nb+1)/2 <= 704 covers M <= 128
 constexpr int IK_MMAX = 128;
 constexpr int IK_CC = 64;     // channel chunk staged in shared memory
+
+__device__ __forceinline__ uint32_t ik_key(float x) {     // monotone float -> uint32 (larger score = larger key)
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
 
 __global__ void __launch_bounds__(IK_THREADS)
 intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k, int32_t* __restrict__ out) {
   extern __shared__ float sm[];
   const int nb = (M + 3) >> 2;          // 4x4 blocks per side
   const int Mp = nb * 4;
+  const int nblk = nb * (nb + 1) / 2;   // blocks with bi <= bj
   const int cc_max = C < IK_CC ? C : IK_CC;
   const int fs = cc_max + 1;            // padded row stride of the staged chunk
   float* fsm = sm;                      // [Mp][fs]
@@ -29,9 +40,19 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
   const int tid = threadIdx.x;
   const float* base = feat + (int64_t)blockIdx.x * M * ld;
 
-  float acc[3][4][4];
+  // block id -> (bi, bj), row-major over the upper triangle: row bi starts at bi*nb - bi(bi-1)/2
+  int tbi[IK_ROUNDS], tbj[IK_ROUNDS];
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+  for (int r = 0; r < IK_ROUNDS; ++r) {
+    const int b = tid + r * IK_THREADS;
+    int bi = 0, start = 0;
+    while (bi + 1 < nb && start + (nb - bi) <= b) { start += nb - bi; ++bi; }
+    tbi[r] = bi; tbj[r] = bi + (b - start);
+  }
+
+  float acc[IK_ROUNDS][4][4];
+#pragma unroll
+  for (int r = 0; r < IK_ROUNDS; ++r)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -49,14 +70,12 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
       for (int c = 0; c < cc; ++c) { const float v = fsm[tid * fs + c]; myxx = __fadd_rn(myxx, __fmul_rn(v, v)); }
     }
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int b = tid + r * IK_THREADS;
-      if (b < nb * nb) {
-        // block (bi, bj) owns rows {bi + nb*i} x {bj + nb*j}: consecutive lanes read consecutive rows (stride fs = odd
-        // number of words) -> conflict-free shared-memory loads
-        const int bi = b / nb, bj = b - bi * nb;
-        const float* fa = fsm + bi * fs;
-        const float* fb = fsm + bj * fs;
+    for (int r = 0; r < IK_ROUNDS; ++r) {
+      if (tid + r * IK_THREADS < nblk) {
+        // block (bi, bj) owns rows {bi + nb*i} x {bj + nb*j}: lanes of a warp share bi (broadcast) and walk consecutive bj
+        // (row stride fs = odd number of words) -> conflict-free shared-memory loads
+        const float* fa = fsm + tbi[r] * fs;
+        const float* fb = fsm + tbj[r] * fs;
         const int rs = nb * fs;
         for (int c = 0; c < cc; ++c) {
           float a[4], bb[4];
@@ -74,10 +93,9 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
   __syncthreads();
   const int ss = M + 1;
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int b = tid + r * IK_THREADS;
-    if (b < nb * nb) {
-      const int bi = b / nb, bj = b - bi * nb;
+  for (int r = 0; r < IK_ROUNDS; ++r) {
+    if (tid + r * IK_THREADS < nblk) {
+      const int bi = tbi[r], bj = tbj[r];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -86,33 +104,38 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
           if (gi < M && gj < M) {
             const float inner = __fmul_rn(-2.0f, acc[r][i][j]);
             sc[gi * ss + gj] = __fsub_rn(__fsub_rn(-xx[gj], inner), xx[gi]);
+            if (bi != bj) sc[gj * ss + gi] = __fsub_rn(__fsub_rn(-xx[gi], inner), xx[gj]);
           }
         }
     }
   }
   __syncthreads();
-  // top-k per row: one warp per row
+  // top-k per row: one warp per row, 4 candidates per lane (j = lane + 32 q)
   const int warp = tid >> 5, lane = tid & 31;
   int32_t* o = out + (int64_t)blockIdx.x * M * k;
   for (int i = warp; i < M; i += IK_THREADS / 32) {
-    float v[4];
+    uint32_t key[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const int j = lane + 32 * q; v[q] = (j < M) ? sc[i * ss + j] : -INFINITY; }
+    for (int q = 0; q < 4; ++q) { const int j = lane + 32 * q; key[q] = (j < M) ? ik_key(__fadd_rn(sc[i * ss + j], 0.0f)) : 0u; }   // (-0 -> +0: equal scores, equal keys)
+    uint32_t bk = key[0]; int bq = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) if (key[q] > bk) { bk = key[q]; bq = q; }
+    int res = 0;
     for (int t = 0; t < k; ++t) {
-      float bv = v[0]; int bj = lane;
+      const uint32_t best = __reduce_max_sync(0xffffffffu, bk);
+      const uint32_t w = __reduce_min_sync(0xffffffffu, bk == best ? (uint32_t)(lane + 32 * bq) : 0xffffffffu);
+      if ((t & 31) == lane) res = (int)w;
+      if ((int)(w & 31u) == lane) {                       // the owner retires the winner and rescans its 4 candidates
+        const int wq = (int)(w >> 5);
 #pragma unroll
-      for (int q = 1; q < 4; ++q) if (v[q] > bv) { bv = v[q]; bj = lane + 32 * q; }
+        for (int q = 0; q < 4; ++q) if (wq == q) key[q] = 0u;
+        bk = key[0]; bq = 0;
 #pragma unroll
-      for (int off = 16; off; off >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-        if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+        for (int q = 1; q < 4; ++q) if (key[q] > bk) { bk = key[q]; bq = q; }
       }
-      if ((bj & 31) == lane) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if ((bj >> 5) == q) v[q] = -INFINITY;
+      if ((t & 31) == 31 || t == k - 1) {                 // coalesced store of up to 32 results
+        if (lane <= (t & 31)) o[i * k + (t & ~31) + lane] = res;
       }
-      if (lane == 0) o[i * k + t] = bj;
     }
   }
 }
@@ -126,7 +149,7 @@ static size_t intra_knn_smem(int M, int C) {
 int launch_intra_knn(const float* feat, int64_t ld, int64_t S, int M, int C, int k, int32_t* idx, cudaStream_t st) {
   SAPCU_REQUIRE(M >= 1 && M <= IK_MMAX, "intra_knn: M=%d outside [1,%d]", M, IK_MMAX);
   SAPCU_REQUIRE(k >= 1 && k <= M, "intra_knn: k=%d outside [1,M=%d]", k, M);
-  SAPCU_REQUIRE(((M + 3) / 4) * ((M + 3) / 4) <= 3 * IK_THREADS, "intra_knn: M too large");
+  SAPCU_REQUIRE(((M + 3) / 4) * ((M + 3) / 4 + 1) / 2 <= IK_ROUNDS * IK_THREADS, "intra_knn: M too large");
   if (S == 0) return 0;
   const size_t smem = intra_knn_smem(M, C);
   static bool attr_done = false;
