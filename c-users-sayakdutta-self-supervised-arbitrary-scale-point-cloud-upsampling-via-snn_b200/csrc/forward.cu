@@ -247,8 +247,24 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
     SAPCU_TRY(launch_neuron_unroll(b == 0, precise, U[b], cout[b], P, cout[b], T, f.blk[b + 1].np, f.blk[b + 1].ep, 1,
                                    p.SPK + off_out[b], 960, st));
   }
-  SAPCU_TRY(g.layer(f.msc, p.SPK, 960, P * T, p.AGG, f.emb, ACT_LEAKY));
-  SAPCU_TRY(launch_group_max(p.AGG, s, M, T, f.emb, p.POOL, st));
+  {
+    // conv5 (multi-scale fusion) + LeakyReLU + max over the patch's points: in the tensor-core modes the 2-CTA kernel
+    // reduces in its epilogue (per-thread running maxima, then float atomic max) and AGG is never written
+    GemmArgs a;
+    const Layer& L = f.msc;
+    a.A = p.SPK; a.lda = 960; a.R = P * T; a.K = L.K; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = L.N;
+    a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LEAKY; a.Y = p.AGG; a.ldc = f.emb;
+    a.pool = p.POOL; a.pool_T = T; a.pool_M = M;
+    static const bool fuse_pool = !(getenv("SAPCU_TC_FUSE_POOL") && atoi(getenv("SAPCU_TC_FUSE_POOL")) == 0);
+    if (mode != SAPCU_MODE_FP32 && fuse_pool && gemm_tc2_supported(a, A_PLAIN)) {
+      SAPCU_TRY(launch_fill(p.POOL, s * T * f.emb, -INFINITY, st));
+      SAPCU_TRY(g.run(a, A_PLAIN));
+    } else {
+      a.pool = nullptr;
+      SAPCU_TRY(g.run(a, A_PLAIN));
+      SAPCU_TRY(launch_group_max(p.AGG, s, M, T, f.emb, p.POOL, st));
+    }
+  }
   SAPCU_TRY(launch_temporal_lif(precise, p.POOL, s, T, f.emb, f.tw, f.snn_fc.np, p.Z, st));
   // StandardDistanceDecoder
   SAPCU_TRY(g.layer(f.fc_in, p.Z, f.emb, s, p.D0, 256, ACT_GELU));

@@ -359,7 +359,7 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if (g.group != 0) return false;                                  // row-group max stays on the SIMT engine
   if (g.act == ACT_GELU) return false;                             // decoder MLPs (rows = patches) stay on the SIMT engine
   if (g.residual && g.act != ACT_NONE) return false;
-  if (g.at_pos) return false;                                      // fused attention epilogue: 2-CTA kernel only
+  if (g.at_pos || g.pool) return false;                                      // fused attention epilogue: 2-CTA kernel only
   if (g.edge_bias && (g.act != ACT_LIF || (g.N % 128) != 0 || !g.Q || !g.Kf || !g.idx || g.kk < 1 || g.Mpts < 1)) return false;
   if (g.edge_bias && (g.R / g.kk + g.Mpts) * g.ldq >= ((int64_t)1 << 31)) return false;     // 32-bit gather offsets
   if (g.R >= ((int64_t)1 << 31) || g.N > (1 << 20)) return false;
@@ -403,7 +403,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, bn); p.err = err;
-  p.at_pos = nullptr; p.at_v = nullptr; p.at_ldv = 0; p.at_sqrt = 1.0f; p.tile_rows = bn;
+  p.pool = nullptr; p.pool_T = 0; p.pool_rows = 0; p.at_pos = nullptr; p.at_v = nullptr; p.at_ldv = 0; p.at_sqrt = 1.0f; p.tile_rows = bn;
   p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);

@@ -287,6 +287,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
         }
       } else {
+      float mx[8];                                            // EXTRA == 4: running max per step t of patch mx_patch
+      int64_t mx_patch = -1;
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8) mx[q8] = -INFINITY;
+      auto pool_flush = [&]() {
+        if (mx_patch >= 0) {
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8)
+            if (q8 < p.pool_T && mx[q8] > -INFINITY) atomic_max_float(p.pool + (mx_patch * p.pool_T + q8) * p.N + c, mx[q8]);
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) mx[q8] = -INFINITY;
+      };
 #pragma unroll 1
       for (int ch = 0; ch < CHUNKS; ++ch) {
         const int col0 = (part * CHUNKS + ch) * 32;
@@ -307,6 +320,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = act_leaky(v[j]);
           }
+          if (EXTRA == 4) {
+            const int64_t patch = r0 / p.pool_rows;
+            const int64_t prow = r0 - patch * p.pool_rows;
+            const int lim1 = (int)((p.pool_rows - prow) < nrows ? (p.pool_rows - prow) : nrows);   // rows still in `patch`
+            if (patch != mx_patch) { pool_flush(); mx_patch = patch; }
+            int tt = (int)(prow % p.pool_T);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < lim1) {
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) if (q8 == tt) mx[q8] = fmaxf(mx[q8], v[j]);
+              }
+              tt = (tt + 1 == p.pool_T) ? 0 : tt + 1;
+            }
+            if (lim1 < nrows) {                                 // the chunk straddles a patch boundary (pool_rows % T == 0)
+              pool_flush(); mx_patch = patch + 1;
+              tt = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j >= lim1 && j < nrows) {
+#pragma unroll
+                  for (int q8 = 0; q8 < 8; ++q8) if (q8 == tt) mx[q8] = fmaxf(mx[q8], v[j]);
+                  tt = (tt + 1 == p.pool_T) ? 0 : tt + 1;
+                }
+              }
+            }
+          } else {
           float* yp = p.Y + r0 * p.ldc + c;
           if (nrows == 32) {
 #pragma unroll
@@ -315,8 +355,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) { if (j < nrows) *yp = v[j]; yp += p.ldc; }
           }
+          }
         }
       }
+      if (EXTRA == 4) pool_flush();
       }
       tc_fence_before();
       __syncwarp();
@@ -332,6 +374,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   }
 }
 
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int launch_fill(float* p, int64_t n, float v, cudaStream_t st) {
+  if (n <= 0) return 0;
+  fill_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(p, n, v);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int fused_tile_rows(int kk) {        // largest multiple of lcm(kk, 16) not above 256, for the instantiated kk
   if (kk == 12 || kk == 24) return 240;
@@ -344,11 +397,15 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   if (enabled < 0) { const char* e = getenv("SAPCU_TC_2CTA"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
   if (fuse < 0) { const char* e = getenv("SAPCU_TC_FUSE_ATTNOUT"); fuse = (e && atoi(e) == 0) ? 0 : 1; }
   GemmArgs base = g;
-  base.at_pos = nullptr;
+  base.at_pos = nullptr; base.pool = nullptr;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
   if (g.N % 256 != 0) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
   if (g.R < 4096) return false;
+  if (g.pool) {
+    if (g.at_pos || g.residual || g.edge_bias || g.act != ACT_LEAKY || g.pool_T < 1 || g.pool_T > 8 || g.pool_M < 1) return false;
+    if (g.R % ((int64_t)g.pool_T * g.pool_M) != 0) return false;
+  }
   if (g.at_pos) {
     if (!fuse || g.act != ACT_NONE || g.residual || !g.at_v || !g.idx || fused_tile_rows(g.kk) == 0) return false;
     if (g.R % g.kk != 0) return false;
@@ -361,7 +418,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
 #define SAPCU_T2_ATTR(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LIF, 2, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
+    SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LIF, 2, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
     SAPCU_T2_ATTR(ACT_NONE, 3, 12); SAPCU_T2_ATTR(ACT_NONE, 3, 18); SAPCU_T2_ATTR(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR
     attr_done = true;
@@ -382,6 +439,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
+  p.pool = g.pool; p.pool_T = g.pool_T; p.pool_rows = (int64_t)g.pool_T * g.pool_M;
   p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
   p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;
@@ -393,6 +451,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   }
   else if (g.act == ACT_LIF && g.edge_bias) SAPCU_T2_LAUNCH(ACT_LIF, 2, 1);
   else if (g.act == ACT_LIF) SAPCU_T2_LAUNCH(ACT_LIF, 0, 1);
+  else if (g.act == ACT_LEAKY && g.pool) SAPCU_T2_LAUNCH(ACT_LEAKY, 4, 1);
   else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH(ACT_LEAKY, 0, 1);
   else if (g.residual) SAPCU_T2_LAUNCH(ACT_NONE, 1, 1);
   else SAPCU_T2_LAUNCH(ACT_NONE, 0, 1);

@@ -25,6 +25,7 @@ int launch_attn_out(bool precise, const float* logits, const float* pos, const f
                     cudaStream_t st);
 int launch_attn_in(const float* Q, const float* Kf, int64_t ldq, const float* pos, const int32_t* idx, int ldi, int kk,
                    int Mpts, int64_t E, int D, float* out, cudaStream_t st);
+int launch_fill(float* p, int64_t n, float v, cudaStream_t st);
 int launch_group_max(const float* X, int64_t S, int M, int Tt, int C, float* out, cudaStream_t st);
 int launch_fn_head(const float* H, int K, int64_t S, const float* W, const float* b, const float* lnw,
                    const float* lnb, float* out, cudaStream_t st);

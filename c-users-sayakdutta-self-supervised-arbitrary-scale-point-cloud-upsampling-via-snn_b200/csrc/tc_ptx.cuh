@@ -134,6 +134,11 @@ template <> __device__ __forceinline__ void tmem_ld_piece<16>(uint32_t taddr, fl
 }
 // tcgen05.wait::ld that also "produces" the 8 registers of a pending tmem_ld_piece<8>, so no use of them can be
 // scheduled ahead of the wait (lets the load of the next piece fly under the arithmetic on the current one)
+// float atomic max through the integer ALU of the L2 (exact, order-independent); *addr starts at -inf
+__device__ __forceinline__ void atomic_max_float(float* addr, float x) {
+  if (x >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(x));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(x));
+}
 __device__ __forceinline__ void tmem_wait_ld8(float (&x)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+f"(x[0]), "+f"(x[1]), "+f"(x[2]), "+f"(x[3]), "+f"(x[4]), "+f"(x[5]), "+f"(x[6]), "+f"(x[7])::"memory");
@@ -179,6 +184,9 @@ struct TcParams {
   // EXTRA == 3 (fn fc_gamma2, 2-CTA kernel): the epilogue applies softmax over the kk edges of a point to the logits
   // (/ at_sqrt) and writes Y[pt,c] = sum_j a_j (at_v[nb_j,c] + at_pos[e_j,c]) instead of the logits
   const float* at_pos; const float* at_v; int64_t at_ldv; float at_sqrt;
+  // EXTRA == 4 (fd conv5, 2-CTA kernel): rows are (point*T + t); the epilogue keeps one running maximum per step and
+  // merges them into pool[(patch*T + t), c] with float atomic max -- the [P*T, N] activation never reaches HBM
+  float* pool; int pool_T; int64_t pool_rows;     // pool_rows = points per patch * T
   int tile_rows;              // activation rows per tile (UMMA N); a multiple of kk when EXTRA == 3
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
