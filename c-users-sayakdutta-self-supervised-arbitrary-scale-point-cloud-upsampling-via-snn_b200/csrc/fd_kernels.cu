@@ -58,54 +58,66 @@ __global__ void fd_block0_kernel(const Block0Args a) {
 // followed by the block's T-step EIF/LIF recurrence, every step's spike written into the [point, t, 960] spike
 // tensor (no HBM round trip between the max-pool and the recurrence).
 constexpr int EGU_PTS = 4;     // points processed together per thread (ILP for the recurrence)
+constexpr int EGU_THREADS = 256;  // 128 channels x 2 halves of the patch's points (occupancy: the kernel is latency-bound)
 template <bool EIF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(EGU_THREADS)
 edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __restrict__ idx, int kk, int Mpts,
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ np, const float* __restrict__ ep, int T,
                           float* __restrict__ U, float* __restrict__ spk, int64_t ldspk_row, int ldo) {
   extern __shared__ float egs[];
-  float* Ps = egs;                                        // [Mpts][128]
-  int* nbs = reinterpret_cast<int*>(egs + Mpts * 128);    // [Mpts][kk]
+  float* Ps = egs;                                                 // [Mpts][128]
+  uint8_t* nbs = reinterpret_cast<uint8_t*>(egs + Mpts * 128);     // [Mpts][kk] local neighbour indices (Mpts <= 256)
+  const int tx = threadIdx.x & 127, half = threadIdx.x >> 7;
   const int64_t patch0 = (int64_t)blockIdx.x * Mpts;
-  const int c = blockIdx.y * 128 + threadIdx.x;           // C is a multiple of 128
-  for (int m = 0; m < Mpts; ++m) Ps[m * 128 + threadIdx.x] = PQ[(patch0 + m) * 2 * C + c];
-  for (int e = threadIdx.x; e < Mpts * kk; e += 128) nbs[e] = idx[patch0 * kk + e];
+  const int c = blockIdx.y * 128 + tx;                             // C is a multiple of 128
+  for (int m = half; m < Mpts; m += 2) Ps[m * 128 + tx] = PQ[(patch0 + m) * 2 * C + c];
+  for (int e = threadIdx.x; e < Mpts * kk; e += EGU_THREADS) nbs[e] = (uint8_t)idx[patch0 * kk + e];
   __syncthreads();
   const float sc = scale[c], sh = shift[c];
   const NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
   EifParams q{1.0f, 1.0f};
   if (EIF) { q.dT = ep[c]; q.thrh = ep[C + c]; }
   const FastNeuronK k = fast_neuron_k(p, q);
-  for (int i0 = 0; i0 < Mpts; i0 += EGU_PTS) {
+  const int mh = (Mpts + 1) >> 1;
+  const int i_begin = half * mh, i_end = half ? Mpts : mh;
+  const float* Pc = Ps + tx;
+  for (int i0 = i_begin; i0 < i_end; i0 += EGU_PTS) {
     float u[EGU_PTS], m[EGU_PTS], th[EGU_PTS], rho[EGU_PTS];
 #pragma unroll
     for (int a = 0; a < EGU_PTS; ++a) {
-      const int i = min(i0 + a, Mpts - 1);
+      const int i = min(i0 + a, i_end - 1);
       const float qv = PQ[(patch0 + i) * 2 * C + C + c];
-      float mx = -INFINITY;
-      for (int j = 0; j < kk; ++j) mx = fmaxf(mx, Ps[nbs[i * kk + j] * 128 + threadIdx.x]);
-      // LeakyReLU(scale*(P-Q)+shift) is monotone in P for scale >= 0 and antitone otherwise: take max or min of P
-      if (sc < 0.0f) {
-        float mn = INFINITY;
-        for (int j = 0; j < kk; ++j) mn = fminf(mn, Ps[nbs[i * kk + j] * 128 + threadIdx.x]);
-        mx = mn;
+      // LeakyReLU(scale*(P-Q)+shift) is monotone in P for scale >= 0 and antitone otherwise: the max over the
+      // neighbours is reached at max P or min P; both are tracked in one pass over the (byte-packed) graph row
+      float mx = -INFINITY, mn = INFINITY;
+      const uint8_t* nr = nbs + i * kk;
+      if ((kk & 3) == 0) {
+        const uint32_t* nw = reinterpret_cast<const uint32_t*>(nr);
+        for (int w = 0; w < (kk >> 2); ++w) {
+          const uint32_t v = nw[w];
+          const float p0 = Pc[(v & 255u) * 128], p1 = Pc[((v >> 8) & 255u) * 128], p2 = Pc[((v >> 16) & 255u) * 128], p3 = Pc[(v >> 24) * 128];
+          mx = fmaxf(fmaxf(mx, p0), fmaxf(p1, fmaxf(p2, p3)));
+          mn = fminf(fminf(mn, p0), fminf(p1, fminf(p2, p3)));
+        }
+      } else {
+        for (int j = 0; j < kk; ++j) { const float pv = Pc[nr[j] * 128]; mx = fmaxf(mx, pv); mn = fminf(mn, pv); }
       }
-      u[a] = act_leaky(fmaf(mx - qv, sc, sh));
-      if (i0 + a < Mpts) U[(patch0 + i) * C + c] = u[a];
+      u[a] = act_leaky(fmaf((sc < 0.0f ? mn : mx) - qv, sc, sh));
+      if (i0 + a < i_end) U[(patch0 + i) * C + c] = u[a];
     }
     float s[EGU_PTS];
 #pragma unroll
     for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, true>(u[a], m[a], th[a], rho[a], k);
 #pragma unroll
     for (int a = 0; a < EGU_PTS; ++a)
-      if (i0 + a < Mpts) spk[(patch0 + i0 + a) * ldspk_row + c] = s[a];
+      if (i0 + a < i_end) spk[(patch0 + i0 + a) * ldspk_row + c] = s[a];
     for (int t = 1; t < T; ++t) {
 #pragma unroll
       for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, false>(0.0f, m[a], th[a], rho[a], k);
 #pragma unroll
       for (int a = 0; a < EGU_PTS; ++a)
-        if (i0 + a < Mpts) spk[(patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c] = s[a];
+        if (i0 + a < i_end) spk[(patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c] = s[a];
     }
   }
 }
@@ -114,8 +126,9 @@ int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* i
                               const float* scale, const float* shift, const float* np, const float* ep, int T, float* U,
                               float* spk, int64_t ldspk_row, int ldo, cudaStream_t st) {
   SAPCU_REQUIRE(C % 128 == 0, "edge_gather_unroll: C=%d must be a multiple of 128", C);
+  SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256, "edge_gather_unroll: M=%d outside [1,256]", Mpts);
   if (S == 0) return 0;
-  const size_t smem = sizeof(float) * ((size_t)Mpts * 128 + (size_t)Mpts * kk);
+  const size_t smem = sizeof(float) * (size_t)Mpts * 128 + (((size_t)Mpts * kk + 15) & ~(size_t)15);
   static bool attr_done = false;
   if (!attr_done) {
     SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_gather_unroll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -124,8 +137,8 @@ int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* i
   }
   SAPCU_REQUIRE(smem <= 160 * 1024, "edge_gather_unroll: patch too large for shared memory");
   dim3 grid((unsigned)S, (unsigned)(C / 128));
-  if (eif) edge_gather_unroll_kernel<true><<<grid, 128, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
-  else     edge_gather_unroll_kernel<false><<<grid, 128, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
+  if (eif) edge_gather_unroll_kernel<true><<<grid, EGU_THREADS, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
+  else     edge_gather_unroll_kernel<false><<<grid, EGU_THREADS, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

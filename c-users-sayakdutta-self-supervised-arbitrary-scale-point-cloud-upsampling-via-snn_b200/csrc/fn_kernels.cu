@@ -38,53 +38,77 @@ __global__ void pointwise3_lif_kernel(const float* __restrict__ xyz, const int32
   out[e] = lif_chain<PRECISE>(y, p, T);
 }
 
-// fc_delta on edge offsets + BN + LIF^T for a tile of EPB edges x 128 channels per CTA: the per-edge index
-// arithmetic is done once per edge (not per element), the per-channel parameters live in registers and the
-// T-step recurrence runs on 8 interleaved edges per thread (MUFU-bound instead of latency-bound).
-constexpr int EPB = 64;
+// fc_delta on edge offsets + BN + LIF^T.  One CTA = one patch x 128 channels: the patch's coordinates and graph are
+// staged in shared memory once, the per-channel parameters live in registers, and the CTA walks the patch's Mpts*kk
+// edges in groups of EPL_G: the offsets xyz_i - xyz_j of the NEXT group are written to the other half of a double
+// buffer before the T-step recurrence of the current one (8 interleaved edges per thread), so the single barrier per
+// group never waits on memory and the MUFU pipe stays fed.
+constexpr int EPL_G = 72;     // = 6 x 12 = 4 x 18 = 3 x 24 edges; a multiple of the 8-edge vector
 template <bool PRECISE>
 __global__ void __launch_bounds__(128)
-edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts,
-                    int E, int C, const float* __restrict__ W, const float* __restrict__ bias,
-                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ np,
-                    int T, float* __restrict__ out) {
-  __shared__ float pd[EPB][3];
-  const int e0 = blockIdx.x * EPB;
-  for (int i = threadIdx.x; i < EPB; i += blockDim.x) {
-    const int e = e0 + i;
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-    if (e < E) {
-      const int pt = e / kk;
-      const int j = e - pt * kk;
-      const int nb = (pt / Mpts) * Mpts + idx[(int64_t)pt * ldi + j];
-      d0 = __fsub_rn(xyz[3 * (int64_t)pt], xyz[3 * (int64_t)nb]);
-      d1 = __fsub_rn(xyz[3 * (int64_t)pt + 1], xyz[3 * (int64_t)nb + 1]);
-      d2 = __fsub_rn(xyz[3 * (int64_t)pt + 2], xyz[3 * (int64_t)nb + 2]);
-    }
-    pd[i][0] = d0; pd[i][1] = d1; pd[i][2] = d2;
-  }
+edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts, int C,
+                    const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ np, int T, float* __restrict__ out) {
+  extern __shared__ float esm[];
+  float* xs = esm;                                              // [Mpts][3]
+  float* pd = xs + 3 * Mpts;                                    // [2][EPL_G][3]
+  uint8_t* nbs = reinterpret_cast<uint8_t*>(pd + 2 * EPL_G * 3);  // [Mpts][kk] local neighbour indices (Mpts <= 256)
+  const int tid = threadIdx.x;
+  const int64_t patch0 = (int64_t)blockIdx.x * Mpts;
+  for (int i = tid; i < 3 * Mpts; i += 128) xs[i] = xyz[3 * patch0 + i];
+  for (int pt = tid >> 5; pt < Mpts; pt += 4)
+    for (int j = tid & 31; j < kk; j += 32) nbs[pt * kk + j] = (uint8_t)idx[(patch0 + pt) * ldi + j];
   __syncthreads();
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= C) return;
-  const float w0 = W[3 * c], w1 = W[3 * c + 1], w2 = W[3 * c + 2];
-  const float bi = bias[c], sc = scale[c], sh = shift[c];
-  const NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
-  float* o = out + (int64_t)e0 * C + c;
-  const int n = (E - e0) < EPB ? (E - e0) : EPB;
-#pragma unroll 1
-  for (int g = 0; g < EPB; g += 8) {
-    if (g >= n) break;
-    float u[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = fmaf(w2, pd[g + j][2], fmaf(w1, pd[g + j][1], __fmul_rn(w0, pd[g + j][0])));
-      y = __fadd_rn(y, bi);
-      u[j] = __fadd_rn(__fmul_rn(y, sc), sh);
+  const int EP = Mpts * kk;
+  const int G = (EP + EPL_G - 1) / EPL_G;
+  auto stage = [&](int g, int buf) {
+    const int e = g * EPL_G + tid;
+    if (tid < EPL_G) {
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      if (e < EP) {
+        const int pt = e / kk;
+        const int nb = nbs[e];
+        d0 = __fsub_rn(xs[3 * pt], xs[3 * nb]);
+        d1 = __fsub_rn(xs[3 * pt + 1], xs[3 * nb + 1]);
+        d2 = __fsub_rn(xs[3 * pt + 2], xs[3 * nb + 2]);
+      }
+      float* q = pd + (buf * EPL_G + tid) * 3;
+      q[0] = d0; q[1] = d1; q[2] = d2;
     }
-    lif_chain_vec<8, PRECISE>(u, p, T);
+  };
+  stage(0, 0);
+  __syncthreads();
+  const int c = blockIdx.y * 128 + tid;
+  const bool cv = c < C;
+  const int cc = cv ? c : 0;
+  const float w0 = W[3 * cc], w1 = W[3 * cc + 1], w2 = W[3 * cc + 2];
+  const float bi = bias[cc], sc = scale[cc], sh = shift[cc];
+  const NeuronParams p{np[cc], np[C + cc], np[2 * C + cc], np[3 * C + cc]};
+  float* o = out + patch0 * kk * (int64_t)C + c;
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    if (g + 1 < G) stage(g + 1, (g + 1) & 1);
+    const float* q = pd + (g & 1) * EPL_G * 3;
+    const int n = (EP - g * EPL_G) < EPL_G ? (EP - g * EPL_G) : EPL_G;
+    if (cv) {
+#pragma unroll 1
+      for (int h = 0; h < EPL_G; h += 8) {
+        if (h >= n) break;
+        float u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (g + j < n) o[(int64_t)(g + j) * C] = u[j];
+        for (int j = 0; j < 8; ++j) {
+          float y = fmaf(w2, q[(h + j) * 3 + 2], fmaf(w1, q[(h + j) * 3 + 1], __fmul_rn(w0, q[(h + j) * 3])));
+          y = __fadd_rn(y, bi);
+          u[j] = __fadd_rn(__fmul_rn(y, sc), sh);
+        }
+        lif_chain_vec<8, PRECISE>(u, p, T);
+        float* og = o + (int64_t)(g * EPL_G + h) * C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (h + j < n) og[(int64_t)j * C] = u[j];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -234,10 +258,12 @@ int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32
                           const float* shift, const float* np, int T, float* out, cudaStream_t st) {
   if (rows == 0) return 0;
   if (edge) {
-    SAPCU_REQUIRE(rows < ((int64_t)1 << 31), "pointwise3_lif: too many edges for 32-bit indexing");
-    dim3 grid((unsigned)ceil_div(rows, EPB), (unsigned)ceil_div(C, 128));
-    if (precise) edge_pos_lif_kernel<true><<<grid, 128, 0, st>>>(xyz, idx, kk, ldi, Mpts, (int)rows, C, W, bias, scale, shift, np, T, out);
-    else         edge_pos_lif_kernel<false><<<grid, 128, 0, st>>>(xyz, idx, kk, ldi, Mpts, (int)rows, C, W, bias, scale, shift, np, T, out);
+    SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256 && kk >= 1 && rows % ((int64_t)Mpts * kk) == 0, "pointwise3_lif: edge rows must be whole patches of <= 256 points");
+    const int64_t S = rows / ((int64_t)Mpts * kk);
+    const size_t smem = sizeof(float) * (3 * (size_t)Mpts + 2 * EPL_G * 3) + (size_t)Mpts * kk;
+    dim3 grid((unsigned)S, (unsigned)ceil_div(C, 128));
+    if (precise) edge_pos_lif_kernel<true><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out);
+    else         edge_pos_lif_kernel<false><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out);
   } else {
     const unsigned grid = (unsigned)ceil_div(rows * C, 256);
     if (precise) pointwise3_lif_kernel<false, true><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);

@@ -275,6 +275,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = act_leaky(v[j]);
         }
+        if (ACT == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = act_gelu(v[j]);
+        }
         if (ACT == ACT_LIF) {
 #pragma unroll
           for (int j0 = 0; j0 < 32; j0 += 8) {
@@ -357,7 +361,6 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if (g.R < 1024) return false;                                   // small row counts (decoder heads) stay on the SIMT engine
   if ((g.lda % 4) != 0 || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return false;
   if (g.group != 0) return false;                                  // row-group max stays on the SIMT engine
-  if (g.act == ACT_GELU) return false;                             // decoder MLPs (rows = patches) stay on the SIMT engine
   if (g.residual && g.act != ACT_NONE) return false;
   if (g.at_pos || g.pool) return false;                                      // fused attention epilogue: 2-CTA kernel only
   if (g.edge_bias && (g.act != ACT_LIF || (g.N % 128) != 0 || !g.Q || !g.Kf || !g.idx || g.kk < 1 || g.Mpts < 1)) return false;
@@ -372,7 +375,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   if (!attr_done) {
 #define SAPCU_TC_ATTR1(A, RS, E, B) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES))
 #define SAPCU_TC_ATTR(A, RS) SAPCU_TC_ATTR1(A, RS, 8, 128); SAPCU_TC_ATTR1(A, RS, 8, 256); SAPCU_TC_ATTR1(A, RS, 16, 128); SAPCU_TC_ATTR1(A, RS, 16, 256)
-    SAPCU_TC_ATTR(ACT_LIF, 0); SAPCU_TC_ATTR(ACT_LIF, 2); SAPCU_TC_ATTR(ACT_LEAKY, 0); SAPCU_TC_ATTR(ACT_NONE, 1); SAPCU_TC_ATTR(ACT_NONE, 0);
+    SAPCU_TC_ATTR(ACT_LIF, 0); SAPCU_TC_ATTR(ACT_LIF, 2); SAPCU_TC_ATTR(ACT_LEAKY, 0); SAPCU_TC_ATTR(ACT_GELU, 0); SAPCU_TC_ATTR(ACT_NONE, 1); SAPCU_TC_ATTR(ACT_NONE, 0);
 #undef SAPCU_TC_ATTR
 #undef SAPCU_TC_ATTR1
     attr_done = true;
@@ -418,6 +421,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   if (g.act == ACT_LIF && g.edge_bias) SAPCU_TC_LAUNCH(ACT_LIF, 2);
   else if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, 0);
   else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, 0);
+  else if (g.act == ACT_GELU) SAPCU_TC_LAUNCH(ACT_GELU, 0);
   else if (g.residual) SAPCU_TC_LAUNCH(ACT_NONE, 1);
   else SAPCU_TC_LAUNCH(ACT_NONE, 0);
 #undef SAPCU_TC_LAUNCH

@@ -399,7 +399,7 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   GemmArgs base = g;
   base.at_pos = nullptr; base.pool = nullptr;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
-  if (g.N % 256 != 0) return false;
+  if (g.N % 256 != 0 || g.act == ACT_GELU) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
   if (g.R < 4096) return false;
   if (g.pool) {
