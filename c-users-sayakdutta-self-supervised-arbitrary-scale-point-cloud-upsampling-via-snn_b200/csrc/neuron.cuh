@@ -148,6 +148,29 @@ __device__ __forceinline__ float lif_chain(float u, const NeuronParams& p, int T
   return s;
 }
 
+// Mixed reciprocal for the interleaved LIF chain: elements i with (i % 8) < SAPCU_LIF_RCP_FMA_N take the FMA-pipe Newton
+// reciprocal, the rest MUFU.RCP.  The recurrence needs 3 MUFU (8 pipe cycles each per warp) against 12 FP
+// instructions per element-step, so in principle moving a few reciprocals over rebalances the two pipes.  Measured on
+// B200 (same box, 8,192-seed step): N = 0: 272.6 ms, 2: 276.3, 4: 276.7, 5: 280.4 -- every extra instruction costs
+// under the board's power cap, so the default stays all-MUFU.
+#ifndef SAPCU_LIF_RCP_FMA_N
+#define SAPCU_LIF_RCP_FMA_N 0
+#endif
+template <int I>
+__device__ __forceinline__ float rcp_lif_mixed(float x) {
+  if ((I & 7) < SAPCU_LIF_RCP_FMA_N) return rcp_fma(fminf(x, 1e30f));
+  return rcp_approx(x);
+}
+template <int NV, int I = 0>
+struct RcpMixed {
+  static __device__ __forceinline__ void run(float (&e)[NV]) {
+    e[I] = rcp_lif_mixed<I>(fmaf(2.0f, e[I], 2.0f));
+    RcpMixed<NV, I + 1>::run(e);
+  }
+};
+template <int NV>
+struct RcpMixed<NV, NV> { static __device__ __forceinline__ void run(float (&)[NV]) {} };
+
 // LIF^T on NV independent accumulators of one channel (interleaved for ILP); fast-math flavour.
 // Algebraically identical to neuron_step, re-associated for the FMA pipe (12 FP + 3 MUFU per element-step):
 //   * the soft spike is > 0, so the refractory gate is open at step 0 only: later steps take no input
@@ -190,8 +213,7 @@ __device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronP
     for (int i = 0; i < NV; ++i) e[i] = exp2f_approx_ord(e[i]);
 #pragma unroll
     for (int i = 0; i < NV; ++i) g[i] = exp2f_approx_ord(g[i]);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) e[i] = rcp_approx_ord(fmaf(2.0f, e[i], 2.0f));
+    RcpMixed<NV>::run(e);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float s = fmaf(c_g, g[i], e[i]);
