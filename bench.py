@@ -73,35 +73,57 @@ def cpu_reference_rate(sd_fn, sd_fd, cloud, seeds, n_sample, steps=1, warmup=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock + throttle reasons sampled during the timed region: NVML in-process (every 20 ms), else nvidia-smi."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.handle))
+        bits = [0x8, 0x40, 0x20, 0x4]     # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        return [str(mhz), str(self.max_mhz)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if self.nvml is not None:
+                    self.samples.append(self._nvml_sample())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 6:
+                        self.samples.append(f)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in self.samples for n, v in zip(self.NAMES, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def run_reference(args):
@@ -243,6 +265,8 @@ def run_ours(args):
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s",
                          "traffic": traffic, "traffic_note": "dram read+write bytes summed over the contraction launches of ONE step (ncu, profiles/r01_gemm_traffic.json); achieved/kernel_ms are likewise per-step sums over the family",
+                         "executed_tflops": achieved_tf * (3 if mode == "tc" else 1),
+                         "executed_note": "tensor-core math actually issued: 3 tf32 passes per product in the parity mode (tf32 runs at half the bf16 rate, so frac <= 1/6 by construction)" if mode == "tc" else "one pass per product",
                          "kernel_ms_per_step": gms.value / args.steps, "kernel_launches_per_step": gn.value / args.steps,
                          "kernel_share_of_step": gms.value / max(ms, 1e-9), "algorithmic_gflop_per_step": gfl.value / args.steps / 1e9},
             "cpu_baseline": cpu,
