@@ -157,7 +157,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
       }
       const float sq = sqrtf((float)(D / f.heads));
       {
-        // fc_gamma2 with the attention tail fused into its epilogue (2-CTA kernel, k in {12,18,24}); otherwise logits -> E3
+        // fc_gamma2 with the attention tail fused into its epilogue (k in {12,18,24}); otherwise logits -> E3
         GemmArgs a;
         const Layer& L = k.fc_gamma2;
         a.A = p.E1; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
@@ -166,7 +166,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
         a.at_pos = p.E2; a.at_v = p.QKV + 2 * D; a.at_ldv = 3 * D; a.at_sqrt = sq;
         a.Y = p.RES; a.ldc = D;
         a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
-        if (gemm_tc2_supported(a, A_PLAIN)) {
+        if (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN)) {
           SAPCU_TRY(g.run(a, A_PLAIN));
         } else {
           SAPCU_TRY(g.layer(k.fc_gamma2, p.E1, D, E, p.E3, D, ACT_NONE));

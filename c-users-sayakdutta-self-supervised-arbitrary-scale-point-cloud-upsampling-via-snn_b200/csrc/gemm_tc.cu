@@ -43,7 +43,7 @@ constexpr size_t TC_SMEM_BYTES = (size_t)3 * 4 * TC_TILE_BYTES + 1024 /*align sl
 
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int ACT, int EXTRA, int EPI, int TC_BN>
+template <int ACT, int EXTRA, int EPI, int TC_BN, int KK = 1>
 __global__ void __launch_bounds__((TC_EPI_WARP0 + EPI) * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                const __grid_constant__ CUtensorMap map_x, const TcParams p) {
@@ -51,7 +51,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   constexpr int TC_ACC = 512 / TC_BN;
   constexpr uint32_t X_BYTES = TC_BN * TC_BK * 4;
   constexpr uint32_t TC_STAGE_BYTES = 2 * TC_TILE_BYTES + 2 * X_BYTES;       // W_hi, W_lo, X_hi, X_lo
-  constexpr uint32_t IDESC = tc_idesc(TC_BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // 128B swizzle needs 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -68,6 +67,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = p.K / TC_BK;
   const int64_t total_tiles = p.n_tiles * p.m_tiles;
+  const int TR = p.tile_rows;                                       // activation rows per tile (= TC_BN unless EXTRA == 3)
+  const uint32_t idesc = tc_idesc(TR);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), TC_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
@@ -98,14 +99,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             // pull the activation tile `l2_prefetch` k-blocks ahead (possibly in this CTA's next tile) into L2
             int kp = kb + p.l2_prefetch; int64_t tp = t;
             if (kp >= nk) { kp -= nk; tp += gridDim.x; }
-            if (kp < nk && tp < total_tiles) tma_prefetch_l2_2d(&map_x, kp * TC_BK, (int)((tp / p.m_tiles) * TC_BN));
+            if (kp < nk && tp < total_tiles) tma_prefetch_l2_2d(&map_x, kp * TC_BK, (int)((tp / p.m_tiles) * TR));
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), ((p.split_w || p.passes == 1) ? 1 : 2) * TC_TILE_BYTES + X_BYTES);
+          mbar_expect_tx(bar_raw(s), ((p.split_w || p.passes == 1) ? 1 : 2) * TC_TILE_BYTES + (uint32_t)TR * 128u);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, m_t * TC_BM);
           if (!p.split_w && p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, m_t * TC_BM);
-          tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, (int)(n_t * TC_BN));
+          tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, (int)(n_t * TR));
           if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -128,11 +129,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
             const uint64_t adv = (uint64_t)(k8 * 2);            // 8 tf32 = 32 B = 2 x 16 B along the swizzled row
             if (p.passes == 3) {
-              umma_tf32(tmem_d, w_lo + adv, x_hi + adv, IDESC, (kb | k8) ? 1u : 0u);
-              umma_tf32(tmem_d, w_hi + adv, x_lo + adv, IDESC, 1u);
-              umma_tf32(tmem_d, w_hi + adv, x_hi + adv, IDESC, 1u);
+              umma_tf32(tmem_d, w_lo + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
+              umma_tf32(tmem_d, w_hi + adv, x_lo + adv, idesc, 1u);
+              umma_tf32(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
             } else {
-              umma_tf32(tmem_d, w_hi + adv, x_hi + adv, IDESC, (kb | k8) ? 1u : 0u);
+              umma_tf32(tmem_d, w_hi + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
             }
           }
           umma_commit(bar_empty(s));                             // frees the smem stage when these MMAs retire
@@ -208,7 +209,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if (ACT == ACT_LIF) { np.d = p.nparams[cc]; np.a = p.nparams[p.N + cc]; np.r = p.nparams[2 * p.N + cc]; np.th0 = p.nparams[3 * p.N + cc]; }
       if (!(ok = mbar_wait(bar_tfull(a), aph, p.err))) break;
       tc_fence_after();
-      if (ACT == ACT_LIF) {
+      if (EXTRA == 3) {
+        // fused attention tail (see gemm_tc2.cu): the tile holds TR / KK whole points; a warp takes every `parts`-th
+        // point, one channel per lane: logits -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j])
+        const int npts = TR / KK;
+        const int parts = (EPI == 16) ? ((npts % 4 == 0) ? 4 : ((npts % 2 == 0) ? 2 : 1)) : ((npts % 2 == 0) ? 2 : 1);
+        const int64_t P_total = p.R / KK;
+        const float inv_s = 1.0f / p.at_sqrt;
+        if (part < parts) {
+          for (int pp = part; pp < npts; pp += parts) {
+            const int64_t pt = n_t * npts + pp;
+            if (pt >= P_total) break;                      // warp-uniform
+            float av[KK];
+            __syncwarp();
+            tmem_ld_cols<KK>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + pp * KK), av);
+            const int64_t patch0 = (pt / p.Mpts) * p.Mpts;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) { av[j] = fmaf(av[j] + bia, sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx((av[j] - mx) * 1.4426950408889634f); sum += av[j]; }
+            const float inv_sum = 1.0f / sum;
+            const float* ps = p.at_pos + (pt * KK) * (int64_t)p.N + c;
+            const int32_t* ip = p.idx + pt * p.ldi;
+            float res = 0.0f;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) {
+              const int64_t nb = patch0 + ip[j];
+              const float vp = p.at_v[nb * p.at_ldv + c] + ps[(int64_t)j * p.N];
+              res = fmaf(av[j] * inv_sum, vp, res);
+            }
+            p.Y[pt * p.ldc + c] = res;
+          }
+        }
+      } else if (ACT == ACT_LIF) {
         // 8 columns at a time with the next piece's TMEM load in flight (see gemm_tc2.cu): keeps all 8 recurrences
         // interleaved instead of 32 live accumulators forcing ptxas to serialise them
         const int colw = part * CHUNKS * 32;
@@ -362,7 +397,11 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if ((g.lda % 4) != 0 || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return false;
   if (g.group != 0) return false;                                  // row-group max stays on the SIMT engine
   if (g.residual && g.act != ACT_NONE) return false;
-  if (g.at_pos || g.pool) return false;                                      // fused attention epilogue: 2-CTA kernel only
+  if (g.pool) return false;                                        // fused max-pool epilogue: 2-CTA kernel only
+  if (g.at_pos) {                                                  // fused attention tail (EXTRA == 3)
+    if (!tc_fuse_attn_out_enabled() || g.act != ACT_NONE || g.residual || g.edge_bias || !g.at_v || !g.idx) return false;
+    if (tc_fused_tile_rows(g.kk) == 0 || g.R % g.kk != 0 || (g.N % 128) != 0 || !g.Whi || !g.Wlo) return false;
+  }
   if (g.edge_bias && (g.act != ACT_LIF || (g.N % 128) != 0 || !g.Q || !g.Kf || !g.idx || g.kk < 1 || g.Mpts < 1)) return false;
   if (g.edge_bias && (g.R / g.kk + g.Mpts) * g.ldq >= ((int64_t)1 << 31)) return false;     // 32-bit gather offsets
   if (g.R >= ((int64_t)1 << 31) || g.N > (1 << 20)) return false;
@@ -376,6 +415,9 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
 #define SAPCU_TC_ATTR1(A, RS, E, B) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES))
 #define SAPCU_TC_ATTR(A, RS) SAPCU_TC_ATTR1(A, RS, 8, 128); SAPCU_TC_ATTR1(A, RS, 8, 256); SAPCU_TC_ATTR1(A, RS, 16, 128); SAPCU_TC_ATTR1(A, RS, 16, 256)
     SAPCU_TC_ATTR(ACT_LIF, 0); SAPCU_TC_ATTR(ACT_LIF, 2); SAPCU_TC_ATTR(ACT_LEAKY, 0); SAPCU_TC_ATTR(ACT_GELU, 0); SAPCU_TC_ATTR(ACT_NONE, 1); SAPCU_TC_ATTR(ACT_NONE, 0);
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, 3, 16, 256, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, 3, 16, 256, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, 3, 16, 256, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
 #undef SAPCU_TC_ATTR
 #undef SAPCU_TC_ATTR1
     attr_done = true;
@@ -399,14 +441,16 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   if (rc) return rc;
   rc = tc_make_map(&mwlo, presplit ? g.Wlo : g.W, g.N, g.K, g.K, TC_BM);
   if (rc) return rc;
-  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, bn);
+  const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : bn;     // the fused attention tail runs the 256-column layout
+  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, tile_rows);
   if (rc) return rc;
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
-  p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, bn); p.err = err;
-  p.pool = nullptr; p.pool_T = 0; p.pool_rows = 0; p.at_pos = nullptr; p.at_v = nullptr; p.at_ldv = 0; p.at_sqrt = 1.0f; p.tile_rows = bn;
+  p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, tile_rows); p.err = err;
+  p.pool = nullptr; p.pool_T = 0; p.pool_rows = 0;
+  p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
   p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
@@ -418,7 +462,12 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
     else if (bn == 128) SAPCU_TC_LAUNCH1(A, RS, 16, 128);                        \
     else SAPCU_TC_LAUNCH1(A, RS, 16, 256);                                       \
   } while (0)
-  if (g.act == ACT_LIF && g.edge_bias) SAPCU_TC_LAUNCH(ACT_LIF, 2);
+  if (g.at_pos) {
+#define SAPCU_TC_LAUNCH3(KQ) gemm_tc_kernel<ACT_NONE, 3, 16, 256, KQ><<<grid, (TC_EPI_WARP0 + 16) * 32, TC_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
+    if (g.kk == 12) SAPCU_TC_LAUNCH3(12); else if (g.kk == 18) SAPCU_TC_LAUNCH3(18); else SAPCU_TC_LAUNCH3(24);
+#undef SAPCU_TC_LAUNCH3
+  }
+  else if (g.act == ACT_LIF && g.edge_bias) SAPCU_TC_LAUNCH(ACT_LIF, 2);
   else if (g.act == ACT_LIF) SAPCU_TC_LAUNCH(ACT_LIF, 0);
   else if (g.act == ACT_LEAKY) SAPCU_TC_LAUNCH(ACT_LEAKY, 0);
   else if (g.act == ACT_GELU) SAPCU_TC_LAUNCH(ACT_GELU, 0);

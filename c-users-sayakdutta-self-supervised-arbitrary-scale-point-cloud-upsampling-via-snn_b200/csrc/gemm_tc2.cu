@@ -386,16 +386,10 @@ int launch_fill(float* p, int64_t n, float v, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static int fused_tile_rows(int kk) {        // largest multiple of lcm(kk, 16) not above 256, for the instantiated kk
-  if (kk == 12 || kk == 24) return 240;
-  if (kk == 18) return 144;
-  return 0;
-}
-
 bool gemm_tc2_supported(const GemmArgs& g, int amode) {
-  static int enabled = -1, fuse = -1;
+  static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("SAPCU_TC_2CTA"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
-  if (fuse < 0) { const char* e = getenv("SAPCU_TC_FUSE_ATTNOUT"); fuse = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool fuse = tc_fuse_attn_out_enabled();
   GemmArgs base = g;
   base.at_pos = nullptr; base.pool = nullptr;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
@@ -407,7 +401,7 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
     if (g.R % ((int64_t)g.pool_T * g.pool_M) != 0) return false;
   }
   if (g.at_pos) {
-    if (!fuse || g.act != ACT_NONE || g.residual || !g.at_v || !g.idx || fused_tile_rows(g.kk) == 0) return false;
+    if (!fuse || g.act != ACT_NONE || g.residual || !g.at_v || !g.idx || tc_fused_tile_rows(g.kk) == 0) return false;
     if (g.R % g.kk != 0) return false;
   }
   return true;
@@ -427,7 +421,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   SAPCU_REQUIRE(err != nullptr, "gemm_tc2: cannot allocate the watchdog flag");
   static int l2pf = -1;
   if (l2pf < 0) { const char* f = getenv("SAPCU_TC_L2PF"); l2pf = f ? atoi(f) : 4; }
-  const int tile_rows = g.at_pos ? fused_tile_rows(g.kk) : T2_BN;
+  const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : T2_BN;
   CUtensorMap mw, mwlo, mx;
   int rc = tc_make_map(&mw, g.Whi, g.N, g.K, g.K, 128);
   if (rc) return rc;

@@ -1,5 +1,6 @@
 // PTX wrappers shared by the tcgen05 GEMM engines (sm_100a): mbarrier, TMA, UMMA descriptors, tcgen05 mma/ld/commit.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <stdint.h>
 #include "common.cuh"
@@ -224,5 +225,17 @@ __device__ __forceinline__ void edge_fetch8(const TcParams& p, int my_qo, int my
 // host helpers (gemm_tc.cu)
 int tc_make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows);
 int* tc_err_flag();
+// rows per tile of the fused attention epilogue (EXTRA == 3): the largest multiple of lcm(kk, 16) not above 256, for the
+// instantiated neighbour counts; 0 = not supported
+inline int tc_fused_tile_rows(int kk) {
+  if (kk == 12 || kk == 24) return 240;
+  if (kk == 18) return 144;
+  return 0;
+}
+inline bool tc_fuse_attn_out_enabled() {
+  static int fuse = -1;
+  if (fuse < 0) { const char* e = getenv("SAPCU_TC_FUSE_ATTNOUT"); fuse = (e && atoi(e) == 0) ? 0 : 1; }
+  return fuse == 1;
+}
 
 }  // namespace sapcu
