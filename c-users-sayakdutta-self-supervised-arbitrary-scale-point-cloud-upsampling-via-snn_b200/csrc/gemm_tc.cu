@@ -67,8 +67,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = p.K / TC_BK;
   const int64_t total_tiles = p.n_tiles * p.m_tiles;
-  const int TR = p.tile_rows;                                       // activation rows per tile (= TC_BN unless EXTRA == 3)
-  const uint32_t idesc = tc_idesc(TR);
+  const int TR = p.tile_rows;                                       // rows a tile advances by (TC_BN; whole points only when EXTRA == 3)
+  constexpr uint32_t idesc = tc_idesc(TC_BN);                       // the MMA always spans TC_BN rows
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), TC_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
@@ -103,7 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), ((p.split_w || p.passes == 1) ? 1 : 2) * TC_TILE_BYTES + (uint32_t)TR * 128u);
+          mbar_expect_tx(bar_raw(s), ((p.split_w || p.passes == 1) ? 1 : 2) * TC_TILE_BYTES + X_BYTES);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, m_t * TC_BM);
           if (!p.split_w && p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, m_t * TC_BM);
           tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, (int)(n_t * TR));
@@ -213,8 +213,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         // fused attention tail (see gemm_tc2.cu): the tile holds TR / KK whole points; a warp takes every `parts`-th
         // point, one channel per lane: logits -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j])
         const int npts = TR / KK;
-        const int parts = (EPI == 16) ? ((npts % 4 == 0) ? 4 : ((npts % 2 == 0) ? 2 : 1)) : ((npts % 2 == 0) ? 2 : 1);
+        constexpr int parts = EPI / 4;
         const int64_t P_total = p.R / KK;
+        {   // pull the pos rows of this CTA's NEXT tile (its 128-channel slab: 4 lines per row) into L2
+          const int64_t tn = t + gridDim.x;
+          if (tn < total_tiles) {
+            const int64_t row0 = (tn / p.m_tiles) * TR;
+            const int cb = (int)(tn % p.m_tiles) * TC_BM;
+            for (int i = (warp - TC_EPI_WARP0) * 32 + lane; i < TR * 4; i += EPI * 32) {
+              const int64_t row = row0 + (i >> 2);
+              if (row < p.R) prefetch_l2(p.at_pos + row * p.N + cb + (i & 3) * 32);
+            }
+          }
+        }
         const float inv_s = 1.0f / p.at_sqrt;
         if (part < parts) {
           for (int pp = part; pp < npts; pp += parts) {
@@ -442,7 +453,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   rc = tc_make_map(&mwlo, presplit ? g.Wlo : g.W, g.N, g.K, g.K, TC_BM);
   if (rc) return rc;
   const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : bn;     // the fused attention tail runs the 256-column layout
-  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, tile_rows);
+  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, g.at_pos ? 256 : bn);
   if (rc) return rc;
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;

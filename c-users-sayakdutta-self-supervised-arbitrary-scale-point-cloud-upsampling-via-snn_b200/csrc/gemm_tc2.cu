@@ -87,8 +87,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nk = p.K / TC_BK;
   const int64_t total_tiles = p.n_tiles * p.m_tiles;       // m_tiles = N / 256 (channel pairs), n_tiles = ceil(R / tile_rows)
-  const int TR = p.tile_rows, HALF = TR >> 1;              // rows per pair tile (<= 256) / staged by each CTA
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  const int TR = p.tile_rows;                              // rows a tile advances by (256; whole points only when EXTRA == 3)
+  constexpr int HALF = T2_BN / 2;                          // rows staged by each CTA: the MMA always spans 256 rows
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < T2_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), 2 * T2_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
@@ -122,7 +123,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), (p.passes == 3 ? 2 : 1) * TC_TILE_BYTES + (uint32_t)HALF * 128u);
+          mbar_expect_tx(bar_raw(s), (p.passes == 3 ? 3 : 2) * TC_TILE_BYTES);
           tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, wrow);
           if (p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, wrow);
           tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, xrow);
@@ -210,8 +211,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         // fused attention tail: this tile holds TR / KK whole points; a warp takes every `parts`-th point, one
         // channel per lane: logits -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j])
         const int npts = TR / KK;
-        const int parts = (npts % 4 == 0) ? 4 : ((npts % 2 == 0) ? 2 : 1);
+        constexpr int parts = T2_EPI / 4;
         const int64_t P_total = p.R / KK;
+        {   // pull the pos rows of this pair's NEXT tile (this CTA's 128-channel slab: 4 lines per row) into L2
+          const int64_t tn = t + npairs;
+          if (tn < total_tiles) {
+            const int64_t row0 = (tn / p.m_tiles) * TR;
+            const int cb = (int)(tn % p.m_tiles) * 256 + (int)rank * 128;
+            for (int i = (warp - T2_EPI_WARP0) * 32 + lane; i < TR * 4; i += T2_EPI * 32) {
+              const int64_t row = row0 + (i >> 2);
+              if (row < p.R) prefetch_l2(p.at_pos + row * p.N + cb + (i & 3) * 32);
+            }
+          }
+        }
         const float inv_s = 1.0f / p.at_sqrt;
         if (part < parts) {
           for (int pp = part; pp < npts; pp += parts) {
@@ -427,7 +439,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   if (rc) return rc;
   rc = tc_make_map(&mwlo, g.Wlo, g.N, g.K, g.K, 128);
   if (rc) return rc;
-  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, tile_rows / 2);
+  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, T2_BN / 2);
   if (rc) return rc;
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;

@@ -58,6 +58,7 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -188,7 +189,7 @@ struct TcParams {
   // EXTRA == 4 (fd conv5, 2-CTA kernel): rows are (point*T + t); the epilogue keeps one running maximum per step and
   // merges them into pool[(patch*T + t), c] with float atomic max -- the [P*T, N] activation never reaches HBM
   float* pool; int pool_T; int64_t pool_rows;     // pool_rows = points per patch * T
-  int tile_rows;              // activation rows per tile (UMMA N); a multiple of kk when EXTRA == 3
+  int tile_rows;              // rows a tile advances by: the MMA tile height, or the whole points inside it when EXTRA == 3
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
   int passes;                 // 3: w_lo*x_hi + w_hi*x_lo + w_hi*x_hi (fp32-grade); 1: w_hi*x_hi only (plain TF32)
@@ -225,11 +226,10 @@ __device__ __forceinline__ void edge_fetch8(const TcParams& p, int my_qo, int my
 // host helpers (gemm_tc.cu)
 int tc_make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows);
 int* tc_err_flag();
-// rows per tile of the fused attention epilogue (EXTRA == 3): the largest multiple of lcm(kk, 16) not above 256, for the
-// instantiated neighbour counts; 0 = not supported
+// rows a tile advances by in the fused attention epilogue (EXTRA == 3): the whole points that fit in the 256-row MMA tile
+// (the few rows behind them are loaded and multiplied but belong to the next tile); 0 = neighbour count not instantiated
 inline int tc_fused_tile_rows(int kk) {
-  if (kk == 12 || kk == 24) return 240;
-  if (kk == 18) return 144;
+  if (kk == 12 || kk == 18 || kk == 24) return (256 / kk) * kk;
   return 0;
 }
 inline bool tc_fuse_attn_out_enabled() {
