@@ -76,7 +76,8 @@ edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ i
       q[0] = d0; q[1] = d1; q[2] = d2;
     }
   };
-  stage(0, 0);
+  const int g0 = blockIdx.z, gstep = gridDim.z;                  // grid.z CTAs share a patch slab (shorter-lived CTAs)
+  if (g0 < G) stage(g0, 0);
   __syncthreads();
   const int c = blockIdx.y * 128 + tid;
   const bool cv = c < C;
@@ -85,10 +86,11 @@ edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ i
   const float bi = bias[cc], sc = scale[cc], sh = shift[cc];
   const NeuronParams p{np[cc], np[C + cc], np[2 * C + cc], np[3 * C + cc]};
   float* o = out + patch0 * kk * (int64_t)C + c;
+  int buf = 0;
 #pragma unroll 1
-  for (int g = 0; g < G; ++g) {
-    if (g + 1 < G) stage(g + 1, (g + 1) & 1);
-    const float* q = pd + (g & 1) * EPL_G * 3;
+  for (int g = g0; g < G; g += gstep, buf ^= 1) {
+    if (g + gstep < G) stage(g + gstep, buf ^ 1);
+    const float* q = pd + buf * EPL_G * 3;
     const int n = (EP - g * EPL_G) < EPL_G ? (EP - g * EPL_G) : EPL_G;
     if (cv) {
 #pragma unroll 1
@@ -255,13 +257,13 @@ __global__ void fn_head_kernel(const float* __restrict__ H, int K, int64_t S, co
 
 int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32_t* idx, int kk, int ldi, int Mpts,
                           int64_t rows, int C, const float* W, const float* bias, const float* scale,
-                          const float* shift, const float* np, int T, float* out, cudaStream_t st) {
+                          const float* shift, const float* np, int T, float* out, cudaStream_t st, int nsplit) {
   if (rows == 0) return 0;
   if (edge) {
     SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256 && kk >= 1 && rows % ((int64_t)Mpts * kk) == 0, "pointwise3_lif: edge rows must be whole patches of <= 256 points");
     const int64_t S = rows / ((int64_t)Mpts * kk);
     const size_t smem = sizeof(float) * (3 * (size_t)Mpts + 2 * EPL_G * 3) + (size_t)Mpts * kk;
-    dim3 grid((unsigned)S, (unsigned)ceil_div(C, 128));
+    dim3 grid((unsigned)S, (unsigned)ceil_div(C, 128), (unsigned)(nsplit < 1 ? 1 : nsplit));
     if (precise) edge_pos_lif_kernel<true><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out);
     else         edge_pos_lif_kernel<false><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out);
   } else {

@@ -120,32 +120,59 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
   SAPCU_TRY(launch_intra_knn(xyz, 3, s, M, 3, p.kmax, p.idx, st));
   SAPCU_TRY(launch_pointwise3_lif(false, precise, xyz, nullptr, 0, 0, M, P, 64, f.conv1.W, f.conv1.bias, f.conv1.scale,
                                   f.conv1.shift, f.snn_init.np, f.T_enc, p.F0, st));
+  // ---- tensor-core schedule helpers ------------------------------------------------------------------------------
+  // fc_gamma's first layer is linear, so W(q_i - k_j + pos_ij) = W q_i - W k_j + W pos_ij: the edge contraction runs on
+  // pos (E2) alone and its epilogue adds the two per-POINT products [W q | W k] (QK, [P, 2D]) gathered through the graph
+  // before BN + LIF; fc_gamma2's epilogue does the softmax over k and the weighted sum.  Neither the attention input nor
+  // the logits are materialised.
+  auto gamma_args = [&](int b, const float* pos, float* out, float* QK) {
+    const FnBlock& k = f.blk[b];
+    const int D = k.D, kk = k.k < M ? k.k : M;
+    GemmArgs a;
+    const Layer& L = k.fc_gamma;
+    a.A = pos; a.lda = D; a.R = P * kk; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
+    a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_gamma.np;
+    a.Y = out; a.ldc = D;
+    a.Q = QK; a.Kf = QK + D; a.ldq = 2 * D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M; a.edge_bias = true;
+    return a;
+  };
+  auto gamma2_args = [&](int b, const float* in, const float* pos) {
+    const FnBlock& k = f.blk[b];
+    const int D = k.D, kk = k.k < M ? k.k : M;
+    GemmArgs a;
+    const Layer& L = k.fc_gamma2;
+    a.A = in; a.lda = D; a.R = P * kk; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
+    a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_NONE;
+    a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
+    a.at_pos = pos; a.at_v = p.QKV + 2 * D; a.at_ldv = 3 * D; a.at_sqrt = sqrtf((float)(D / f.heads));   // torch divides by the python scalar sqrt(head_dim)
+    a.Y = p.RES; a.ldc = D;
+    a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+    return a;
+  };
+  auto edge_pos = [&](int b, float* out, cudaStream_t s_, int nsplit) {
+    const FnBlock& k = f.blk[b];
+    const int kk = k.k < M ? k.k : M;
+    return launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, P * kk, k.D, k.fc_delta.W, k.fc_delta.bias,
+                                 k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, out, s_, nsplit);
+  };
+  static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
   for (int b = 0; b < 3; ++b) {
     const FnBlock& k = f.blk[b];
     const int D = k.D, kk = k.k < M ? k.k : M;
     const float* fin = b == 0 ? p.F0 : p.FCAT + 64 * (b - 1);
     const int64_t ldin = b == 0 ? 64 : 192;
     const int64_t E = P * kk;
+    float* Xb = p.E1;                                             // this block's edge buffer (pos-enc layer 1, then fc_gamma's output)
     SAPCU_TRY(g.layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
     SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
-    SAPCU_TRY(launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias,
-                                    k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, p.E1, st));
+    SAPCU_TRY(edge_pos(b, Xb, st, 1));
     if (mode != SAPCU_MODE_FP32) {
-      // tensor-core schedule.  fc_gamma's first layer is linear, so W(q_i - k_j + pos_ij) = W q_i - W k_j + W pos_ij:
-      // the edge contraction runs on pos (E2) alone and its epilogue adds the two per-POINT products (gathered through
-      // the graph) before BN + LIF -- the [E, D] attention input is never materialised.  E3 holds [W q | W k] ([P, 2D]).
-      SAPCU_TRY(g.layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
+      SAPCU_TRY(g.layer(k.fc_delta2, Xb, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
       {
-        GemmArgs a;
-        const Layer& L = k.fc_gamma;
-        a.A = p.E2; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
-        a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_gamma.np;
-        a.Y = p.E1; a.ldc = D;
-        float* QK = p.E3;
-        a.Q = QK; a.Kf = QK + D; a.ldq = 2 * D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M; a.edge_bias = true;
-        static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
+        float* QK = p.E3;                                          // [W q | W k], [P, 2D]
+        GemmArgs a = gamma_args(b, p.E2, Xb, QK);
         if (factorise && kk >= 2 && gemm_tc_supported(a, A_PLAIN)) {
-          Layer Lw = L;
+          Layer Lw = k.fc_gamma;
           Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;
           SAPCU_TRY(g.layer(Lw, p.QKV, 3 * D, P, QK, 2 * D, ACT_NONE));
           SAPCU_TRY(g.layer(Lw, p.QKV + D, 3 * D, P, QK + D, 2 * D, ACT_NONE));
@@ -155,22 +182,13 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
           SAPCU_TRY(g.layer(k.fc_gamma, p.E3, D, E, p.E1, D, ACT_LIF, &k.snn_gamma, 4));
         }
       }
-      const float sq = sqrtf((float)(D / f.heads));
       {
-        // fc_gamma2 with the attention tail fused into its epilogue (k in {12,18,24}); otherwise logits -> E3
-        GemmArgs a;
-        const Layer& L = k.fc_gamma2;
-        a.A = p.E1; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
-        a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_NONE;
-        a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
-        a.at_pos = p.E2; a.at_v = p.QKV + 2 * D; a.at_ldv = 3 * D; a.at_sqrt = sq;
-        a.Y = p.RES; a.ldc = D;
-        a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+        GemmArgs a = gamma2_args(b, Xb, p.E2);
         if (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN)) {
           SAPCU_TRY(g.run(a, A_PLAIN));
         } else {
           SAPCU_TRY(g.layer(k.fc_gamma2, p.E1, D, E, p.E3, D, ACT_NONE));
-          SAPCU_TRY(launch_attn_out(precise, p.E3, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, sq, p.RES, st));
+          SAPCU_TRY(launch_attn_out(precise, p.E3, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, a.at_sqrt, p.RES, st));
         }
       }
       SAPCU_TRY(g.layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));

@@ -30,7 +30,6 @@ constexpr int T2_BN = 256;                      // rows per pair tile (128 stage
 #endif
 constexpr int T2_SPLIT_WARP0 = 2, T2_SPLIT_WARPS = SAPCU_T2_SPLIT_WARPS;
 constexpr int T2_EPI_WARP0 = T2_SPLIT_WARP0 + T2_SPLIT_WARPS, T2_EPI = 16;
-constexpr int T2_THREADS = (T2_EPI_WARP0 + T2_EPI) * 32;
 constexpr uint32_t T2_STAGE_BYTES = 4 * TC_TILE_BYTES;          // W_hi, W_lo, X(raw = hi), X_lo : 64 KiB
 constexpr size_t T2_SMEM_BYTES = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 + 256;
 
@@ -67,7 +66,7 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives
 }
 
 template <int ACT, int EXTRA, int KK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((T2_EPI_WARP0 + T2_EPI) * 32, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                 const __grid_constant__ CUtensorMap map_x, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -451,7 +450,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   const int64_t total = p.n_tiles * p.m_tiles;
   int pairs = (int)(total < kNumSMs / 2 ? total : kNumSMs / 2);
   const int grid = 2 * pairs;
-#define SAPCU_T2_LAUNCH(A, X, KQ) gemm_tc2_kernel<A, X, KQ><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
+#define SAPCU_T2_LAUNCH(A, X, KQ) gemm_tc2_kernel<A, X, KQ><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
   if (g.at_pos) {
     if (g.kk == 12) SAPCU_T2_LAUNCH(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH(ACT_NONE, 3, 24);
   }
