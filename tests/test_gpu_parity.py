@@ -550,3 +550,44 @@ def test_fused_epilogues_match_unfused_schedule(lib, sphere, tmp_path):
     print("fused vs unfused: normals %.2e deg, distances %.2e rel" % (ang, rel))
     assert ang < 0.01
     assert rel < 5e-3          # fd is free-running here (own feature graphs): near-tie neighbour swaps are allowed for
+
+
+@pytest.mark.parametrize("M,C,k", [(7, 3, 7), (33, 3, 12), (64, 70, 32), (128, 64, 48), (100, 256, 32), (50, 130, 1)])
+def test_intra_knn_shapes(lib, M, C, k):
+    """Odd patch sizes / channel counts / k through the triangular-block + REDUX top-k kernel, against the reference
+    formula on the CPU (well-separated random features: exact index equality)."""
+    S = 9
+    f = torch.randn(S, M, C + 5, generator=torch.Generator().manual_seed(M * 1000 + C))
+    ref = orc.intra_knn(f[:, :, :C].permute(0, 2, 1).contiguous(), k).numpy()
+    out = torch.full((S * M, k), -1, dtype=torch.int32, device=DEV)
+    df = f.to(DEV)
+    N.check(lib.sapcu_intra_knn(N.ptr(df), C + 5, S, M, C, k, N.ptr(out), None))
+    got = out.view(S, M, k).cpu().numpy()
+    assert (got == ref).mean() >= 0.999, (got == ref).mean()
+    assert (got[:, :, 0] == np.arange(M)[None, :]).all()
+    assert (np.sort(got, -1)[:, :, 1:] != np.sort(got, -1)[:, :, :-1]).all()       # k distinct neighbours per row
+
+
+def test_models_other_patch_size(lib, sphere):
+    """K = 64 neighbours per seed (patch size != 100): tile, group and pooling boundaries fall elsewhere in every fused
+    kernel (edge groups of 72, 252-row attention tiles, 7 x 64-row pooling windows).  Tensor-core mode vs the oracle."""
+    cloud, seeds = sphere
+    B, M = 24, 64
+    mfn, mfd, sd_fn, sd_fd = _models(True)
+    mfn.set_mode("tc"), mfd.set_mode("tc")
+    idx = oracle_c.knn(cloud, seeds[:B], M)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx))
+    with torch.no_grad():
+        ref_n = orc.fn_forward(sd_fn, p).numpy()
+    got_n = mfn(p.to(DEV)).cpu().numpy()
+    assert _angle_deg(got_n, ref_n).max() < 0.1
+    rng = np.random.default_rng(5)
+    pr = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx, rng.normal(size=(B, 3)).astype(np.float32)))
+    taps = {}
+    with torch.no_grad():
+        ref_d = orc.fd_forward(sd_fd, pr, schedule="dce", taps=taps).numpy()
+    forced = torch.stack([gi.to(torch.int32) for gi in taps["graph_idx"]], 0)
+    got_d = mfd(pr.to(DEV), forced_idx=forced).cpu().numpy()
+    rel = np.abs(got_d - ref_d) / np.maximum(np.abs(ref_d), 1e-6)
+    print("M=64: normals %.2e deg, distances %.2e rel" % (_angle_deg(got_n, ref_n).max(), rel.max()))
+    assert rel.max() < 1e-3
