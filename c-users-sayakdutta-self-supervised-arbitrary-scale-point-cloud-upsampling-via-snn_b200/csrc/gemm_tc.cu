@@ -214,7 +214,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         // point, one channel per lane: logits -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j])
         const int npts = TR / KK;
         constexpr int parts = EPI / 4;
-        const int64_t P_total = p.R / KK;
         {   // pull the pos rows of this CTA's NEXT tile (its 128-channel slab: 4 lines per row) into L2
           const int64_t tn = t + gridDim.x;
           if (tn < total_tiles) {
@@ -226,34 +225,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             }
           }
         }
-        const float inv_s = 1.0f / p.at_sqrt;
-        if (part < parts) {
-          for (int pp = part; pp < npts; pp += parts) {
-            const int64_t pt = n_t * npts + pp;
-            if (pt >= P_total) break;                      // warp-uniform
-            float av[KK];
-            __syncwarp();
-            tmem_ld_cols<KK>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + pp * KK), av);
-            const int64_t patch0 = (pt / p.Mpts) * p.Mpts;
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < KK; ++j) { av[j] = fmaf(av[j] + bia, sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
-            float sum = 0.0f;
-#pragma unroll
-            for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx((av[j] - mx) * 1.4426950408889634f); sum += av[j]; }
-            const float inv_sum = 1.0f / sum;
-            const float* ps = p.at_pos + (pt * KK) * (int64_t)p.N + c;
-            const int32_t* ip = p.idx + pt * p.ldi;
-            float res = 0.0f;
-#pragma unroll
-            for (int j = 0; j < KK; ++j) {
-              const int64_t nb = patch0 + ip[j];
-              const float vp = p.at_v[nb * p.at_ldv + c] + ps[(int64_t)j * p.N];
-              res = fmaf(av[j] * inv_sum, vp, res);
-            }
-            p.Y[pt * p.ldc + c] = res;
-          }
-        }
+        if (part < parts)
+          attn_tail_points<KK>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN), part, parts, npts, n_t, c, bia, sc, sh);
       } else if (ACT == ACT_LIF) {
         // 8 columns at a time with the next piece's TMEM load in flight (see gemm_tc2.cu): keeps all 8 recurrences
         // interleaved instead of 32 live accumulators forcing ptxas to serialise them
@@ -411,7 +384,7 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
   if (g.pool) return false;                                        // fused max-pool epilogue: 2-CTA kernel only
   if (g.at_pos) {                                                  // fused attention tail (EXTRA == 3)
     if (!tc_fuse_attn_out_enabled() || g.act != ACT_NONE || g.residual || g.edge_bias || !g.at_v || !g.idx) return false;
-    if (tc_fused_tile_rows(g.kk) == 0 || g.R % g.kk != 0 || (g.N % 128) != 0 || !g.Whi || !g.Wlo) return false;
+    if (g.Mpts > 256 || tc_fused_tile_rows(g.kk) == 0 || g.R % g.kk != 0 || (g.N % 128) != 0 || !g.Whi || !g.Wlo) return false;
   }
   if (g.edge_bias && (g.act != ACT_LIF || (g.N % 128) != 0 || !g.Q || !g.Kf || !g.idx || g.kk < 1 || g.Mpts < 1)) return false;
   if (g.edge_bias && (g.R / g.kk + g.Mpts) * g.ldq >= ((int64_t)1 << 31)) return false;     // 32-bit gather offsets

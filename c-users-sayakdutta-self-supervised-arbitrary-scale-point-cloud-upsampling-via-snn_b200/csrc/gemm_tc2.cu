@@ -211,7 +211,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         // channel per lane: logits -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j])
         const int npts = TR / KK;
         constexpr int parts = T2_EPI / 4;
-        const int64_t P_total = p.R / KK;
         {   // pull the pos rows of this pair's NEXT tile (this CTA's 128-channel slab: 4 lines per row) into L2
           const int64_t tn = t + npairs;
           if (tn < total_tiles) {
@@ -223,34 +222,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             }
           }
         }
-        const float inv_s = 1.0f / p.at_sqrt;
-        if (part < parts) {
-          for (int pp = part; pp < npts; pp += parts) {
-            const int64_t pt = n_t * npts + pp;
-            if (pt >= P_total) break;                      // warp-uniform
-            float av[KK];
-            __syncwarp();
-            tmem_ld_cols<KK>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T2_BN + pp * KK), av);
-            const int64_t patch0 = (pt / p.Mpts) * p.Mpts;
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < KK; ++j) { av[j] = fmaf(av[j] + bia, sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
-            float sum = 0.0f;
-#pragma unroll
-            for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx((av[j] - mx) * 1.4426950408889634f); sum += av[j]; }
-            const float inv_sum = 1.0f / sum;
-            const float* ps = p.at_pos + (pt * KK) * (int64_t)p.N + c;
-            const int32_t* ip = p.idx + pt * p.ldi;
-            float res = 0.0f;
-#pragma unroll
-            for (int j = 0; j < KK; ++j) {
-              const int64_t nb = patch0 + ip[j];
-              const float vp = p.at_v[nb * p.at_ldv + c] + ps[(int64_t)j * p.N];
-              res = fmaf(av[j] * inv_sum, vp, res);
-            }
-            p.Y[pt * p.ldc + c] = res;
-          }
-        }
+        if (part < parts)
+          attn_tail_points<KK>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T2_BN), part, parts, npts, n_t, c, bia, sc, sh);
       } else if (ACT == ACT_LIF) {
         // 8 columns (= rows of Y) at a time: 24 state + 24 temporary registers leave ptxas room to interleave all 8
         // recurrences (with 32 accumulators live it serialised half of them); the next piece is loaded under the math
@@ -412,7 +385,7 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
     if (g.R % ((int64_t)g.pool_T * g.pool_M) != 0) return false;
   }
   if (g.at_pos) {
-    if (!fuse || g.act != ACT_NONE || g.residual || !g.at_v || !g.idx || tc_fused_tile_rows(g.kk) == 0) return false;
+    if (!fuse || g.act != ACT_NONE || g.residual || !g.at_v || !g.idx || g.Mpts > 256 || tc_fused_tile_rows(g.kk) == 0) return false;
     if (g.R % g.kk != 0) return false;
   }
   return true;

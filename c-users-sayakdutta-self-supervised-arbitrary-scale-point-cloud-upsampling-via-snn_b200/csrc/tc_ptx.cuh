@@ -1,6 +1,7 @@
 // PTX wrappers shared by the tcgen05 GEMM engines (sm_100a): mbarrier, TMA, UMMA descriptors, tcgen05 mma/ld/commit.
 #pragma once
 #include <cstdlib>
+#include "neuron.cuh"
 #include <cuda.h>
 #include <stdint.h>
 #include "common.cuh"
@@ -222,6 +223,54 @@ __device__ __forceinline__ void edge_fetch8(const TcParams& p, int my_qo, int my
   }
 }
 
+
+// Fused attention tail (EXTRA == 3) for the points pp = part, part + parts, ... of one tile: logits (TMEM columns
+// pp*KK .. pp*KK+KK-1 of this thread's channel c) -> /sqrt(d_h) -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j]).
+// Latency plan per point: the neighbour indices were fetched one point ahead; the 2*KK operand loads are issued first,
+// the TMEM read and the softmax run under them, the weighted sum consumes them last.
+template <int KK>
+__device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tmem_cols, int part, int parts, int npts,
+                                                 int64_t n_t, int c, float bia, float sc, float sh) {
+  const int64_t P_total = p.R / KK;
+  const float inv_s = 1.0f / p.at_sqrt;
+  const float* vc = p.at_v + c;
+  uint32_t nbn[(KK + 3) / 4];                                    // graph row of the next point, 4 patch-local indices (< 256) per word
+  auto fetch_row = [&](int64_t ptq) {
+    const int32_t* ip = p.idx + (ptq < P_total ? ptq : P_total - 1) * p.ldi;
+#pragma unroll
+    for (int w = 0; w < (KK + 3) / 4; ++w) nbn[w] = 0u;
+#pragma unroll
+    for (int j = 0; j < KK; ++j) nbn[j >> 2] |= (uint32_t)ip[j] << (8 * (j & 3));
+  };
+  fetch_row(n_t * npts + part);
+  for (int pp = part; pp < npts; pp += parts) {
+    const int64_t pt = n_t * npts + pp;
+    if (pt >= P_total) break;                                    // warp-uniform
+    const int64_t patch0 = (pt / p.Mpts) * p.Mpts;
+    const float* ps = p.at_pos + (pt * KK) * (int64_t)p.N + c;
+    float vr[KK], pr[KK];
+#pragma unroll
+    for (int j = 0; j < KK; ++j) {
+      vr[j] = vc[(patch0 + (int64_t)((nbn[j >> 2] >> (8 * (j & 3))) & 255u)) * p.at_ldv];
+      pr[j] = ps[(int64_t)j * p.N];
+    }
+    fetch_row(pt + parts);                                       // indices of this warp's next point (clamped at the end)
+    float av[KK];
+    __syncwarp();
+    tmem_ld_cols<KK>(tmem_cols + (uint32_t)(pp * KK), av);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KK; ++j) { av[j] = fmaf(av[j] + bia, sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx((av[j] - mx) * 1.4426950408889634f); sum += av[j]; }
+    const float inv_sum = 1.0f / sum;
+    float res = 0.0f;
+#pragma unroll
+    for (int j = 0; j < KK; ++j) res = fmaf(av[j] * inv_sum, vr[j] + pr[j], res);
+    p.Y[pt * p.ldc + c] = res;
+  }
+}
 
 // host helpers (gemm_tc.cu)
 int tc_make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows);
