@@ -7,20 +7,26 @@
 // contraction off the FFMA pipe.
 //
 // Orientation: the WEIGHT tile is the UMMA A operand (M = 128 output channels -> TMEM lanes) and the
-// ACTIVATION tile is the B operand (N = 128 rows -> TMEM columns).  One epilogue thread therefore owns one
+// ACTIVATION tile is the B operand (N = BN rows -> TMEM columns).  One epilogue thread therefore owns one
 // output channel: bias / BatchNorm / neuron parameters live in registers, the LIF^T recurrence runs on
 // register-resident accumulators, a max over 32 consecutive rows (EdgeConv k = 32) is thread-local, and
 // the 32 lanes of a warp store 32 consecutive channels of one row (one 128-byte line).
 //
-// Persistent, warp-specialised CTA (1 per SM, 448 threads):
-//   warp 0        TMA producer   cp.async.bulk.tensor of the raw fp32 W and X tiles (128B swizzle)
-//   warp 1        MMA issuer     tcgen05.mma.kind::tf32 (12 per k-block), tcgen05.commit; owns TMEM alloc
-//   warps 2..5    splitter       rewrite the landed tile as hi (in place) and lo (second buffer)
-//   warps 6..13   epilogue       tcgen05.ld -> bias/BN/activation/LIF -> coalesced global stores
-// Pipelines: smem ring of 3 stages x 64 KiB (mbarriers raw-full / split-full / empty) and 4 TMEM accumulator
-// buffers of 128 columns (mbarriers tmem-full / tmem-empty) so the epilogue of tile i overlaps the MMAs of
-// tile i+1..i+3.  Every mbarrier wait carries a clock64() watchdog: a protocol error surfaces as an error
+// Persistent, warp-specialised CTA (1 per SM, 640 threads with the default 16 epilogue warps):
+//   warp 0        TMA producer   cp.async.bulk.tensor of the pre-split tf32 W hi/lo tiles and the raw fp32 X tile
+//                                (128B swizzle) + cp.async.bulk.prefetch.tensor L2 look-ahead for X
+//   warp 1        MMA issuer     tcgen05.mma.kind::tf32 (12 per 32-wide k-block), tcgen05.commit; owns TMEM alloc
+//   warps 2..3    splitter       lo = x - trunc_tf32(x) into the second buffer (the raw tile is the hi operand: the
+//                                tensor core ignores the low 13 mantissa bits)
+//   warps 4..19   epilogue       tcgen05.ld -> bias / BN / activation / LIF^T / fused tails -> 128-byte row stores
+// Pipelines: smem ring of 2 stages x 96 KiB at BN = 256 (3 x 64 KiB at BN = 128; mbarriers raw-full / split-full /
+// empty) and 512 / BN TMEM accumulator buffers (mbarriers tmem-full / tmem-empty) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Every mbarrier wait carries a clock64() watchdog: a protocol error surfaces as an error
 // code, never as a hung GPU.
+//
+// Epilogue flavours (template EXTRA): 0 plain, 1 + residual, 2 edge bias W q_i - W k_j added before BN + LIF (factorised
+// attention input), 3 fused attention tail (softmax over the KK edges of a point and the weighted sum; tc_ptx.cuh).
+// The LIF path reads TMEM 8 columns at a time with the next piece in flight.
 //
 // Roofline: tensor pipe (tf32: 2048 MAC/clk/SM, x3 passes); the LIF epilogue is MUFU bound (3 MUFU per
 // element-step, 16/clk/SM) and overlaps the MMA stream.

@@ -8,12 +8,15 @@
 //
 // Cross-CTA protocol (all waits are watchdogged):
 //   raw[s]    local   TMA bytes of this CTA landed                       -> this CTA's splitter
-//   split[s]  LEADER  256 arrivals (128 splitter threads of each CTA; the follower arrives remotely via mapa)
+//   split[s]  LEADER  one arrival per splitter thread of both CTAs (the follower arrives remotely via mapa)
 //   empty[s]  both    tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11) -> each CTA's TMA producer
 //   tfull[a]  both    multicast commit after the last k-block           -> each CTA's epilogue
 //   tempty[a] LEADER  2 x EPI arrivals (epilogue warps of both CTAs)    -> leader's MMA issuer
-// Roles per CTA: warp 0 TMA, warp 1 MMA (leader only; both CTAs allocate TMEM with cta_group::2), warps 2..5
-// splitter (lo = x - trunc_tf32(x); the raw tile is the hi operand), warps 6..21 epilogue (same code as gemm_tc.cu).
+// Roles per CTA: warp 0 TMA, warp 1 MMA (leader only; both CTAs allocate TMEM with cta_group::2), warps 2..3
+// splitter (lo = x - trunc_tf32(x); the raw tile is the hi operand), warps 4..19 epilogue (same flavours as
+// gemm_tc.cu, plus EXTRA == 4: max over the patch's points fused into the conv5 epilogue).
+// ncu: on the K = 512 layers the MMA issuer never waits on a barrier -- the MMA stream is the limiter (tensor pipe
+// ~71 % active = ~790 TFLOP/s of issued tf32 math under the board's power cap); K <= 256 LIF layers are MUFU-bound.
 #include <cuda.h>
 #include <stdlib.h>
 #include "gemm_tc.h"
