@@ -103,9 +103,10 @@ struct G {
   }
   // plain layer: Y[R, L.N] (ldc) = act(affine(X[R, L.K] (lda)))
   int layer(const Layer& L, const float* X, int64_t lda, int64_t R, float* Y, int64_t ldc, int act,
-            const Neuron* nr = nullptr, int T = 0, const float* res = nullptr, int64_t ldr = 0) const {
+            const Neuron* nr = nullptr, int T = 0, const float* res = nullptr, int64_t ldr = 0, bool x_unit = false) const {
     GemmArgs g;
     g.A = X; g.lda = lda; g.R = R; g.K = L.K; g.W = L.W; g.Whi = L.Whi; g.Wlo = L.Wlo; g.N = L.N; g.bias = L.bias; g.scale = L.scale; g.shift = L.shift;
+    g.Wh = L.Wh; g.Wl = L.Wl; g.winv = L.winv; g.x_unit = x_unit;
     g.act = act; g.T = T; g.nparams = nr ? nr->np : nullptr; g.residual = res; g.ldr = ldr; g.Y = Y; g.ldc = ldc;
     return run(g, A_PLAIN);
   }
@@ -134,6 +135,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_gamma.np;
     a.Y = out; a.ldc = D;
     a.Q = QK; a.Kf = QK + D; a.ldq = 2 * D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M; a.edge_bias = true;
+    a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;                     // pos is a LIF output
     return a;
   };
   auto gamma2_args = [&](int b, const float* in, const float* pos) {
@@ -146,6 +148,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
     a.at_pos = pos; a.at_v = p.QKV + 2 * D; a.at_ldv = 3 * D; a.at_sqrt = sqrtf((float)(D / f.heads));   // torch divides by the python scalar sqrt(head_dim)
     a.Y = p.RES; a.ldc = D;
+    a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;                     // fc_gamma's LIF output
     a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
     return a;
   };
@@ -167,7 +170,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
     SAPCU_TRY(edge_pos(b, Xb, st, 1));
     if (mode != SAPCU_MODE_FP32) {
-      SAPCU_TRY(g.layer(k.fc_delta2, Xb, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
+      SAPCU_TRY(g.layer(k.fc_delta2, Xb, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4, nullptr, 0, true));   // input: LIF output
       {
         float* QK = p.E3;                                          // [W q | W k], [P, 2D]
         GemmArgs a = gamma_args(b, p.E2, Xb, QK);
@@ -273,6 +276,7 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
     a.A = p.SPK; a.lda = 960; a.R = P * T; a.K = L.K; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = L.N;
     a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LEAKY; a.Y = p.AGG; a.ldc = f.emb;
     a.pool = p.POOL; a.pool_T = T; a.pool_M = M;
+    a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;                       // the spike tensor
     static const bool fuse_pool = !(getenv("SAPCU_TC_FUSE_POOL") && atoi(getenv("SAPCU_TC_FUSE_POOL")) == 0);
     if (mode != SAPCU_MODE_FP32 && fuse_pool && gemm_tc2_supported(a, A_PLAIN)) {
       SAPCU_TRY(launch_fill(p.POOL, s * T * f.emb, -INFINITY, st));

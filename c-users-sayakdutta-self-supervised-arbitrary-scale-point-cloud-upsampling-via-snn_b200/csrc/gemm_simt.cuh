@@ -41,6 +41,9 @@ struct GemmArgs {
   // tensor-core engine only: fuse softmax_k(Y / at_sqrt) and sum_j a_j (at_v[nb_j] + at_pos[e_j]) into the epilogue; Y becomes [points, N]
   const float* at_pos = nullptr; const float* at_v = nullptr; int64_t at_ldv = 0; float at_sqrt = 1.0f;
   float* pool = nullptr; int pool_T = 0, pool_M = 0;   // 2-CTA tensor-core engine: rows are (point*T + t); instead of Y emit pool[(patch*T + t), c] = max over the patch's pool_M points (buffer pre-filled with -inf)
+  // fp16x3 tensor-core path (2-CTA kernel): half (hi, lo) copies of W * 2^e, winv = 2^-e; x_unit = the activations are LIF
+  // outputs (soft spikes in (0, 0.7)), so x * 2^13 and its residual are representable in fp16
+  const float* Wh = nullptr; const float* Wl = nullptr; float winv = 1.0f; bool x_unit = false;
   bool edge_bias = false;   // tensor-core engines, A_PLAIN: add Q[pt,c] - Kf[nb,c] (per-point products) to the accumulator, see tc_ptx.cuh
   int group = 0;   // 0 or 32
 };

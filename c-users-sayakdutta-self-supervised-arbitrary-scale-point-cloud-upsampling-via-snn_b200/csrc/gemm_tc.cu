@@ -232,7 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           }
         }
         if (part < parts)
-          attn_tail_points<KK>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN), part, parts, npts, n_t, c, bia, sc, sh);
+          attn_tail_points<KK>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN), part, parts, npts, n_t, c, bia, sc, sh, 1.0f);
       } else if (ACT == ACT_LIF) {
         // 8 columns at a time with the next piece's TMEM load in flight (see gemm_tc2.cu): keeps all 8 recurrences
         // interleaved instead of 32 live accumulators forcing ptxas to serialise them
@@ -371,6 +371,20 @@ int tc_make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t 
   return 0;
 }
 
+int tc_make_map_f16(CUtensorMap* m, const void* base, int64_t rows, int K, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled entry point unavailable"); return -2; }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled(f16) failed (%d) rows=%lld K=%d", (int)r, (long long)rows, K); return -2; }
+  return 0;
+}
+
 int* tc_err_flag() {       // one device word per process, zero-initialised
   static int* flag = nullptr;
   if (!flag) {
@@ -439,7 +453,7 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
   p.m_tiles = (int)ceil_div(g.N, TC_BM); p.n_tiles = ceil_div(g.R, tile_rows); p.err = err;
-  p.pool = nullptr; p.pool_T = 0; p.pool_rows = 0;
+  p.pool = nullptr; p.pool_T = 0; p.pool_rows = 0; p.acc_scale = 1.0f; p.x_scale = 1.0f;
   p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
   p.split_w = presplit ? 0 : 1; p.raw_hi = raw_hi; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   const int64_t total = p.n_tiles * p.m_tiles;

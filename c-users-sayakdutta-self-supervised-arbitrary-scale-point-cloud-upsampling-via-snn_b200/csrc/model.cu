@@ -4,6 +4,8 @@
 //   invstd = 1/sqrt(running_var + 1e-5) ; scale = weight*invstd ; shift = bias_bn - running_mean*scale
 //   neuron parameters are clamped to the ranges the reference clamps to at every step
 //   (fn/snn_coder.py:116-118, fd/snn_coder.py:231-235); fd temporal weights are soft-maxed (fd/snn_coder.py:327).
+#include <cmath>
+#include <algorithm>
 #include <math.h>
 #include <string.h>
 #include "../../include/sapcu_b200.h"
@@ -12,6 +14,36 @@
 using namespace sapcu;
 
 namespace {
+
+// IEEE binary16 conversions on the host (round to nearest even, subnormals kept)
+static uint16_t f32_to_f16_rn(float f) {
+  uint32_t x; memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const uint32_t ax = x & 0x7FFFFFFFu;
+  if (ax >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (ax > 0x7F800000u ? 0x200u : 0));   // inf / nan
+  if (ax >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                                      // rounds to inf
+  if (ax < 0x33000001u) return (uint16_t)sign;                                                   // below half the smallest subnormal
+  int exp = (int)(ax >> 23) - 127;
+  uint32_t man = (ax & 0x7FFFFFu) | 0x800000u;                        // 24-bit significand
+  int shift = exp >= -14 ? 13 : 13 + (-14 - exp);                      // bits dropped
+  uint32_t half_man = man >> shift;
+  const uint32_t rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_man & 1u))) ++half_man;
+  uint32_t out;
+  if (exp >= -14) out = ((uint32_t)(exp + 15) << 10) + (half_man - 0x400u);   // carry into the exponent is handled by +
+  else out = half_man;                                                         // subnormal (may round up to the smallest normal)
+  return (uint16_t)(sign | out);
+}
+static float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const int exp = (h >> 10) & 31; const uint32_t man = h & 0x3FFu;
+  float v;
+  if (exp == 0) v = std::ldexp((float)man, -24);
+  else if (exp == 31) { uint32_t b = sign | 0x7F800000u | (man << 13); memcpy(&v, &b, 4); return v; }
+  else v = std::ldexp((float)(man | 0x400u), exp - 25);
+  uint32_t b; memcpy(&b, &v, 4); b |= sign; memcpy(&v, &b, 4);
+  return v;
+}
 
 struct Builder {
   sapcu_model* m;
@@ -48,6 +80,22 @@ struct Builder {
       hi[i] = h; lo[i] = w[i] - h;
     }
     put(hi.data(), n, &L.Whi); put(lo.data(), n, &L.Wlo);
+    // fp16 (hi, lo) of w * 2^e with max |w| * 2^e in [2^13, 2^14): both halves stay in fp16's normal range for every
+    // weight within 2^-9 of the largest one, smaller ones keep 6e-8 absolute (scaled) precision
+    float mx = 0.0f;
+    for (size_t i = 0; i < n; ++i) if (std::isfinite(w[i])) mx = std::max(mx, std::fabs(w[i]));
+    int e = 0;
+    if (mx > 0.0f) { int ex; std::frexp(mx, &ex); e = 14 - ex; }          // mx = f * 2^ex, f in [0.5, 1)
+    const float sc = std::ldexp(1.0f, e);
+    std::vector<uint16_t> hh((n + 1) & ~(size_t)1), hl((n + 1) & ~(size_t)1);
+    for (size_t i = 0; i < n; ++i) {
+      const float ws = w[i] * sc;                                         // exact (power of two)
+      const uint16_t h = f32_to_f16_rn(ws);
+      hh[i] = h; hl[i] = f32_to_f16_rn(ws - f16_to_f32(h));
+    }
+    put(reinterpret_cast<const float*>(hh.data()), hh.size() / 2, &L.Wh);
+    put(reinterpret_cast<const float*>(hl.data()), hl.size() / 2, &L.Wl);
+    L.winv = std::ldexp(1.0f, -e);
   }
   // conv/linear `wname`.weight [N,K(,1,1)], optional .bias; optional BatchNorm `bnname`
   void layer(Layer& L, const std::string& wname, const std::string& bnname, int N, int K, bool bias) {

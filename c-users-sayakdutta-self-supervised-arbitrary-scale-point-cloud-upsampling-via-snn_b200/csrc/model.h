@@ -12,6 +12,9 @@ namespace sapcu {
 struct Layer {     // 1x1 conv / Linear (+ folded eval BatchNorm):  y = (x W^T + bias) * scale + shift
   const float* W = nullptr; const float* Whi = nullptr; const float* Wlo = nullptr; const float* bias = nullptr; const float* scale = nullptr; const float* shift = nullptr;
   int N = 0, K = 0;
+  // fp16 (hi, lo) split of W * 2^wexp for the fp16x3 tensor-core path (inputs known to lie in the LIF output range);
+  // the pointers address raw half data inside the float blob, winv = 2^-wexp
+  const float* Wh = nullptr; const float* Wl = nullptr; float winv = 1.0f;
 };
 struct Neuron {    // clamped per-channel parameters: np = [4][C] (d, a, r, th0); ep = [2][C] (dT, th_rh) for EIF
   const float* np = nullptr; const float* ep = nullptr; int C = 0;

@@ -190,6 +190,7 @@ struct TcParams {
   // EXTRA == 4 (fd conv5, 2-CTA kernel): rows are (point*T + t); the epilogue keeps one running maximum per step and
   // merges them into pool[(patch*T + t), c] with float atomic max -- the [P*T, N] activation never reaches HBM
   float* pool; int pool_T; int64_t pool_rows;     // pool_rows = points per patch * T
+  float acc_scale, x_scale;   // fp16x3 path: operands are W * 2^e and x * x_scale, acc_scale = 2^-e / x_scale undoes both (exact)
   int tile_rows;              // rows a tile advances by: the MMA tile height, or the whole points inside it when EXTRA == 3
   int m_tiles; int64_t n_tiles;
   int split_w;                // 1: W arrives raw and is split in shared memory; 0: map_w / map_wlo hold pre-split (hi, lo)
@@ -230,7 +231,7 @@ __device__ __forceinline__ void edge_fetch8(const TcParams& p, int my_qo, int my
 // the TMEM read and the softmax run under them, the weighted sum consumes them last.
 template <int KK>
 __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tmem_cols, int part, int parts, int npts,
-                                                 int64_t n_t, int c, float bia, float sc, float sh) {
+                                                 int64_t n_t, int c, float bia, float sc, float sh, float acc_scale) {
   const int64_t P_total = p.R / KK;
   const float inv_s = 1.0f / p.at_sqrt;
   const float* vc = p.at_v + c;
@@ -260,7 +261,7 @@ __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tme
     tmem_ld_cols<KK>(tmem_cols + (uint32_t)(pp * KK), av);
     float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < KK; ++j) { av[j] = fmaf(av[j] + bia, sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
+    for (int j = 0; j < KK; ++j) { av[j] = fmaf(fmaf(av[j], acc_scale, bia), sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
     float sum = 0.0f;
 #pragma unroll
     for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx((av[j] - mx) * 1.4426950408889634f); sum += av[j]; }
@@ -275,6 +276,8 @@ __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tme
 // host helpers (gemm_tc.cu)
 int tc_make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld, int box_rows);
 int* tc_err_flag();
+// 2-D fp16 row-major [rows, K] -> boxes of [box_rows, 64 halfs] with 128B swizzle
+int tc_make_map_f16(CUtensorMap* m, const void* base, int64_t rows, int K, int box_rows);
 // rows a tile advances by in the fused attention epilogue (EXTRA == 3): the whole points that fit in the 256-row MMA tile
 // (the few rows behind them are loaded and multiplied but belong to the next tile); 0 = neighbour count not instantiated
 inline int tc_fused_tile_rows(int kk) {
