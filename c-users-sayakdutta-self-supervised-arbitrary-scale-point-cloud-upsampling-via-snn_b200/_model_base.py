@@ -103,5 +103,10 @@ class NativeModel(nn.Module):
         off, rows, cols, ld = (ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64())
         N.check(N.lib().sapcu_model_tap(self._ensure_handle(), name.encode(), S, M, self.mode, ctypes.byref(off), ctypes.byref(rows),
                                         ctypes.byref(cols), ctypes.byref(ld)), "model_tap(%s)" % name)
+        fmt = N.lib().sapcu_model_tap_format(self._ensure_handle(), name.encode())
+        if fmt == 1:      # fp16 (hi, lo) planes of x * 2^13 (see include/sapcu_b200.h)
+            n = rows.value * cols.value
+            h = self._ws.view(torch.float16)[2 * off.value: 2 * off.value + 2 * n].view(2, rows.value, cols.value)
+            return (h[0].float() + h[1].float()) / 8192.0
         flat = self._ws.view(torch.float32) if dtype == torch.float32 else self._ws.view(torch.int32)
         return flat[off.value: off.value + rows.value * ld.value].view(rows.value, ld.value)[:, :cols.value]

@@ -4,6 +4,7 @@
 //   attn_out       : softmax over the k neighbours of a/sqrt(head_dim) and sum_j a_ij (v_j + pos_ij) (:379-391)
 //   group_max      : max over the M points of a patch (adaptive_max_pool1d, :472; fd/snn_coder.py:479)
 //   fn_head        : Linear 256->3, LayerNorm(3), L2 normalise (:545-548)
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "neuron.cuh"
@@ -48,7 +49,8 @@ template <bool PRECISE>
 __global__ void __launch_bounds__(128)
 edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts, int C,
                     const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ scale,
-                    const float* __restrict__ shift, const float* __restrict__ np, int T, float* __restrict__ out) {
+                    const float* __restrict__ shift, const float* __restrict__ np, int T, float* __restrict__ out,
+                    int out_h2, int64_t plane) {
   extern __shared__ float esm[];
   float* xs = esm;                                              // [Mpts][3]
   float* pd = xs + 3 * Mpts;                                    // [2][EPL_G][3]
@@ -104,6 +106,19 @@ edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ i
           u[j] = __fadd_rn(__fmul_rn(y, sc), sh);
         }
         lif_chain_vec<8, PRECISE>(u, p, T);
+        if (out_h2) {                                             // fp16 (hi, lo) planes of y * 2^13 (tc_ptx.cuh)
+          __half* hp = reinterpret_cast<__half*>(out) + (patch0 * kk + g * EPL_G + h) * (int64_t)C + c;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (h + j < n) {
+              const float ys = u[j] * 8192.0f;
+              const __half hv = __float2half_rn(ys);
+              hp[(int64_t)j * C] = hv;
+              hp[plane + (int64_t)j * C] = __float2half_rn(ys - __half2float(hv));
+            }
+          }
+          continue;
+        }
         float* og = o + (int64_t)(g * EPL_G + h) * C;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -257,15 +272,15 @@ __global__ void fn_head_kernel(const float* __restrict__ H, int K, int64_t S, co
 
 int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32_t* idx, int kk, int ldi, int Mpts,
                           int64_t rows, int C, const float* W, const float* bias, const float* scale,
-                          const float* shift, const float* np, int T, float* out, cudaStream_t st, int nsplit) {
+                          const float* shift, const float* np, int T, float* out, cudaStream_t st, int nsplit, bool out_h2) {
   if (rows == 0) return 0;
   if (edge) {
     SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256 && kk >= 1 && rows % ((int64_t)Mpts * kk) == 0, "pointwise3_lif: edge rows must be whole patches of <= 256 points");
     const int64_t S = rows / ((int64_t)Mpts * kk);
     const size_t smem = sizeof(float) * (3 * (size_t)Mpts + 2 * EPL_G * 3) + (size_t)Mpts * kk;
     dim3 grid((unsigned)S, (unsigned)ceil_div(C, 128), (unsigned)(nsplit < 1 ? 1 : nsplit));
-    if (precise) edge_pos_lif_kernel<true><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out);
-    else         edge_pos_lif_kernel<false><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out);
+    if (precise) edge_pos_lif_kernel<true><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out, out_h2 ? 1 : 0, rows * C);
+    else         edge_pos_lif_kernel<false><<<grid, 128, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, W, bias, scale, shift, np, T, out, out_h2 ? 1 : 0, rows * C);
   } else {
     const unsigned grid = (unsigned)ceil_div(rows * C, 256);
     if (precise) pointwise3_lif_kernel<false, true><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);

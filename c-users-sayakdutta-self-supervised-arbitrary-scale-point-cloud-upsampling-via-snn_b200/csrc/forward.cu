@@ -112,6 +112,10 @@ struct G {
   }
 };
 
+// layout of the most recent fn forward's fc_gamma spikes of the last block (the 'trans3.snn_gamma' tap): 1 = fp16 (hi, lo)
+// planes of x * 2^13, 0 = fp32
+static int g_tap_gamma_h2 = 0;
+
 #define SAPCU_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals, const FnPlan& p, int mode, cudaStream_t st) {
@@ -152,13 +156,15 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
     return a;
   };
-  auto edge_pos = [&](int b, float* out, cudaStream_t s_, int nsplit) {
+  auto edge_pos = [&](int b, float* out, cudaStream_t s_, int nsplit, bool h2) {
     const FnBlock& k = f.blk[b];
     const int kk = k.k < M ? k.k : M;
     return launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, P * kk, k.D, k.fc_delta.W, k.fc_delta.bias,
-                                 k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, out, s_, nsplit);
+                                 k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, out, s_, nsplit, h2);
   };
   static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
+  static const int h2_env = getenv("SAPCU_TC_H2_PLANES") ? atoi(getenv("SAPCU_TC_H2_PLANES")) : 1;   // 0 off, 1 both hand-overs, 2 / 3 only the first / second
+  const bool h2_delta = h2_env == 1 || h2_env == 2, h2_gamma = h2_env == 1 || h2_env == 3;
   for (int b = 0; b < 3; ++b) {
     const FnBlock& k = f.blk[b];
     const int D = k.D, kk = k.k < M ? k.k : M;
@@ -166,15 +172,35 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     const int64_t ldin = b == 0 ? 64 : 192;
     const int64_t E = P * kk;
     float* Xb = p.E1;                                             // this block's edge buffer (pos-enc layer 1, then fc_gamma's output)
+    bool xb_h2 = false;                                           // fc_gamma's output stored as fp16 planes (see below)
     SAPCU_TRY(g.layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
     SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
-    SAPCU_TRY(edge_pos(b, Xb, st, 1));
+    if (mode == SAPCU_MODE_FP32) { g_tap_gamma_h2 = 0; SAPCU_TRY(edge_pos(b, Xb, st, 1, false)); }
     if (mode != SAPCU_MODE_FP32) {
-      SAPCU_TRY(g.layer(k.fc_delta2, Xb, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4, nullptr, 0, true));   // input: LIF output
+      // fc_delta2 on the pos-enc layer-1 spikes.  When it runs on the fp16x3 path, edge_pos_lif hands the spikes over as
+      // fp16 (hi, lo) planes of x * 2^13 (same bytes as fp32) and the contraction loads them without converting.
+      {
+        GemmArgs a;
+        const Layer& L = k.fc_delta2;
+        a.A = Xb; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
+        a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_delta2.np;
+        a.Y = p.E2; a.ldc = D; a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;   // input: LIF output
+        a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+        a.x_h2 = h2_delta && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_fp16x3(a);
+        SAPCU_TRY(edge_pos(b, Xb, st, 1, a.x_h2));
+        SAPCU_TRY(g.run(a, A_PLAIN));
+      }
       {
         float* QK = p.E3;                                          // [W q | W k], [P, 2D]
         GemmArgs a = gamma_args(b, p.E2, Xb, QK);
-        if (factorise && kk >= 2 && gemm_tc_supported(a, A_PLAIN)) {
+        a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+        {   // fc_gamma's spikes go to fc_gamma2 only: hand them over as fp16 planes when both run on the 2-CTA fp16x3 path
+          GemmArgs a2 = gamma2_args(b, Xb, p.E2);
+          xb_h2 = h2_gamma && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fp16x3(a2);
+        }
+        a.out_h2 = xb_h2;
+        if (b == 2) g_tap_gamma_h2 = xb_h2 ? 1 : 0;
+        if (factorise && kk >= 2 && (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN))) {
           Layer Lw = k.fc_gamma;
           Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;
           SAPCU_TRY(g.layer(Lw, p.QKV, 3 * D, P, QK, 2 * D, ACT_NONE));
@@ -187,6 +213,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
       }
       {
         GemmArgs a = gamma2_args(b, Xb, p.E2);
+        a.x_h2 = xb_h2;
         if (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN)) {
           SAPCU_TRY(g.run(a, A_PLAIN));
         } else {
@@ -366,6 +393,12 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
     SAPCU_TRY(fd_chunk(m->fd, d_patches + s0 * M * 3, s, M, d_dist + s0, forced, p, mode, st));
   }
   if (mode != SAPCU_MODE_FP32) SAPCU_TRY(gemm_tc_check(st));
+  return 0;
+}
+
+int sapcu_model_tap_format(const sapcu_model* m, const char* name) {
+  SAPCU_REQUIRE(m && name, "model_tap_format: bad argument");
+  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_gamma") return g_tap_gamma_h2;
   return 0;
 }
 

@@ -44,6 +44,9 @@ struct GemmArgs {
   // fp16x3 tensor-core path (2-CTA kernel): half (hi, lo) copies of W * 2^e, winv = 2^-e; x_unit = the activations are LIF
   // outputs (soft spikes in (0, 0.7)), so x * 2^13 and its residual are representable in fp16
   const float* Wh = nullptr; const float* Wl = nullptr; float winv = 1.0f; bool x_unit = false;
+  // fp16 (hi, lo) plane format of x * 2^13 ([R, K] halfs each, hi plane first): x_h2 = A is stored that way (consumed by the
+  // fp16x3 kernel without conversion), out_h2 = the LIF epilogue writes Y that way; both need ld == row length
+  bool x_h2 = false, out_h2 = false;
   bool edge_bias = false;   // tensor-core engines, A_PLAIN: add Q[pt,c] - Kf[nb,c] (per-point products) to the accumulator, see tc_ptx.cuh
   int group = 0;   // 0 or 32
 };

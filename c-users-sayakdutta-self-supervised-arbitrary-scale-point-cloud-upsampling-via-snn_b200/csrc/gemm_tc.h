@@ -12,4 +12,7 @@ int gemm_tc_check(cudaStream_t st);
 // 2-CTA (cta_group::2) variant for N % 256 == 0 problems (gemm_tc2.cu)
 bool gemm_tc2_supported(const GemmArgs& g, int amode);
 int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st);
+// true when launch_gemm_tc2 would run this problem on the fp16x3 operand path (needed to agree on the fp16-plane
+// activation format between the kernel that writes a tensor and the one that reads it)
+bool gemm_tc2_fp16x3(const GemmArgs& g);
 }  // namespace sapcu

@@ -80,12 +80,16 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives
 // splitter turns the raw fp32 activation tile into fp16 (hi, lo) of x * x_scale, and 12 kind::f16 MMAs per 64-wide
 // k-block (hi*hi + hi*lo + lo*hi, fp32 accumulate) replace 24 kind::tf32 ones: the same 22-bit products at twice the
 // tensor-pipe rate and 2/3 of the operand bytes.  Stage = W_hi, W_lo, X_hi, X_lo (16 KiB each) + 32 KiB raw X; 2 stages.
-template <int ACT, int EXTRA, int KK, bool H16 = false>
+template <int ACT, int EXTRA, int KK, int HM = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((T2_EPI_WARP0 + T2_EPI) * 32, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
-                const __grid_constant__ CUtensorMap map_x, const TcParams p) {
-  constexpr int T2_STAGES = H16 ? 2 : 3;
-  constexpr uint32_t T2_STAGE_BYTES = (H16 ? 6 : 4) * TC_TILE_BYTES;
+                const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2, const TcParams p) {
+  // HM: 0 = 3xTF32; 1 = fp16x3, raw fp32 activations converted by the splitter warps; 2 = fp16x3, activations already
+  // stored as fp16 (hi, lo) planes of x * 2^13 by the kernel that produced them (map_x = hi plane, map_x2 = lo plane): four
+  // TMA loads per stage, no conversion, no raw staging -- a third less shared-memory traffic per k-block
+  constexpr bool H16 = HM != 0;
+  constexpr int T2_STAGES = HM == 1 ? 2 : 3;
+  constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : 4) * TC_TILE_BYTES;
   constexpr int BKE = H16 ? 64 : TC_BK;                    // k elements per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -139,12 +143,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             if (kp >= nk) { kp -= nk; tp += npairs; }
             if (kp < nk && tp < total_tiles) {
               tma_prefetch_l2_2d(&map_x, kp * BKE, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
-              if (H16) tma_prefetch_l2_2d(&map_x, kp * BKE + 32, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
+              if (HM == 1) tma_prefetch_l2_2d(&map_x, kp * BKE + 32, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
+              if (HM == 2) tma_prefetch_l2_2d(&map_x2, kp * BKE, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
             }
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
-          if (H16) {
+          if (HM == 2) {
+            mbar_expect_tx(bar_raw(s), 4 * TC_TILE_BYTES);
+            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // four fp16 tiles: 64 halfs x 128 rows
+            tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * BKE, wrow);
+            tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
+            tma_load_2d(st + 3 * TC_TILE_BYTES, &map_x2, bar_raw(s), kb * BKE, xrow);
+          } else if (H16) {
             mbar_expect_tx(bar_raw(s), 4 * TC_TILE_BYTES);
             tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // fp16 tiles: 64 halfs x 128 rows
             tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * BKE, wrow);
@@ -209,6 +220,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
       for (int kb = 0; kb < nk; ++kb) {
         if (!(ok = mbar_wait(bar_raw(s), ph, p.err))) break;
         uint8_t* st = smem_gen + s * T2_STAGE_BYTES;
+        if (HM == 2) {                                            // operands arrive ready-made: forward the arrival
+          if (rank == 0) mbar_arrive(bar_split(s)); else mbar_arrive_cluster(bar_split(s), 0);
+          if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
+          continue;
+        }
         if (H16) {
           // raw fp32 boxes (128B-swizzled rows of 32 floats) -> fp16 hi / lo tiles in the same swizzled K-major layout:
           // item (r, c) = 8 consecutive k of row r: two 16-byte raw chunks in, one 16-byte chunk out per tile
@@ -333,7 +349,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j] + bia, sc, sh);
             lif_chain_vec_fast<8>(u, np, p.T);
             float* yp = p.Y + r0 * p.ldc + c;
-            if (nrows == 8) {
+            if (p.out_h2) {                                       // fp16 (hi, lo) planes of y * 2^13 for a fp16x3 consumer
+              __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
+              __half* lp = hp + p.R * p.ldc;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (j < nrows) {
+                  const float ys = u[j] * 8192.0f;
+                  const __half h = __float2half_rn(ys);
+                  hp[(int64_t)j * p.ldc] = h;
+                  lp[(int64_t)j * p.ldc] = __float2half_rn(ys - __half2float(h));
+                }
+              }
+            } else if (nrows == 8) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { *yp = u[j]; yp += p.ldc; }
             } else {
@@ -447,7 +475,7 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   if (enabled < 0) { const char* e = getenv("SAPCU_TC_2CTA"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
   const bool fuse = tc_fuse_attn_out_enabled();
   GemmArgs base = g;
-  base.at_pos = nullptr; base.pool = nullptr;
+  base.at_pos = nullptr; base.pool = nullptr; base.x_h2 = false; base.out_h2 = false;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
   if (g.N % 256 != 0 || g.act == ACT_GELU) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
@@ -463,6 +491,15 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   return true;
 }
 
+// fp16x3 operands: only where the activations are LIF outputs, the weights carry their half split and the epilogue
+// flavour is instantiated
+bool gemm_tc2_fp16x3(const GemmArgs& g) {
+  static int h16_env = -1;
+  if (h16_env < 0) { const char* e = getenv("SAPCU_TC_FP16X3"); h16_env = (e && atoi(e) == 0) ? 0 : 1; }
+  return h16_env && g.x_unit && g.Wh && g.Wl && g.K % 64 == 0 && g.tc_passes != 1 && !g.residual &&
+         (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool) || g.act == ACT_NONE);
+}
+
 int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   SAPCU_REQUIRE(gemm_tc2_supported(g, A_PLAIN), "gemm_tc2: unsupported problem");
   static bool attr_done = false;
@@ -471,10 +508,13 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LIF, 2, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
     SAPCU_T2_ATTR(ACT_NONE, 3, 12); SAPCU_T2_ATTR(ACT_NONE, 3, 18); SAPCU_T2_ATTR(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR
-#define SAPCU_T2_ATTR_H(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
+#define SAPCU_T2_ATTR_H(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
     SAPCU_T2_ATTR_H(ACT_LIF, 0, 1); SAPCU_T2_ATTR_H(ACT_LIF, 2, 1); SAPCU_T2_ATTR_H(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_H(ACT_NONE, 0, 1);
     SAPCU_T2_ATTR_H(ACT_NONE, 3, 12); SAPCU_T2_ATTR_H(ACT_NONE, 3, 18); SAPCU_T2_ATTR_H(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_H
+#define SAPCU_T2_ATTR_P(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
+    SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
+#undef SAPCU_T2_ATTR_P
     attr_done = true;
   }
   int* err = tc_err_flag();
@@ -482,19 +522,26 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   static int l2pf = -1;
   if (l2pf < 0) { const char* f = getenv("SAPCU_TC_L2PF"); l2pf = f ? atoi(f) : 4; }
   const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : T2_BN;
-  // fp16x3 operands: only where the activations are LIF outputs, the weights carry their half split and the epilogue
-  // flavour is instantiated
-  static int h16_env = -1;
-  if (h16_env < 0) { const char* e = getenv("SAPCU_TC_FP16X3"); h16_env = (e && atoi(e) == 0) ? 0 : 1; }
-  const bool h16 = h16_env && g.x_unit && g.Wh && g.Wl && g.K % 64 == 0 && g.tc_passes != 1 && !g.residual &&
-                   (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool) || g.act == ACT_NONE);
-  CUtensorMap mw, mwlo, mx;
+  const bool h16 = gemm_tc2_fp16x3(g);
+  const bool pre = h16 && g.x_h2;                            // activations already stored as fp16 (hi, lo) planes
+  SAPCU_REQUIRE(!g.x_h2 || (h16 && g.lda == g.K && (g.at_pos || g.act == ACT_LIF)), "gemm_tc2: fp16-plane input needs the fp16x3 path and lda == K");
+  SAPCU_REQUIRE(!g.out_h2 || (g.act == ACT_LIF && g.ldc == g.N), "gemm_tc2: fp16-plane output is a LIF epilogue with ldc == N");
+  CUtensorMap mw, mwlo, mx, mx2;
   int rc = h16 ? tc_make_map_f16(&mw, g.Wh, g.N, g.K, 128) : tc_make_map(&mw, g.Whi, g.N, g.K, g.K, 128);
   if (rc) return rc;
   rc = h16 ? tc_make_map_f16(&mwlo, g.Wl, g.N, g.K, 128) : tc_make_map(&mwlo, g.Wlo, g.N, g.K, g.K, 128);
   if (rc) return rc;
-  rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, T2_BN / 2);
-  if (rc) return rc;
+  if (pre) {
+    const uint16_t* hp = reinterpret_cast<const uint16_t*>(g.A);
+    rc = tc_make_map_f16(&mx, hp, g.R, g.K, T2_BN / 2);
+    if (rc) return rc;
+    rc = tc_make_map_f16(&mx2, hp + g.R * g.K, g.R, g.K, T2_BN / 2);
+    if (rc) return rc;
+  } else {
+    rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, T2_BN / 2);
+    if (rc) return rc;
+    mx2 = mx;
+  }
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
@@ -502,12 +549,21 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   p.pool = g.pool; p.pool_T = g.pool_T; p.pool_rows = (int64_t)g.pool_T * g.pool_M;
   p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
   p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
+  p.out_h2 = g.out_h2 ? 1 : 0;
   p.x_scale = h16 ? 8192.0f : 1.0f;                         // soft spikes lie in (0, 0.7): x * 2^13 < 2^13, residual * 2^13 >= fp16's normal range
   p.acc_scale = h16 ? g.winv / 8192.0f : 1.0f;
   const int64_t total = p.n_tiles * p.m_tiles;
   int pairs = (int)(total < kNumSMs / 2 ? total : kNumSMs / 2);
   const int grid = 2 * pairs;
-#define SAPCU_T2_LAUNCH_H(A, X, KQ) gemm_tc2_kernel<A, X, KQ, true><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
+#define SAPCU_T2_LAUNCH_H(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 1><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
+#define SAPCU_T2_LAUNCH_P(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 2><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
+  if (pre) {
+    if (g.at_pos) {
+      if (g.kk == 12) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 24);
+    } else SAPCU_T2_LAUNCH_P(ACT_LIF, 0, 1);
+    SAPCU_LAUNCH_CHECK();
+    return 0;
+  }
   if (h16) {
     if (g.at_pos) {
       if (g.kk == 12) SAPCU_T2_LAUNCH_H(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH_H(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH_H(ACT_NONE, 3, 24);
@@ -520,7 +576,8 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     return 0;
   }
 #undef SAPCU_T2_LAUNCH_H
-#define SAPCU_T2_LAUNCH(A, X, KQ) gemm_tc2_kernel<A, X, KQ><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, p)
+#undef SAPCU_T2_LAUNCH_P
+#define SAPCU_T2_LAUNCH(A, X, KQ) gemm_tc2_kernel<A, X, KQ><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
   if (g.at_pos) {
     if (g.kk == 12) SAPCU_T2_LAUNCH(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH(ACT_NONE, 3, 24);
   }

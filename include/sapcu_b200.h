@@ -146,6 +146,10 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
  * float offset  off + r*ld + c.  Returns SAPCU_EINVAL for an unknown name. */
 int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, int mode,
                     int64_t* off_floats, int64_t* rows, int64_t* cols, int64_t* ld);
+/* Storage format the most recent forward used for a tap: 0 = fp32 [rows, ld]; 1 = two consecutive fp16 planes
+ * [rows, cols] (hi, then lo) of x * 2^13, i.e. x = (hi + lo) / 8192 -- the hand-over format between an epilogue and the
+ * fp16x3 contraction that consumes its spikes (MODE_TC, 'trans3.snn_gamma').  Negative: error code. */
+int sapcu_model_tap_format(const sapcu_model* m, const char* name);
 
 /* ------------------------------------------------------------------------------------
  * Stand-alone operators exported for unit parity tests (each is used by the forwards above).
