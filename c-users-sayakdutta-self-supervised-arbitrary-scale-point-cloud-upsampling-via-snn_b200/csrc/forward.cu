@@ -114,7 +114,7 @@ struct G {
 
 // layout of the most recent fn forward's fc_gamma spikes of the last block (the 'trans3.snn_gamma' tap): 1 = fp16 (hi, lo)
 // planes of x * 2^13, 0 = fp32
-static int g_tap_gamma_h2 = 0;
+static int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0;
 
 #define SAPCU_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
@@ -163,8 +163,12 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
                                  k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, out, s_, nsplit, h2);
   };
   static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
-  static const int h2_env = getenv("SAPCU_TC_H2_PLANES") ? atoi(getenv("SAPCU_TC_H2_PLANES")) : 1;   // 0 off, 1 both hand-overs, 2 / 3 only the first / second
-  const bool h2_delta = h2_env == 1 || h2_env == 2, h2_gamma = h2_env == 1 || h2_env == 3;
+  // fp16-plane hand-overs: 0 off; 1 (default) pos-enc layer 1 -> fc_delta2 and fc_gamma -> fc_gamma2; 2 / 3 only the first /
+  // second; 4 only pos (fc_delta2 -> fc_gamma + attention tail); 5 all three.  The pos planes are measured slower (the
+  // attention tail then issues two 2-byte loads per operand instead of one 4-byte load) and stay off.
+  static const int h2_env = getenv("SAPCU_TC_H2_PLANES") ? atoi(getenv("SAPCU_TC_H2_PLANES")) : 1;
+  const bool h2_delta = h2_env == 1 || h2_env == 2 || h2_env == 5, h2_gamma = h2_env == 1 || h2_env == 3 || h2_env == 5,
+             h2_pos = h2_env == 4 || h2_env == 5;
   for (int b = 0; b < 3; ++b) {
     const FnBlock& k = f.blk[b];
     const int D = k.D, kk = k.k < M ? k.k : M;
@@ -172,10 +176,10 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     const int64_t ldin = b == 0 ? 64 : 192;
     const int64_t E = P * kk;
     float* Xb = p.E1;                                             // this block's edge buffer (pos-enc layer 1, then fc_gamma's output)
-    bool xb_h2 = false;                                           // fc_gamma's output stored as fp16 planes (see below)
+    bool xb_h2 = false, e2_h2 = false;                            // fc_gamma's output / pos stored as fp16 planes (see below)
     SAPCU_TRY(g.layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
     SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
-    if (mode == SAPCU_MODE_FP32) { g_tap_gamma_h2 = 0; SAPCU_TRY(edge_pos(b, Xb, st, 1, false)); }
+    if (mode == SAPCU_MODE_FP32) { g_tap_gamma_h2 = 0; g_tap_delta2_h2 = 0; SAPCU_TRY(edge_pos(b, Xb, st, 1, false)); }
     if (mode != SAPCU_MODE_FP32) {
       // fc_delta2 on the pos-enc layer-1 spikes.  When it runs on the fp16x3 path, edge_pos_lif hands the spikes over as
       // fp16 (hi, lo) planes of x * 2^13 (same bytes as fp32) and the contraction loads them without converting.
@@ -187,6 +191,14 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
         a.Y = p.E2; a.ldc = D; a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;   // input: LIF output
         a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
         a.x_h2 = h2_delta && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_fp16x3(a);
+        {   // pos (E2) has two readers, fc_gamma's contraction and the fused attention tail: planes when both take them
+          GemmArgs a1 = gamma_args(b, p.E2, Xb, p.E3), a2 = gamma2_args(b, Xb, p.E2);
+          a1.tc_passes = a2.tc_passes = a.tc_passes;
+          e2_h2 = h2_pos && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a1, A_PLAIN) &&
+                  gemm_tc2_fp16x3(a1) && gemm_tc2_supported(a2, A_PLAIN);
+        }
+        a.out_h2 = e2_h2;
+        if (b == 2) g_tap_delta2_h2 = e2_h2 ? 1 : 0;
         SAPCU_TRY(edge_pos(b, Xb, st, 1, a.x_h2));
         SAPCU_TRY(g.run(a, A_PLAIN));
       }
@@ -198,7 +210,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
           GemmArgs a2 = gamma2_args(b, Xb, p.E2);
           xb_h2 = h2_gamma && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fp16x3(a2);
         }
-        a.out_h2 = xb_h2;
+        a.out_h2 = xb_h2; a.x_h2 = e2_h2;
         if (b == 2) g_tap_gamma_h2 = xb_h2 ? 1 : 0;
         if (factorise && kk >= 2 && (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN))) {
           Layer Lw = k.fc_gamma;
@@ -213,7 +225,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
       }
       {
         GemmArgs a = gamma2_args(b, Xb, p.E2);
-        a.x_h2 = xb_h2;
+        a.x_h2 = xb_h2; a.pos_h2 = e2_h2;
         if (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN)) {
           SAPCU_TRY(g.run(a, A_PLAIN));
         } else {
@@ -399,6 +411,7 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
 int sapcu_model_tap_format(const sapcu_model* m, const char* name) {
   SAPCU_REQUIRE(m && name, "model_tap_format: bad argument");
   if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_gamma") return g_tap_gamma_h2;
+  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_delta2") return g_tap_delta2_h2;
   return 0;
 }
 

@@ -46,7 +46,7 @@ struct GemmArgs {
   const float* Wh = nullptr; const float* Wl = nullptr; float winv = 1.0f; bool x_unit = false;
   // fp16 (hi, lo) plane format of x * 2^13 ([R, K] halfs each, hi plane first): x_h2 = A is stored that way (consumed by the
   // fp16x3 kernel without conversion), out_h2 = the LIF epilogue writes Y that way; both need ld == row length
-  bool x_h2 = false, out_h2 = false;
+  bool x_h2 = false, out_h2 = false, pos_h2 = false;   // pos_h2: at_pos (fused attention tail) is stored as planes
   bool edge_bias = false;   // tensor-core engines, A_PLAIN: add Q[pt,c] - Kf[nb,c] (per-point products) to the accumulator, see tc_ptx.cuh
   int group = 0;   // 0 or 32
 };

@@ -306,7 +306,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             const int cb = (int)(tn % p.m_tiles) * 256 + (int)rank * 128;
             for (int i = (warp - T2_EPI_WARP0) * 32 + lane; i < TR * 4; i += T2_EPI * 32) {
               const int64_t row = row0 + (i >> 2);
-              if (row < p.R) prefetch_l2(p.at_pos + row * p.N + cb + (i & 3) * 32);
+              if (row >= p.R) continue;
+              if (p.pos_h2) prefetch_l2(reinterpret_cast<const __half*>(p.at_pos) + ((i & 2) ? p.R * (int64_t)p.N : 0) + row * p.N + cb + (i & 1) * 64);
+              else prefetch_l2(p.at_pos + row * p.N + cb + (i & 3) * 32);
             }
           }
         }
@@ -475,7 +477,7 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   if (enabled < 0) { const char* e = getenv("SAPCU_TC_2CTA"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
   const bool fuse = tc_fuse_attn_out_enabled();
   GemmArgs base = g;
-  base.at_pos = nullptr; base.pool = nullptr; base.x_h2 = false; base.out_h2 = false;
+  base.at_pos = nullptr; base.pool = nullptr; base.x_h2 = false; base.out_h2 = false; base.pos_h2 = false;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
   if (g.N % 256 != 0 || g.act == ACT_GELU) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
@@ -513,7 +515,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     SAPCU_T2_ATTR_H(ACT_NONE, 3, 12); SAPCU_T2_ATTR_H(ACT_NONE, 3, 18); SAPCU_T2_ATTR_H(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_H
 #define SAPCU_T2_ATTR_P(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
+    SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_LIF, 2, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_P
     attr_done = true;
   }
@@ -549,7 +551,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   p.pool = g.pool; p.pool_T = g.pool_T; p.pool_rows = (int64_t)g.pool_T * g.pool_M;
   p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
   p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
-  p.out_h2 = g.out_h2 ? 1 : 0;
+  p.out_h2 = g.out_h2 ? 1 : 0; p.pos_h2 = g.pos_h2 ? 1 : 0;
   p.x_scale = h16 ? 8192.0f : 1.0f;                         // soft spikes lie in (0, 0.7): x * 2^13 < 2^13, residual * 2^13 >= fp16's normal range
   p.acc_scale = h16 ? g.winv / 8192.0f : 1.0f;
   const int64_t total = p.n_tiles * p.m_tiles;
@@ -560,7 +562,8 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   if (pre) {
     if (g.at_pos) {
       if (g.kk == 12) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 24);
-    } else SAPCU_T2_LAUNCH_P(ACT_LIF, 0, 1);
+    } else if (g.edge_bias) SAPCU_T2_LAUNCH_P(ACT_LIF, 2, 1);
+    else SAPCU_T2_LAUNCH_P(ACT_LIF, 0, 1);
     SAPCU_LAUNCH_CHECK();
     return 0;
   }
