@@ -6,6 +6,7 @@
 //   head_attention   : StandardSelfAttention core on [S,64] (:782-795)
 //   layernorm_rows   : LayerNorm over the last dim (:798)
 //   fd_tail          : Linear 32 -> 1 + Softplus(beta=5) (:722-725)
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "neuron.cuh"
@@ -64,7 +65,10 @@ __global__ void __launch_bounds__(EGU_THREADS)
 edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __restrict__ idx, int kk, int Mpts,
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ np, const float* __restrict__ ep, int T,
-                          float* __restrict__ U, float* __restrict__ spk, int64_t ldspk_row, int ldo) {
+                          float* __restrict__ U, float* __restrict__ spk, int64_t ldspk_row, int ldo,
+                          int h2, float* __restrict__ spk0, int64_t plane, int choff) {
+  // h2: spikes go out as fp16 (hi, lo) planes of s * 2^13, row (point*T + t) of `ldo` halfs, for the fp16x3 conv5; the
+  // step-0 spikes -- the only ones the next block's graph and EdgeConv read -- also as fp32 into spk0 [point, ldo]
   extern __shared__ float egs[];
   float* Ps = egs;                                                 // [Mpts][128]
   uint8_t* nbs = reinterpret_cast<uint8_t*>(egs + Mpts * 128);     // [Mpts][kk] local neighbour indices (Mpts <= 256)
@@ -109,22 +113,33 @@ edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __
     float s[EGU_PTS];
 #pragma unroll
     for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, true>(u[a], m[a], th[a], rho[a], k);
+    auto put = [&](int a, int t, float v) {
+      if (h2) {
+        __half* hp = reinterpret_cast<__half*>(spk) + ((patch0 + i0 + a) * T + t) * (int64_t)ldo + choff + c;
+        const float ys = v * 8192.0f;
+        const __half hv = __float2half_rn(ys);
+        hp[0] = hv; hp[plane] = __float2half_rn(ys - __half2float(hv));
+        if (t == 0) spk0[(patch0 + i0 + a) * (int64_t)ldo + choff + c] = v;
+      } else {
+        spk[(patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c] = v;
+      }
+    };
 #pragma unroll
     for (int a = 0; a < EGU_PTS; ++a)
-      if (i0 + a < i_end) spk[(patch0 + i0 + a) * ldspk_row + c] = s[a];
+      if (i0 + a < i_end) put(a, 0, s[a]);
     for (int t = 1; t < T; ++t) {
 #pragma unroll
       for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, false>(0.0f, m[a], th[a], rho[a], k);
 #pragma unroll
       for (int a = 0; a < EGU_PTS; ++a)
-        if (i0 + a < i_end) spk[(patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c] = s[a];
+        if (i0 + a < i_end) put(a, t, s[a]);
     }
   }
 }
 
 int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* idx, int kk, int Mpts, int64_t S,
                               const float* scale, const float* shift, const float* np, const float* ep, int T, float* U,
-                              float* spk, int64_t ldspk_row, int ldo, cudaStream_t st) {
+                              float* spk, int64_t ldspk_row, int ldo, cudaStream_t st, bool h2, float* spk0, int64_t plane, int choff) {
   SAPCU_REQUIRE(C % 128 == 0, "edge_gather_unroll: C=%d must be a multiple of 128", C);
   SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256, "edge_gather_unroll: M=%d outside [1,256]", Mpts);
   if (S == 0) return 0;
@@ -137,8 +152,8 @@ int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* i
   }
   SAPCU_REQUIRE(smem <= 160 * 1024, "edge_gather_unroll: patch too large for shared memory");
   dim3 grid((unsigned)S, (unsigned)(C / 128));
-  if (eif) edge_gather_unroll_kernel<true><<<grid, EGU_THREADS, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
-  else     edge_gather_unroll_kernel<false><<<grid, EGU_THREADS, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo);
+  if (eif) edge_gather_unroll_kernel<true><<<grid, EGU_THREADS, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo, h2 ? 1 : 0, spk0, plane, choff);
+  else     edge_gather_unroll_kernel<false><<<grid, EGU_THREADS, smem, st>>>(PQ, C, idx, kk, Mpts, scale, shift, np, ep, T, U, spk, ldspk_row, ldo, h2 ? 1 : 0, spk0, plane, choff);
   SAPCU_LAUNCH_CHECK();
   return 0;
 }
@@ -148,7 +163,7 @@ int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* i
 template <bool EIF, bool PRECISE>
 __global__ void neuron_unroll_kernel(const float* __restrict__ U, int64_t ldu, int64_t rows, int C, int T,
                                      const float* __restrict__ np, const float* __restrict__ ep, int all_steps,
-                                     float* __restrict__ out, int64_t ldo) {
+                                     float* __restrict__ out, int64_t ldo, int h2, float* __restrict__ out0, int64_t plane, int choff) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= rows * C) return;
   const int64_t row = e / C;
@@ -161,7 +176,13 @@ __global__ void neuron_unroll_kernel(const float* __restrict__ U, int64_t ldu, i
   float* o = all_steps ? out + row * (int64_t)T * ldo + c : out + row * ldo + c;
   for (int t = 0; t < T; ++t) {
     s = neuron_step<EIF, PRECISE>(s, st, p, q);
-    if (all_steps) o[(int64_t)t * ldo] = s;
+    if (h2) {                                            // fp16 planes for conv5 + fp32 step-0 copy (see edge_gather_unroll)
+      __half* hp = reinterpret_cast<__half*>(out) + (row * T + t) * ldo + choff + c;
+      const float ys = s * 8192.0f;
+      const __half hv = __float2half_rn(ys);
+      hp[0] = hv; hp[plane] = __float2half_rn(ys - __half2float(hv));
+      if (t == 0) out0[row * ldo + choff + c] = s;
+    } else if (all_steps) o[(int64_t)t * ldo] = s;
   }
   if (!all_steps) *o = s;
 }
@@ -250,10 +271,11 @@ int launch_fd_block0(const float* xyz, const int32_t* idx, int ldi, int Mpts, in
 }
 
 int launch_neuron_unroll(bool eif, bool precise, const float* U, int64_t ldu, int64_t rows, int C, int T,
-                         const float* np, const float* ep, int all_steps, float* out, int64_t ldo, cudaStream_t st) {
+                         const float* np, const float* ep, int all_steps, float* out, int64_t ldo, cudaStream_t st,
+                         bool h2, float* out0, int64_t plane, int choff) {
   if (rows == 0) return 0;
   const unsigned grid = (unsigned)ceil_div(rows * C, 256);
-#define SAPCU_NU(E, P) neuron_unroll_kernel<E, P><<<grid, 256, 0, st>>>(U, ldu, rows, C, T, np, ep, all_steps, out, ldo)
+#define SAPCU_NU(E, P) neuron_unroll_kernel<E, P><<<grid, 256, 0, st>>>(U, ldu, rows, C, T, np, ep, all_steps, out, ldo, h2 ? 1 : 0, out0, plane, choff)
   if (eif) { if (precise) SAPCU_NU(true, true); else SAPCU_NU(true, false); }
   else     { if (precise) SAPCU_NU(false, true); else SAPCU_NU(false, false); }
 #undef SAPCU_NU

@@ -55,7 +55,7 @@ FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
 }
 
 struct FdPlan {
-  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *PQ, *SPK, *AGG, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
+  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *PQ, *SPK, *SPK0, *AGG, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
   size_t bytes; int k, kmax0;
 };
 FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
@@ -68,6 +68,7 @@ FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
   p.U0 = b.take<float>(P * 64); p.U1 = b.take<float>(P * 128); p.U2 = b.take<float>(P * 256); p.U3 = b.take<float>(P * 512);
   p.PQ = b.take<float>(P * 1024);          // factorised EdgeConv (P | Q) rows, tensor-core mode
   p.SPK = b.take<float>(P * f.T * 960);
+  p.SPK0 = b.take<float>(P * 960);         // fp32 copy of the step-0 spikes when SPK holds fp16 planes (tensor-core modes)
   p.AGG = b.take<float>(P * f.T * f.emb);
   p.POOL = b.take<float>(s * f.T * f.emb); p.Z = b.take<float>(s * f.emb);
   p.D0 = b.take<float>(s * 256); p.T1 = b.take<float>(s * 128); p.R = b.take<float>(s * 128);
@@ -114,7 +115,7 @@ struct G {
 
 // layout of the most recent fn forward's fc_gamma spikes of the last block (the 'trans3.snn_gamma' tap): 1 = fp16 (hi, lo)
 // planes of x * 2^13, 0 = fp32
-static int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0;
+static int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0, g_tap_spk_h2 = 0;
 
 #define SAPCU_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
@@ -279,22 +280,46 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
   }
   SAPCU_TRY(g.layer(f.fusion, p.F0, 64 * f.nscales, P, p.U0, 64, ACT_LEAKY));
   const int64_t ldspk = (int64_t)T * 960;
-  SAPCU_TRY(launch_neuron_unroll(true, precise, p.U0, 64, P, 64, T, f.blk[0].np, f.blk[0].ep, 1, p.SPK, 960, st));
+  // conv5 (multi-scale fusion) + LeakyReLU + max over the patch's points: in the tensor-core modes the 2-CTA kernel
+  // reduces in its epilogue (per-thread running maxima, then float atomic max) and AGG is never written
+  GemmArgs c5;
+  {
+    const Layer& L = f.msc;
+    c5.A = p.SPK; c5.lda = 960; c5.R = P * T; c5.K = L.K; c5.W = L.W; c5.Whi = L.Whi; c5.Wlo = L.Wlo; c5.N = L.N;
+    c5.bias = L.bias; c5.scale = L.scale; c5.shift = L.shift; c5.act = ACT_LEAKY; c5.Y = p.AGG; c5.ldc = f.emb;
+    c5.pool = p.POOL; c5.pool_T = T; c5.pool_M = M;
+    c5.Wh = L.Wh; c5.Wl = L.Wl; c5.winv = L.winv; c5.x_unit = true;                   // the spike tensor
+    c5.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+  }
+  static const bool fuse_pool = !(getenv("SAPCU_TC_FUSE_POOL") && atoi(getenv("SAPCU_TC_FUSE_POOL")) == 0);
+  static const bool spk_planes = !(getenv("SAPCU_TC_SPIKE_PLANES") && atoi(getenv("SAPCU_TC_SPIKE_PLANES")) == 0);
+  const bool pooled = mode != SAPCU_MODE_FP32 && fuse_pool && gemm_tc2_supported(c5, A_PLAIN);
+  // When conv5 runs on the fp16x3 path the spike tensor is stored as fp16 (hi, lo) planes of s * 2^13 (rows = point*T + t)
+  // that it loads without converting; the step-0 spikes, which the graphs and EdgeConvs of the next block read, are
+  // also kept in fp32 (SPK0, [P, 960]).
+  const bool spk_h2 = pooled && spk_planes && gemm_tc2_fp16x3(c5);
+  g_tap_spk_h2 = spk_h2 ? 1 : 0;
+  const int64_t plane = P * T * 960;
+  const float* S0 = spk_h2 ? p.SPK0 : p.SPK;                     // step-0 spikes: row stride ld0
+  const int64_t ld0 = spk_h2 ? 960 : ldspk;
+  if (spk_h2) SAPCU_TRY(launch_neuron_unroll(true, precise, p.U0, 64, P, 64, T, f.blk[0].np, f.blk[0].ep, 1, p.SPK, 960, st, true, p.SPK0, plane, 0));
+  else SAPCU_TRY(launch_neuron_unroll(true, precise, p.U0, 64, P, 64, T, f.blk[0].np, f.blk[0].ep, 1, p.SPK, 960, st));
   const int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 512};
   const int off_in[3] = {0, 64, 192}, off_out[3] = {64, 192, 448};
   float* U[3] = {p.U1, p.U2, p.U3};
   for (int b = 0; b < 3; ++b) {
     const int32_t* idx = forced[b];
     if (!idx) {
-      SAPCU_TRY(launch_intra_knn(p.SPK + off_in[b], ldspk, s, M, cin[b], p.k, p.idxf, st));
+      SAPCU_TRY(launch_intra_knn(S0 + off_in[b], ld0, s, M, cin[b], p.k, p.idxf, st));
       idx = p.idxf;
     }
     if (mode != SAPCU_MODE_FP32) {
       // factorised EdgeConv: one per-POINT contraction [P, Cin] x [2 Cout, Cin]^T, then gather / BN / LeakyReLU / max_k
       Layer L = f.convf[b];
-      SAPCU_TRY(g.layer(L, p.SPK + off_in[b], ldspk, P, p.PQ, 2 * cout[b], ACT_NONE));
+      SAPCU_TRY(g.layer(L, S0 + off_in[b], ld0, P, p.PQ, 2 * cout[b], ACT_NONE));
       SAPCU_TRY(launch_edge_gather_unroll(b == 0, p.PQ, cout[b], idx, p.k, M, s, f.conv[b].scale, f.conv[b].shift,
-                                          f.blk[b + 1].np, f.blk[b + 1].ep, T, U[b], p.SPK + off_out[b], ldspk, 960, st));
+                                          f.blk[b + 1].np, f.blk[b + 1].ep, T, U[b], spk_h2 ? p.SPK : p.SPK + off_out[b], ldspk, 960, st,
+                                          spk_h2, p.SPK0, plane, off_out[b]));
       continue;
     } else {
       GemmArgs a;
@@ -307,24 +332,14 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
     SAPCU_TRY(launch_neuron_unroll(b == 0, precise, U[b], cout[b], P, cout[b], T, f.blk[b + 1].np, f.blk[b + 1].ep, 1,
                                    p.SPK + off_out[b], 960, st));
   }
-  {
-    // conv5 (multi-scale fusion) + LeakyReLU + max over the patch's points: in the tensor-core modes the 2-CTA kernel
-    // reduces in its epilogue (per-thread running maxima, then float atomic max) and AGG is never written
-    GemmArgs a;
-    const Layer& L = f.msc;
-    a.A = p.SPK; a.lda = 960; a.R = P * T; a.K = L.K; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = L.N;
-    a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LEAKY; a.Y = p.AGG; a.ldc = f.emb;
-    a.pool = p.POOL; a.pool_T = T; a.pool_M = M;
-    a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;                       // the spike tensor
-    static const bool fuse_pool = !(getenv("SAPCU_TC_FUSE_POOL") && atoi(getenv("SAPCU_TC_FUSE_POOL")) == 0);
-    if (mode != SAPCU_MODE_FP32 && fuse_pool && gemm_tc2_supported(a, A_PLAIN)) {
-      SAPCU_TRY(launch_fill(p.POOL, s * T * f.emb, -INFINITY, st));
-      SAPCU_TRY(g.run(a, A_PLAIN));
-    } else {
-      a.pool = nullptr;
-      SAPCU_TRY(g.run(a, A_PLAIN));
-      SAPCU_TRY(launch_group_max(p.AGG, s, M, T, f.emb, p.POOL, st));
-    }
+  if (pooled) {
+    c5.x_h2 = spk_h2;
+    SAPCU_TRY(launch_fill(p.POOL, s * T * f.emb, -INFINITY, st));
+    SAPCU_TRY(g.run(c5, A_PLAIN));
+  } else {
+    c5.pool = nullptr;
+    SAPCU_TRY(g.run(c5, A_PLAIN));
+    SAPCU_TRY(launch_group_max(p.AGG, s, M, T, f.emb, p.POOL, st));
   }
   SAPCU_TRY(launch_temporal_lif(precise, p.POOL, s, T, f.emb, f.tw, f.snn_fc.np, p.Z, st));
   // StandardDistanceDecoder
@@ -412,6 +427,7 @@ int sapcu_model_tap_format(const sapcu_model* m, const char* name) {
   SAPCU_REQUIRE(m && name, "model_tap_format: bad argument");
   if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_gamma") return g_tap_gamma_h2;
   if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_delta2") return g_tap_delta2_h2;
+  if (m->kind == SAPCU_MODEL_FD && std::string(name) == "spikes") return g_tap_spk_h2;
   return 0;
 }
 

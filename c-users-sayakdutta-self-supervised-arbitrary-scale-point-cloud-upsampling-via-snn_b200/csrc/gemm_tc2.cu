@@ -515,7 +515,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     SAPCU_T2_ATTR_H(ACT_NONE, 3, 12); SAPCU_T2_ATTR_H(ACT_NONE, 3, 18); SAPCU_T2_ATTR_H(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_H
 #define SAPCU_T2_ATTR_P(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_LIF, 2, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
+    SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_LIF, 2, 1); SAPCU_T2_ATTR_P(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_P
     attr_done = true;
   }
@@ -526,7 +526,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : T2_BN;
   const bool h16 = gemm_tc2_fp16x3(g);
   const bool pre = h16 && g.x_h2;                            // activations already stored as fp16 (hi, lo) planes
-  SAPCU_REQUIRE(!g.x_h2 || (h16 && g.lda == g.K && (g.at_pos || g.act == ACT_LIF)), "gemm_tc2: fp16-plane input needs the fp16x3 path and lda == K");
+  SAPCU_REQUIRE(!g.x_h2 || (h16 && g.lda == g.K && (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool))), "gemm_tc2: fp16-plane input needs the fp16x3 path and lda == K");
   SAPCU_REQUIRE(!g.out_h2 || (g.act == ACT_LIF && g.ldc == g.N), "gemm_tc2: fp16-plane output is a LIF epilogue with ldc == N");
   CUtensorMap mw, mwlo, mx, mx2;
   int rc = h16 ? tc_make_map_f16(&mw, g.Wh, g.N, g.K, 128) : tc_make_map(&mw, g.Whi, g.N, g.K, g.K, 128);
@@ -562,7 +562,8 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   if (pre) {
     if (g.at_pos) {
       if (g.kk == 12) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 24);
-    } else if (g.edge_bias) SAPCU_T2_LAUNCH_P(ACT_LIF, 2, 1);
+    } else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH_P(ACT_LEAKY, 4, 1);
+    else if (g.edge_bias) SAPCU_T2_LAUNCH_P(ACT_LIF, 2, 1);
     else SAPCU_T2_LAUNCH_P(ACT_LIF, 0, 1);
     SAPCU_LAUNCH_CHECK();
     return 0;

@@ -35,9 +35,10 @@ int launch_fd_block0(const float* xyz, const int32_t* idx, int ldi, int Mpts, in
                      cudaStream_t st);
 int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* idx, int kk, int Mpts, int64_t S,
                               const float* scale, const float* shift, const float* np, const float* ep, int T, float* U,
-                              float* spk, int64_t ldspk_row, int ldo, cudaStream_t st);
+                              float* spk, int64_t ldspk_row, int ldo, cudaStream_t st, bool h2 = false, float* spk0 = nullptr, int64_t plane = 0, int choff = 0);
 int launch_neuron_unroll(bool eif, bool precise, const float* U, int64_t ldu, int64_t rows, int C, int T,
-                         const float* np, const float* ep, int all_steps, float* out, int64_t ldo, cudaStream_t st);
+                         const float* np, const float* ep, int all_steps, float* out, int64_t ldo, cudaStream_t st,
+                         bool h2 = false, float* out0 = nullptr, int64_t plane = 0, int choff = 0);
 int launch_temporal_lif(bool precise, const float* pool, int64_t S, int Tt, int C, const float* wsm, const float* np,
                         float* out, cudaStream_t st);
 int launch_head_attention(const float* qkv, int64_t S, int H, int hd, float scale, float* out, cudaStream_t st);
