@@ -249,10 +249,10 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tc": "tf32x3", "tf32": "tf32"}[mode], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tc": "fp16x3/tf32x3 (fp32 accumulate)", "tf32": "tf32"}[mode], "data": "synthetic",
             "config": {"workload": "configs[1]: 2,048-pt sphere cloud x4 -> 8,192 seeds per GPU, K=100, fn.yaml+fd.yaml "
                                    "random-init weights, %s" % {"fp32": "fp32 parity mode (FFMA contractions)",
-                                                              "tc": "fp32 parity mode (3xTF32 tcgen05 contractions, fp32 accumulate)",
+                                                              "tc": "fp32 parity mode (tcgen05 contractions with 3 split products per MAC: fp16 hi/lo on spike-tensor inputs, tf32 hi/lo elsewhere; fp32 accumulate)",
                                                               "tf32": "fast mode (single-pass TF32 tcgen05 contractions; deviation in profiles/)"}[mode],
                        "seeds_total": S_total, "l2": "256 MiB flush buffer written between timed steps",
                        "collective": "one all-gather of [S,3] f64 per step" if world > 1 else "none"},
@@ -261,12 +261,12 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(cloud.nbytes + h_seeds.nbytes), "d2h_bytes_per_step": int(h_seeds.shape[0] * 24)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_simt_kernel (all 1x1-conv/linear contractions, fused LIF epilogues)"
-                         if mode == "fp32" else "gemm_tc2_kernel + gemm_tc_kernel (tcgen05 3xTF32 contractions, cta_group::2 where N % 256 == 0; fused BN / LIF / attention / max-pool epilogues; rows < 1024 on gemm_simt_kernel)",
+                         if mode == "fp32" else "gemm_tc2_kernel + gemm_tc_kernel (tcgen05 split-product contractions: fp16x3 / 3xTF32, cta_group::2 where N % 256 == 0; fused BN / LIF / attention / max-pool epilogues; rows < 1024 on gemm_simt_kernel)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s",
                          "traffic": traffic, "traffic_note": "dram read+write bytes summed over the contraction launches of ONE step (ncu, profiles/r01_gemm_traffic.json); achieved/kernel_ms are likewise per-step sums over the family",
                          "executed_tflops": achieved_tf * (3 if mode == "tc" else 1),
-                         "executed_note": "tensor-core math actually issued: 3 tf32 passes per product in the parity mode (tf32 runs at half the bf16 rate, so frac <= 1/6 by construction)" if mode == "tc" else "one pass per product",
+                         "executed_note": "tensor-core math actually issued: 3 split products per MAC in the parity mode (fp16 hi/lo at the bf16 rate on 85 % of the FLOPs, tf32 hi/lo at half of it on the rest), so frac <= ~0.3 by construction" if mode == "tc" else "one pass per product",
                          "kernel_ms_per_step": gms.value / args.steps, "kernel_launches_per_step": gn.value / args.steps,
                          "kernel_share_of_step": gms.value / max(ms, 1e-9), "algorithmic_gflop_per_step": gfl.value / args.steps / 1e9},
             "cpu_baseline": cpu,
