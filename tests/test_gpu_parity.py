@@ -591,3 +591,20 @@ def test_models_other_patch_size(lib, sphere):
     rel = np.abs(got_d - ref_d) / np.maximum(np.abs(ref_d), 1e-6)
     print("M=64: normals %.2e deg, distances %.2e rel" % (_angle_deg(got_n, ref_n).max(), rel.max()))
     assert rel.max() < 1e-3
+
+
+def test_tensor_core_mode_chunk_invariance(lib, sphere):
+    """MODE_TC (fp16x3 / fp16 planes / fused epilogues): a workspace that only holds 24 of 64 patches changes the chunking
+    (24 + 24 + 16, so tiles, pooling windows and plane offsets fall elsewhere), never a single bit of the result."""
+    cloud, seeds = sphere
+    B = 64
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx)).to(DEV)
+    mfn, mfd, _, _ = _models(True)
+    mfn.set_mode("tc"), mfd.set_mode("tc")
+    n_ref, d_ref = mfn(p).clone(), mfd(p).clone()
+    for m in (mfn, mfd):
+        m.WORKSPACE_CAP = N.lib().sapcu_model_workspace_bytes(m._ensure_handle(), 24, 100)
+        m._ws = None
+    assert torch.equal(mfn(p), n_ref)
+    assert torch.equal(mfd(p), d_ref)
