@@ -608,3 +608,44 @@ def test_tensor_core_mode_chunk_invariance(lib, sphere):
         m._ws = None
     assert torch.equal(mfn(p), n_ref)
     assert torch.equal(mfd(p), d_ref)
+
+
+def test_non_yaml_configs_take_the_fallback_paths(lib, sphere):
+    """Neighbour counts and step counts other than the yaml ones: k = 16/10/6 in fn (no fused attention tail instance ->
+    logits + attn_out kernel, the factorised attention input stays), k = 18 / scales 4..20 / T = 5 in fd (byte-wise graph
+    rows in the EdgeConv tail, other pooling windows).  Tensor-core mode vs the oracle with the same config."""
+    import copy
+    from sapcu_b200.fn import config as fc
+    from sapcu_b200.fd import config as dc
+    cloud, seeds = sphere
+    B = 16
+    cfn = fc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fn.yaml"))
+    cfd = dc.load_config(os.path.join(sapcu_b200.CONFIG_DIR, "fd.yaml"))
+    cfn, cfd = copy.deepcopy(cfn), copy.deepcopy(cfd)
+    cfn["model"]["k_values"] = [16, 10, 6]
+    cfn["model"]["time_steps_enc"] = 4
+    cfd["model"]["k"] = 18
+    cfd["model"]["k_scales"] = [4, 8, 12, 20]
+    cfd["model"]["time_steps_enc"] = 5
+    mfn, mfd = fc.get_model(cfn), dc.get_model(cfd, None)
+    syn.init_weights(mfn, seed=11, stress=True)
+    syn.init_weights(mfd, seed=12, stress=True)
+    sd_fn = {k: v.clone() for k, v in mfn.state_dict().items()}
+    sd_fd = {k: v.clone() for k, v in mfd.state_dict().items()}
+    mfn, mfd = mfn.to(DEV), mfd.to(DEV)
+    mfn.set_mode("tc"), mfd.set_mode("tc")
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx))
+    with torch.no_grad():
+        ref_n = orc.fn_forward(sd_fn, p, dict(k_values=[16, 10, 6], time_steps_enc=4, num_heads=8)).numpy()
+    got_n = mfn(p.to(DEV)).cpu().numpy()
+    assert _angle_deg(got_n, ref_n).max() < 0.1
+    taps = {}
+    ocfg = dict(k=18, time_steps_enc=5, k_scales=[4, 8, 12, 20], num_heads=8)
+    with torch.no_grad():
+        ref_d = orc.fd_forward(sd_fd, p, ocfg, schedule="dce", taps=taps).numpy()
+    forced = torch.stack([gi.to(torch.int32) for gi in taps["graph_idx"]], 0)
+    got_d = mfd(p.to(DEV), forced_idx=forced).cpu().numpy()
+    rel = np.abs(got_d - ref_d) / np.maximum(np.abs(ref_d), 1e-6)
+    print("non-yaml configs: normals %.2e deg, distances %.2e rel" % (_angle_deg(got_n, ref_n).max(), rel.max()))
+    assert rel.max() < 1e-3
