@@ -59,7 +59,7 @@ __global__ void fd_block0_kernel(const Block0Args a) {
 // followed by the block's T-step EIF/LIF recurrence, every step's spike written into the [point, t, 960] spike
 // tensor (no HBM round trip between the max-pool and the recurrence).
 constexpr int EGU_PTS = 4;     // points processed together per thread (ILP for the recurrence)
-constexpr int EGU_THREADS = 256;  // 128 channels x 2 halves of the patch's points (occupancy: the kernel is latency-bound)
+constexpr int EGU_THREADS = 256;  // 64 channel pairs x 4 quarters of the patch's points
 template <bool EIF>
 __global__ void __launch_bounds__(EGU_THREADS)
 edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __restrict__ idx, int kk, int Mpts,
@@ -68,71 +68,96 @@ edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __
                           float* __restrict__ U, float* __restrict__ spk, int64_t ldspk_row, int ldo,
                           int h2, float* __restrict__ spk0, int64_t plane, int choff) {
   // h2: spikes go out as fp16 (hi, lo) planes of s * 2^13, row (point*T + t) of `ldo` halfs, for the fp16x3 conv5; the
-  // step-0 spikes -- the only ones the next block's graph and EdgeConv read -- also as fp32 into spk0 [point, ldo]
+  // step-0 spikes -- the only ones the next block's graph and EdgeConv read -- also as fp32 into spk0 [point, ldo].
+  // A thread owns two adjacent channels: one 8-byte shared-memory load per neighbour serves both (the gather is
+  // instruction-bound), and every global store is a 4- or 8-byte pair.
   extern __shared__ float egs[];
   float* Ps = egs;                                                 // [Mpts][128]
   uint8_t* nbs = reinterpret_cast<uint8_t*>(egs + Mpts * 128);     // [Mpts][kk] local neighbour indices (Mpts <= 256)
-  const int tx = threadIdx.x & 127, half = threadIdx.x >> 7;
   const int64_t patch0 = (int64_t)blockIdx.x * Mpts;
-  const int c = blockIdx.y * 128 + tx;                             // C is a multiple of 128
-  for (int m = half; m < Mpts; m += 2) Ps[m * 128 + tx] = PQ[(patch0 + m) * 2 * C + c];
+  {
+    const int tx = threadIdx.x & 127, hf = threadIdx.x >> 7;
+    const int cs = blockIdx.y * 128 + tx;                          // C is a multiple of 128
+    for (int m = hf; m < Mpts; m += 2) Ps[m * 128 + tx] = PQ[(patch0 + m) * 2 * C + cs];
+  }
   for (int e = threadIdx.x; e < Mpts * kk; e += EGU_THREADS) nbs[e] = (uint8_t)idx[patch0 * kk + e];
   __syncthreads();
-  const float sc = scale[c], sh = shift[c];
-  const NeuronParams p{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
-  EifParams q{1.0f, 1.0f};
-  if (EIF) { q.dT = ep[c]; q.thrh = ep[C + c]; }
-  const FastNeuronK k = fast_neuron_k(p, q);
-  const int mh = (Mpts + 1) >> 1;
-  const int i_begin = half * mh, i_end = half ? Mpts : mh;
-  const float* Pc = Ps + tx;
-  for (int i0 = i_begin; i0 < i_end; i0 += EGU_PTS) {
-    float u[EGU_PTS], m[EGU_PTS], th[EGU_PTS], rho[EGU_PTS];
+  const int tp = threadIdx.x & 63, quarter = threadIdx.x >> 6;
+  const int c = blockIdx.y * 128 + 2 * tp;                         // channels c, c + 1
+  const float sc0 = scale[c], sh0 = shift[c], sc1 = scale[c + 1], sh1 = shift[c + 1];
+  FastNeuronK k0, k1;
+  {
+    const NeuronParams p0{np[c], np[C + c], np[2 * C + c], np[3 * C + c]};
+    const NeuronParams p1{np[c + 1], np[C + c + 1], np[2 * C + c + 1], np[3 * C + c + 1]};
+    EifParams q0{1.0f, 1.0f}, q1{1.0f, 1.0f};
+    if (EIF) { q0.dT = ep[c]; q0.thrh = ep[C + c]; q1.dT = ep[c + 1]; q1.thrh = ep[C + c + 1]; }
+    k0 = fast_neuron_k(p0, q0); k1 = fast_neuron_k(p1, q1);
+  }
+  const int mq = (Mpts + 3) >> 2;
+  const int i_begin = quarter * mq, i_end = min(Mpts, i_begin + mq);
+  const float2* Pc = reinterpret_cast<const float2*>(Ps) + tp;      // row stride 64 float2
+  constexpr int NP = EGU_PTS / 2;                                  // points per pass: NP x 2 channels = EGU_PTS recurrences
+  for (int i0 = i_begin; i0 < i_end; i0 += NP) {
+    float u[EGU_PTS], m[EGU_PTS], th[EGU_PTS], rho[EGU_PTS];        // [2a] channel c, [2a+1] channel c+1 of point i0+a
 #pragma unroll
-    for (int a = 0; a < EGU_PTS; ++a) {
+    for (int a = 0; a < NP; ++a) {
       const int i = min(i0 + a, i_end - 1);
-      const float qv = PQ[(patch0 + i) * 2 * C + C + c];
+      const float2 qv = *reinterpret_cast<const float2*>(PQ + (patch0 + i) * 2 * C + C + c);
       // LeakyReLU(scale*(P-Q)+shift) is monotone in P for scale >= 0 and antitone otherwise: the max over the
       // neighbours is reached at max P or min P; both are tracked in one pass over the (byte-packed) graph row
-      float mx = -INFINITY, mn = INFINITY;
+      float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
       const uint8_t* nr = nbs + i * kk;
       if ((kk & 3) == 0) {
         const uint32_t* nw = reinterpret_cast<const uint32_t*>(nr);
         for (int w = 0; w < (kk >> 2); ++w) {
           const uint32_t v = nw[w];
-          const float p0 = Pc[(v & 255u) * 128], p1 = Pc[((v >> 8) & 255u) * 128], p2 = Pc[((v >> 16) & 255u) * 128], p3 = Pc[(v >> 24) * 128];
-          mx = fmaxf(fmaxf(mx, p0), fmaxf(p1, fmaxf(p2, p3)));
-          mn = fminf(fminf(mn, p0), fminf(p1, fminf(p2, p3)));
+          const float2 p0 = Pc[(v & 255u) * 64], p1 = Pc[((v >> 8) & 255u) * 64], p2 = Pc[((v >> 16) & 255u) * 64], p3 = Pc[(v >> 24) * 64];
+          mx0 = fmaxf(fmaxf(mx0, p0.x), fmaxf(p1.x, fmaxf(p2.x, p3.x)));
+          mn0 = fminf(fminf(mn0, p0.x), fminf(p1.x, fminf(p2.x, p3.x)));
+          mx1 = fmaxf(fmaxf(mx1, p0.y), fmaxf(p1.y, fmaxf(p2.y, p3.y)));
+          mn1 = fminf(fminf(mn1, p0.y), fminf(p1.y, fminf(p2.y, p3.y)));
         }
       } else {
-        for (int j = 0; j < kk; ++j) { const float pv = Pc[nr[j] * 128]; mx = fmaxf(mx, pv); mn = fminf(mn, pv); }
+        for (int j = 0; j < kk; ++j) {
+          const float2 pv = Pc[nr[j] * 64];
+          mx0 = fmaxf(mx0, pv.x); mn0 = fminf(mn0, pv.x); mx1 = fmaxf(mx1, pv.y); mn1 = fminf(mn1, pv.y);
+        }
       }
-      u[a] = act_leaky(fmaf((sc < 0.0f ? mn : mx) - qv, sc, sh));
-      if (i0 + a < i_end) U[(patch0 + i) * C + c] = u[a];
+      u[2 * a] = act_leaky(fmaf((sc0 < 0.0f ? mn0 : mx0) - qv.x, sc0, sh0));
+      u[2 * a + 1] = act_leaky(fmaf((sc1 < 0.0f ? mn1 : mx1) - qv.y, sc1, sh1));
+      if (i0 + a < i_end) *reinterpret_cast<float2*>(U + (patch0 + i) * C + c) = make_float2(u[2 * a], u[2 * a + 1]);
     }
     float s[EGU_PTS];
 #pragma unroll
-    for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, true>(u[a], m[a], th[a], rho[a], k);
-    auto put = [&](int a, int t, float v) {
+    for (int a = 0; a < NP; ++a) {
+      s[2 * a] = neuron_step_fast<EIF, true>(u[2 * a], m[2 * a], th[2 * a], rho[2 * a], k0);
+      s[2 * a + 1] = neuron_step_fast<EIF, true>(u[2 * a + 1], m[2 * a + 1], th[2 * a + 1], rho[2 * a + 1], k1);
+    }
+    auto put = [&](int a, int t, float v0, float v1) {
       if (h2) {
         __half* hp = reinterpret_cast<__half*>(spk) + ((patch0 + i0 + a) * T + t) * (int64_t)ldo + choff + c;
-        const float ys = v * 8192.0f;
-        const __half hv = __float2half_rn(ys);
-        hp[0] = hv; hp[plane] = __float2half_rn(ys - __half2float(hv));
-        if (t == 0) spk0[(patch0 + i0 + a) * (int64_t)ldo + choff + c] = v;
+        const float y0 = v0 * 8192.0f, y1 = v1 * 8192.0f;
+        const __half2 hv = __floats2half2_rn(y0, y1);
+        const float2 hf = __half22float2(hv);
+        *reinterpret_cast<__half2*>(hp) = hv;
+        *reinterpret_cast<__half2*>(hp + plane) = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+        if (t == 0) *reinterpret_cast<float2*>(spk0 + (patch0 + i0 + a) * (int64_t)ldo + choff + c) = make_float2(v0, v1);
       } else {
-        spk[(patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c] = v;
+        *reinterpret_cast<float2*>(spk + (patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c) = make_float2(v0, v1);
       }
     };
 #pragma unroll
-    for (int a = 0; a < EGU_PTS; ++a)
-      if (i0 + a < i_end) put(a, 0, s[a]);
+    for (int a = 0; a < NP; ++a)
+      if (i0 + a < i_end) put(a, 0, s[2 * a], s[2 * a + 1]);
     for (int t = 1; t < T; ++t) {
 #pragma unroll
-      for (int a = 0; a < EGU_PTS; ++a) s[a] = neuron_step_fast<EIF, false>(0.0f, m[a], th[a], rho[a], k);
+      for (int a = 0; a < NP; ++a) {
+        s[2 * a] = neuron_step_fast<EIF, false>(0.0f, m[2 * a], th[2 * a], rho[2 * a], k0);
+        s[2 * a + 1] = neuron_step_fast<EIF, false>(0.0f, m[2 * a + 1], th[2 * a + 1], rho[2 * a + 1], k1);
+      }
 #pragma unroll
-      for (int a = 0; a < EGU_PTS; ++a)
-        if (i0 + a < i_end) put(a, t, s[a]);
+      for (int a = 0; a < NP; ++a)
+        if (i0 + a < i_end) put(a, t, s[2 * a], s[2 * a + 1]);
     }
   }
 }
