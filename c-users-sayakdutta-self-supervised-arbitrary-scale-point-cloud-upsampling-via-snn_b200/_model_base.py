@@ -31,8 +31,11 @@ class NativeModel(nn.Module):
         # parameters/buffers are re-uploaded when any of them was modified in place or replaced
         return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
 
-    def _ensure_handle(self):
-        ver = self._state_version()
+    def _ensure_handle(self, device=None):
+        """The native handle for the module's current parameters on `device` (the weights are uploaded to the CUDA device
+        that is current at finalize time, so the device is part of the version key; callers hold torch.cuda.device(device))."""
+        dev_index = torch.device(device).index if device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        ver = (dev_index,) + self._state_version()
         if self._handle is not None and ver == self._handle_version:
             return self._handle
         self._drop_handle()
@@ -76,15 +79,16 @@ class NativeModel(nn.Module):
         return super().train(False)
 
     def set_mode(self, mode):
-        """'fp32' (FFMA, reference-faithful arithmetic), 'tc' (tcgen05 3xTF32, parity-grade) or 'tf32' (tcgen05
-        single-pass TF32, the fast mode whose deviation is reported separately)."""
-        self.mode = {"fp32": N.MODE_FP32, "tc": N.MODE_TC, "tf32": N.MODE_TF32}[mode] if isinstance(mode, str) else int(mode)
+        """'fp32' (FFMA, reference-faithful arithmetic), 'tc' (tcgen05 split products, parity-grade), 'tf32' (tcgen05
+        single-pass TF32) or 'fast' (single fp16 product per MAC on fp16 spike tensors + cheap LIF chains; the fast mode
+        whose deviation is reported separately)."""
+        self.mode = {"fp32": N.MODE_FP32, "tc": N.MODE_TC, "tf32": N.MODE_TF32, "fast": N.MODE_FAST}[mode] if isinstance(mode, str) else int(mode)
         return self
 
     # ------------------------------------------------------------------ helpers for subclasses
     def _workspace(self, S, M, device):
         L = N.lib()
-        h = self._ensure_handle()
+        h = self._ensure_handle(device)
         need = L.sapcu_model_workspace_bytes(h, S, M)
         one = L.sapcu_model_workspace_bytes(h, 1, M)
         want = max(one, min(need, self.WORKSPACE_CAP))

@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 MODEL_FN, MODEL_FD = 0, 1
-MODE_FP32, MODE_TC, MODE_TF32 = 0, 1, 2
+MODE_FP32, MODE_TC, MODE_TF32, MODE_FAST = 0, 1, 2, 3
 
 _lock = threading.Lock()
 _lib = None
@@ -92,9 +92,13 @@ _SIGS = {
     "sapcu_profile": (ctypes.c_int, [ctypes.c_int]),
     "sapcu_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_int64)]),
+    "sapcu_profile_report": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_size_t]),
     "sapcu_knn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
     "sapcu_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "sapcu_knn_batched_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
+    "sapcu_knn_batched": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "sapcu_gather_center_rotate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_void_p]),
@@ -167,6 +171,7 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device)."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,8 +1,10 @@
 // C ABI glue: error string, launch counter, and the stand-alone operator entry points.
 #include <atomic>
 #include <mutex>
+#include <string>
 #include <vector>
 #include <stdarg.h>
+#include <string.h>
 #include "../../include/sapcu_b200.h"
 #include "gemm_simt.cuh"
 #include "gemm_tc.h"
@@ -24,23 +26,22 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // ---- optional live timing of the contraction kernels (bench.py roofline)
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
-static double g_prof_flops = 0.0;
+struct ProfEntry { cudaEvent_t a, b; const char* label; ProfWork w; };
+static std::vector<ProfEntry> g_prof_ev;
 
-bool prof_begin(cudaStream_t st, double flops, int* slot) {
+bool prof_begin(cudaStream_t st, const char* label, const ProfWork& w, int* slot) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (!g_prof_on) return false;
   cudaEvent_t a, b;
   if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
   cudaEventRecord(a, st);
-  g_prof_ev.emplace_back(a, b);
-  g_prof_flops += flops;
+  g_prof_ev.push_back(ProfEntry{a, b, label, w});
   *slot = (int)g_prof_ev.size() - 1;
   return true;
 }
 void prof_end(cudaStream_t st, int slot) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (slot >= 0 && slot < (int)g_prof_ev.size()) cudaEventRecord(g_prof_ev[slot].second, st);
+  if (slot >= 0 && slot < (int)g_prof_ev.size()) cudaEventRecord(g_prof_ev[slot].b, st);
 }
 
 }  // namespace sapcu
@@ -55,24 +56,51 @@ int64_t sapcu_launch_count(void) { return g_launches.load(std::memory_order_rela
 
 int sapcu_profile(int enable) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  for (auto& e : g_prof_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& e : g_prof_ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   g_prof_ev.clear();
-  g_prof_flops = 0.0;
   g_prof_on = enable != 0;
   return 0;
+}
+
+int64_t sapcu_profile_report(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { double ms = 0, flops = 0, elsteps = 0, bytes = 0; int64_t n = 0; };
+  std::vector<std::pair<std::string, Agg>> agg;                 // first-seen order
+  for (auto& e : g_prof_ev) {
+    if (cudaEventSynchronize(e.b) != cudaSuccess) { set_error("profile_report: event sync failed"); return SAPCU_ECUDA; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess) { set_error("profile_report: elapsed time failed"); return SAPCU_ECUDA; }
+    size_t i = 0;
+    for (; i < agg.size(); ++i) if (agg[i].first == e.label) break;
+    if (i == agg.size()) agg.emplace_back(std::string(e.label), Agg());
+    Agg& a = agg[i].second;
+    a.ms += t; a.flops += e.w.flops; a.elsteps += e.w.elsteps; a.bytes += e.w.bytes; a.n += 1;
+  }
+  std::string js = "[";
+  char line[512];
+  for (size_t i = 0; i < agg.size(); ++i) {
+    const Agg& a = agg[i].second;
+    snprintf(line, sizeof(line), "%s{\"label\": \"%s\", \"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"lif_elsteps\": %.6e, \"bytes\": %.6e}",
+             i ? ", " : "", agg[i].first.c_str(), (long long)a.n, a.ms, a.flops, a.elsteps, a.bytes);
+    js += line;
+  }
+  js += "]";
+  if (buf && cap > 0) { const size_t n = js.size() < cap - 1 ? js.size() : cap - 1; memcpy(buf, js.data(), n); buf[n] = 0; }
+  return (int64_t)js.size() + 1;
 }
 
 int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
   SAPCU_REQUIRE(gemm_ms && gemm_flops && gemm_launches, "profile_read: null pointer");
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  double ms = 0.0;
+  double ms = 0.0, flops = 0.0; int64_t n = 0;
   for (auto& e : g_prof_ev) {
-    SAPCU_CUDA_CHECK(cudaEventSynchronize(e.second));
+    if (!e.w.gemm) continue;
+    SAPCU_CUDA_CHECK(cudaEventSynchronize(e.b));
     float t = 0.f;
-    SAPCU_CUDA_CHECK(cudaEventElapsedTime(&t, e.first, e.second));
-    ms += t;
+    SAPCU_CUDA_CHECK(cudaEventElapsedTime(&t, e.a, e.b));
+    ms += t; flops += e.w.flops; ++n;
   }
-  *gemm_ms = ms; *gemm_flops = g_prof_flops; *gemm_launches = (int64_t)g_prof_ev.size();
+  *gemm_ms = ms; *gemm_flops = flops; *gemm_launches = n;
   return 0;
 }
 
@@ -92,6 +120,29 @@ int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S
   float* c32 = reinterpret_cast<float*>(d_ws);
   float* rmax = reinterpret_cast<float*>(reinterpret_cast<char*>(d_ws) + align_up((size_t)(4 * N) * sizeof(float), 256));
   return launch_knn_seed(d_cloud, N, d_seeds, S, K, d_idx, c32, rmax, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t sapcu_knn_batched_workspace_bytes(int64_t N_total, int B) {
+  if (N_total < 0 || B < 0) return 0;
+  return align_up((size_t)(4 * N_total) * sizeof(float), 256) + 256 + align_up(3 * (size_t)(B + 1) * sizeof(int64_t), 256);
+}
+
+int sapcu_knn_batched(const double* d_clouds, const int64_t* h_cloud_off, const double* d_seeds, const int64_t* h_seed_off,
+                      int B, int K, int32_t* d_idx, void* d_ws, size_t ws_bytes, void* stream) {
+  SAPCU_REQUIRE(B >= 1 && h_cloud_off && h_seed_off, "sapcu_knn_batched: bad batch description");
+  const int64_t N = h_cloud_off[B], S = h_seed_off[B];
+  SAPCU_REQUIRE(N >= 1 && S >= 0, "sapcu_knn_batched: bad sizes N=%lld S=%lld", (long long)N, (long long)S);
+  SAPCU_REQUIRE(d_clouds && (S == 0 || (d_seeds && d_idx)) && d_ws, "sapcu_knn_batched: null pointer");
+  if (ws_bytes < sapcu_knn_batched_workspace_bytes(N, B)) {
+    set_error("sapcu_knn_batched: workspace %zu < %zu bytes", ws_bytes, sapcu_knn_batched_workspace_bytes(N, B));
+    return SAPCU_EWORKSPACE;
+  }
+  char* w = reinterpret_cast<char*>(d_ws);
+  float* c32 = reinterpret_cast<float*>(w);
+  float* rmax = reinterpret_cast<float*>(w + align_up((size_t)(4 * N) * sizeof(float), 256));
+  int64_t* tab = reinterpret_cast<int64_t*>(w + align_up((size_t)(4 * N) * sizeof(float), 256) + 256);
+  return launch_knn_seed_batched(d_clouds, h_cloud_off, d_seeds, h_seed_off, B, K, d_idx, c32, rmax, tab,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }
 
 int sapcu_gather_center_rotate(const double* d_cloud, int64_t N, const double* d_seeds, const int32_t* d_idx,

@@ -11,8 +11,23 @@ namespace sapcu {
 void set_error(const char* fmt, ...);
 extern thread_local char g_err[512];
 void count_launch(int n = 1);
-bool prof_begin(cudaStream_t st, double flops, int* slot);
+// live per-launch timing (bench.py's roofline entries): algorithmic work of one launch, by the roofline it is graded on
+struct ProfWork {
+  double flops = 0.0;      // tensor / FFMA: 2*R*K*N of a contraction
+  double elsteps = 0.0;    // MUFU: LIF / EIF element-steps (elements x T)
+  double bytes = 0.0;      // HBM: algorithmic bytes read + written
+  bool gemm = false;       // member of the contraction family (sapcu_profile_read's aggregate)
+};
+bool prof_begin(cudaStream_t st, const char* label, const ProfWork& w, int* slot);
 void prof_end(cudaStream_t st, int slot);
+#define SAPCU_PROF(st, label, work, expr)                                             \
+  do {                                                                                \
+    int _slot = -1;                                                                   \
+    const bool _p = sapcu::prof_begin(st, label, work, &_slot);                       \
+    const int _rc = (expr);                                                           \
+    if (_p) sapcu::prof_end(st, _slot);                                               \
+    if (_rc) return _rc;                                                              \
+  } while (0)
 
 #define SAPCU_CUDA_CHECK(expr)                                                        \
   do {                                                                                \

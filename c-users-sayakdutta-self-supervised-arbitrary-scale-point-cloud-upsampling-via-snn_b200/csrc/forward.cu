@@ -91,11 +91,23 @@ int64_t pick_chunk(const sapcu_model* m, int64_t S, int M, size_t ws_bytes) {
 // ---- GEMM helper: dispatch on the arithmetic mode
 struct G {
   int mode; cudaStream_t st;
+  mutable const char* lab = nullptr;                       // profiler label of the next launch: g.L("fn.fc1").layer(...)
+  const G& L(const char* l) const { lab = l; return *this; }
   int run(GemmArgs& g, int amode) const {
+    if (lab) { g.label = lab; lab = nullptr; }
     int slot = -1;
-    const bool prof = prof_begin(st, 2.0 * (double)g.R * g.K * g.N, &slot);
+    ProfWork w;
+    w.gemm = true;
+    w.flops = 2.0 * (double)g.R * g.K * g.N;
+    if (g.act == ACT_LIF) w.elsteps = (double)g.R * g.N * g.T;
+    {   // algorithmic HBM bytes: the activation read once, the result written once (fp16 planes keep the fp32 byte count), the weights once
+      const double out_rows = g.at_pos ? (double)g.R / (g.kk > 0 ? g.kk : 1) : (g.pool ? (double)g.R / (g.pool_M > 0 ? g.pool_M : 1) : (double)g.R);
+      w.bytes = (double)g.R * g.K * 4.0 + out_rows * g.N * 4.0 + (double)g.N * g.K * 4.0;
+      if (g.at_pos) w.bytes += (double)g.R * g.N * 4.0;             // pos rows read by the fused attention tail
+    }
+    const bool prof = prof_begin(st, g.label, w, &slot);
     int rc;
-    g.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+    g.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
     if (mode != SAPCU_MODE_FP32 && gemm_tc2_supported(g, amode)) rc = launch_gemm_tc2(g, st);
     else if (mode != SAPCU_MODE_FP32 && gemm_tc_supported(g, amode)) rc = launch_gemm_tc(g, amode, st);
     else rc = launch_gemm_simt(g, amode, mode == SAPCU_MODE_FP32, st);
@@ -123,9 +135,11 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
   const int64_t P = s * M;
   const bool precise = mode == SAPCU_MODE_FP32;
   const G g{mode, st};
-  SAPCU_TRY(launch_intra_knn(xyz, 3, s, M, 3, p.kmax, p.idx, st));
-  SAPCU_TRY(launch_pointwise3_lif(false, precise, xyz, nullptr, 0, 0, M, P, 64, f.conv1.W, f.conv1.bias, f.conv1.scale,
-                                  f.conv1.shift, f.snn_init.np, f.T_enc, p.F0, st));
+  { ProfWork w; w.flops = (double)s * M * M * 3; w.bytes = (double)P * (12 + 4.0 * p.kmax);
+    SAPCU_PROF(st, "fn.intra_knn(xyz)", w, launch_intra_knn(xyz, 3, s, M, 3, p.kmax, p.idx, st)); }
+  { ProfWork w; w.elsteps = (double)P * 64 * f.T_enc; w.bytes = (double)P * (12 + 256);
+    SAPCU_PROF(st, "fn.conv1+lif", w, launch_pointwise3_lif(false, precise, xyz, nullptr, 0, 0, M, P, 64, f.conv1.W, f.conv1.bias, f.conv1.scale,
+                                  f.conv1.shift, f.snn_init.np, f.T_enc, p.F0, st)); }
   // ---- tensor-core schedule helpers ------------------------------------------------------------------------------
   // fc_gamma's first layer is linear, so W(q_i - k_j + pos_ij) = W q_i - W k_j + W pos_ij: the edge contraction runs on
   // pos (E2) alone and its epilogue adds the two per-POINT products [W q | W k] (QK, [P, 2D]) gathered through the graph
@@ -154,14 +168,17 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     a.at_pos = pos; a.at_v = p.QKV + 2 * D; a.at_ldv = 3 * D; a.at_sqrt = sqrtf((float)(D / f.heads));   // torch divides by the python scalar sqrt(head_dim)
     a.Y = p.RES; a.ldc = D;
     a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;                     // fc_gamma's LIF output
-    a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+    a.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
     return a;
   };
   auto edge_pos = [&](int b, float* out, cudaStream_t s_, int nsplit, bool h2) {
     const FnBlock& k = f.blk[b];
     const int kk = k.k < M ? k.k : M;
-    return launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, P * kk, k.D, k.fc_delta.W, k.fc_delta.bias,
-                                 k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, out, s_, nsplit, h2);
+    ProfWork w; w.elsteps = (double)P * kk * k.D * 4; w.bytes = (double)P * kk * k.D * 4.0;
+    SAPCU_PROF(s_, "fn.fc_delta(K=3)+lif (edge_pos_lif)", w,
+               launch_pointwise3_lif(true, precise, xyz, p.idx, kk, p.kmax, M, P * kk, k.D, k.fc_delta.W, k.fc_delta.bias,
+                                     k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, out, s_, nsplit, h2));
+    return 0;
   };
   static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
   // fp16-plane hand-overs: 0 off; 1 (default) pos-enc layer 1 -> fc_delta2 and fc_gamma -> fc_gamma2; 2 / 3 only the first /
@@ -178,8 +195,8 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     const int64_t E = P * kk;
     float* Xb = p.E1;                                             // this block's edge buffer (pos-enc layer 1, then fc_gamma's output)
     bool xb_h2 = false, e2_h2 = false;                            // fc_gamma's output / pos stored as fp16 planes (see below)
-    SAPCU_TRY(g.layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
-    SAPCU_TRY(g.layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
+    SAPCU_TRY(g.L("fn.fc1+lif").layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
+    SAPCU_TRY(g.L("fn.qkv+lif").layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
     if (mode == SAPCU_MODE_FP32) { g_tap_gamma_h2 = 0; g_tap_delta2_h2 = 0; SAPCU_TRY(edge_pos(b, Xb, st, 1, false)); }
     if (mode != SAPCU_MODE_FP32) {
       // fc_delta2 on the pos-enc layer-1 spikes.  When it runs on the fp16x3 path, edge_pos_lif hands the spikes over as
@@ -190,7 +207,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
         a.A = Xb; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
         a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_delta2.np;
         a.Y = p.E2; a.ldc = D; a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;   // input: LIF output
-        a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+        a.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
         a.x_h2 = h2_delta && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_fp16x3(a);
         {   // pos (E2) has two readers, fc_gamma's contraction and the fused attention tail: planes when both take them
           GemmArgs a1 = gamma_args(b, p.E2, Xb, p.E3), a2 = gamma2_args(b, Xb, p.E2);
@@ -201,12 +218,12 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
         a.out_h2 = e2_h2;
         if (b == 2) g_tap_delta2_h2 = e2_h2 ? 1 : 0;
         SAPCU_TRY(edge_pos(b, Xb, st, 1, a.x_h2));
-        SAPCU_TRY(g.run(a, A_PLAIN));
+        SAPCU_TRY(g.L("fn.fc_delta2+lif").run(a, A_PLAIN));
       }
       {
         float* QK = p.E3;                                          // [W q | W k], [P, 2D]
         GemmArgs a = gamma_args(b, p.E2, Xb, QK);
-        a.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+        a.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
         {   // fc_gamma's spikes go to fc_gamma2 only: hand them over as fp16 planes when both run on the 2-CTA fp16x3 path
           GemmArgs a2 = gamma2_args(b, Xb, p.E2);
           xb_h2 = h2_gamma && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fp16x3(a2);
@@ -216,50 +233,50 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
         if (factorise && kk >= 2 && (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN))) {
           Layer Lw = k.fc_gamma;
           Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;
-          SAPCU_TRY(g.layer(Lw, p.QKV, 3 * D, P, QK, 2 * D, ACT_NONE));
-          SAPCU_TRY(g.layer(Lw, p.QKV + D, 3 * D, P, QK + D, 2 * D, ACT_NONE));
-          SAPCU_TRY(g.run(a, A_PLAIN));
+          SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV, 3 * D, P, QK, 2 * D, ACT_NONE));
+          SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV + D, 3 * D, P, QK + D, 2 * D, ACT_NONE));
+          SAPCU_TRY(g.L("fn.fc_gamma+edge_bias+lif").run(a, A_PLAIN));
         } else {
           SAPCU_TRY(launch_attn_in(p.QKV, p.QKV + D, 3 * D, p.E2, p.idx, p.kmax, kk, M, E, D, p.E3, st));
-          SAPCU_TRY(g.layer(k.fc_gamma, p.E3, D, E, p.E1, D, ACT_LIF, &k.snn_gamma, 4));
+          SAPCU_TRY(g.L("fn.fc_gamma+lif").layer(k.fc_gamma, p.E3, D, E, p.E1, D, ACT_LIF, &k.snn_gamma, 4));
         }
       }
       {
         GemmArgs a = gamma2_args(b, Xb, p.E2);
         a.x_h2 = xb_h2; a.pos_h2 = e2_h2;
         if (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN)) {
-          SAPCU_TRY(g.run(a, A_PLAIN));
+          SAPCU_TRY(g.L("fn.fc_gamma2+softmax+sum(attention tail)").run(a, A_PLAIN));
         } else {
-          SAPCU_TRY(g.layer(k.fc_gamma2, p.E1, D, E, p.E3, D, ACT_NONE));
+          SAPCU_TRY(g.L("fn.fc_gamma2").layer(k.fc_gamma2, p.E1, D, E, p.E3, D, ACT_NONE));
           SAPCU_TRY(launch_attn_out(precise, p.E3, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, a.at_sqrt, p.RES, st));
         }
       }
-      SAPCU_TRY(g.layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
-      SAPCU_TRY(g.layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
+      SAPCU_TRY(g.L("fn.out_proj").layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
+      SAPCU_TRY(g.L("fn.fc2+residual").layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
       continue;
     }
-    SAPCU_TRY(g.layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
+    SAPCU_TRY(g.L("fn.fc_delta2+lif").layer(k.fc_delta2, p.E1, D, E, p.E2, D, ACT_LIF, &k.snn_delta2, 4));
     {
       GemmArgs a;
       a.A = p.E2; a.lda = D; a.R = E; a.K = D; a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
       a.Q = p.QKV; a.Kf = p.QKV + D; a.ldq = 3 * D;
       a.W = k.fc_gamma.W; a.N = D; a.bias = k.fc_gamma.bias; a.scale = k.fc_gamma.scale; a.shift = k.fc_gamma.shift;
       a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_gamma.np; a.Y = p.E3; a.ldc = D;
-      SAPCU_TRY(g.run(a, A_ATTNIN));
+      SAPCU_TRY(g.L("fn.fc_gamma+lif").run(a, A_ATTNIN));
     }
-    SAPCU_TRY(g.layer(k.fc_gamma2, p.E3, D, E, p.E1, D, ACT_NONE));
+    SAPCU_TRY(g.L("fn.fc_gamma2").layer(k.fc_gamma2, p.E3, D, E, p.E1, D, ACT_NONE));
     // torch (CPU) divides the logits by the python scalar sqrt(head_dim)
     const float sq = sqrtf((float)(D / f.heads));
     SAPCU_TRY(launch_attn_out(precise, p.E1, p.E2, p.QKV + 2 * D, 3 * D, p.idx, p.kmax, kk, M, P, D, sq, p.RES, st));
-    SAPCU_TRY(g.layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
-    SAPCU_TRY(g.layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
+    SAPCU_TRY(g.L("fn.out_proj").layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
+    SAPCU_TRY(g.L("fn.fc2+residual").layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
   }
-  SAPCU_TRY(g.layer(f.conv_final, p.FCAT, 192, P, p.G, f.emb, ACT_LIF, &f.snn_final, f.T_enc));
+  SAPCU_TRY(g.L("fn.conv_final+lif").layer(f.conv_final, p.FCAT, 192, P, p.G, f.emb, ACT_LIF, &f.snn_final, f.T_enc));
   SAPCU_TRY(launch_group_max(p.G, s, M, 1, f.emb, p.GM, st));
-  SAPCU_TRY(g.layer(f.fc_out, p.GM, f.emb, s, p.H0, 2048, ACT_NONE));
-  SAPCU_TRY(g.layer(f.mlp[0], p.H0, 2048, s, p.H1, 1024, ACT_GELU));
-  SAPCU_TRY(g.layer(f.mlp[1], p.H1, 1024, s, p.H2, 512, ACT_GELU));
-  SAPCU_TRY(g.layer(f.mlp[2], p.H2, 512, s, p.H3, 256, ACT_GELU));
+  SAPCU_TRY(g.L("fn.decoder").layer(f.fc_out, p.GM, f.emb, s, p.H0, 2048, ACT_NONE));
+  SAPCU_TRY(g.L("fn.decoder").layer(f.mlp[0], p.H0, 2048, s, p.H1, 1024, ACT_GELU));
+  SAPCU_TRY(g.L("fn.decoder").layer(f.mlp[1], p.H1, 1024, s, p.H2, 512, ACT_GELU));
+  SAPCU_TRY(g.L("fn.decoder").layer(f.mlp[2], p.H2, 512, s, p.H3, 256, ACT_GELU));
   SAPCU_TRY(launch_fn_head(p.H3, 256, s, f.head.W, f.head.bias, f.ln_w, f.ln_b, normals, st));
   return 0;
 }
@@ -270,15 +287,17 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
   const bool precise = mode == SAPCU_MODE_FP32;
   const G g{mode, st};
   const int T = f.T;
-  SAPCU_TRY(launch_intra_knn(xyz, 3, s, M, 3, p.kmax0, p.idx0, st));
+  { ProfWork w; w.flops = (double)s * M * M * 3; w.bytes = (double)P * (12 + 4.0 * p.kmax0);
+    SAPCU_PROF(st, "fd.intra_knn(xyz)", w, launch_intra_knn(xyz, 3, s, M, 3, p.kmax0, p.idx0, st)); }
   {
     int ks[8]; const float* W[8]; const float* sc[8]; const float* sh[8];
     for (int i = 0; i < f.nscales; ++i) {
       ks[i] = f.kscales[i] < M ? f.kscales[i] : M; W[i] = f.first[i].W; sc[i] = f.first[i].scale; sh[i] = f.first[i].shift;
     }
-    SAPCU_TRY(launch_fd_block0(xyz, p.idx0, p.kmax0, M, P, f.nscales, ks, W, sc, sh, p.F0, st));
+    ProfWork w; for (int i = 0; i < f.nscales; ++i) w.flops += 2.0 * P * ks[i] * 6 * 64; w.bytes = (double)P * (12 + 4.0 * p.kmax0 + 256.0 * f.nscales);
+    SAPCU_PROF(st, "fd.block0(4-scale EdgeConv)", w, launch_fd_block0(xyz, p.idx0, p.kmax0, M, P, f.nscales, ks, W, sc, sh, p.F0, st));
   }
-  SAPCU_TRY(g.layer(f.fusion, p.F0, 64 * f.nscales, P, p.U0, 64, ACT_LEAKY));
+  SAPCU_TRY(g.L("fd.scale_fusion").layer(f.fusion, p.F0, 64 * f.nscales, P, p.U0, 64, ACT_LEAKY));
   const int64_t ldspk = (int64_t)T * 960;
   // conv5 (multi-scale fusion) + LeakyReLU + max over the patch's points: in the tensor-core modes the 2-CTA kernel
   // reduces in its epilogue (per-thread running maxima, then float atomic max) and AGG is never written
@@ -289,7 +308,7 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
     c5.bias = L.bias; c5.scale = L.scale; c5.shift = L.shift; c5.act = ACT_LEAKY; c5.Y = p.AGG; c5.ldc = f.emb;
     c5.pool = p.POOL; c5.pool_T = T; c5.pool_M = M;
     c5.Wh = L.Wh; c5.Wl = L.Wl; c5.winv = L.winv; c5.x_unit = true;                   // the spike tensor
-    c5.tc_passes = mode == SAPCU_MODE_TF32 ? 1 : 3;
+    c5.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
   }
   static const bool fuse_pool = !(getenv("SAPCU_TC_FUSE_POOL") && atoi(getenv("SAPCU_TC_FUSE_POOL")) == 0);
   static const bool spk_planes = !(getenv("SAPCU_TC_SPIKE_PLANES") && atoi(getenv("SAPCU_TC_SPIKE_PLANES")) == 0);
@@ -310,16 +329,19 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
   for (int b = 0; b < 3; ++b) {
     const int32_t* idx = forced[b];
     if (!idx) {
-      SAPCU_TRY(launch_intra_knn(S0 + off_in[b], ld0, s, M, cin[b], p.k, p.idxf, st));
+      ProfWork w; w.flops = (double)s * M * M * cin[b]; w.bytes = (double)P * (4.0 * cin[b] + 4.0 * p.k);
+      SAPCU_PROF(st, "fd.intra_knn(features)", w, launch_intra_knn(S0 + off_in[b], ld0, s, M, cin[b], p.k, p.idxf, st));
       idx = p.idxf;
     }
     if (mode != SAPCU_MODE_FP32) {
       // factorised EdgeConv: one per-POINT contraction [P, Cin] x [2 Cout, Cin]^T, then gather / BN / LeakyReLU / max_k
       Layer L = f.convf[b];
-      SAPCU_TRY(g.layer(L, S0 + off_in[b], ld0, P, p.PQ, 2 * cout[b], ACT_NONE));
-      SAPCU_TRY(launch_edge_gather_unroll(b == 0, p.PQ, cout[b], idx, p.k, M, s, f.conv[b].scale, f.conv[b].shift,
-                                          f.blk[b + 1].np, f.blk[b + 1].ep, T, U[b], spk_h2 ? p.SPK : p.SPK + off_out[b], ldspk, 960, st,
-                                          spk_h2, p.SPK0, plane, off_out[b]));
+      SAPCU_TRY(g.L("fd.edgeconv(per-point P|Q)").layer(L, S0 + off_in[b], ld0, P, p.PQ, 2 * cout[b], ACT_NONE));
+      ProfWork w; w.elsteps = (double)P * cout[b] * T; w.bytes = (double)P * cout[b] * (8.0 + 4.0 * T) + (double)P * p.k * 4.0;
+      SAPCU_PROF(st, "fd.edgeconv gather+max+neuron unroll", w,
+                 launch_edge_gather_unroll(b == 0, p.PQ, cout[b], idx, p.k, M, s, f.conv[b].scale, f.conv[b].shift,
+                                           f.blk[b + 1].np, f.blk[b + 1].ep, T, U[b], spk_h2 ? p.SPK : p.SPK + off_out[b], ldspk, 960, st,
+                                           spk_h2, p.SPK0, plane, off_out[b]));
       continue;
     } else {
       GemmArgs a;
@@ -327,7 +349,7 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
       a.F = p.SPK + off_in[b]; a.ldf = ldspk; a.C = cin[b];
       a.W = f.conv[b].W; a.N = cout[b]; a.scale = f.conv[b].scale; a.shift = f.conv[b].shift;
       a.act = ACT_LEAKY; a.group = 32; a.Y = U[b]; a.ldc = cout[b];
-      SAPCU_TRY(g.run(a, A_EDGECAT));
+      SAPCU_TRY(g.L("fd.edgeconv(per-edge)").run(a, A_EDGECAT));
     }
     SAPCU_TRY(launch_neuron_unroll(b == 0, precise, U[b], cout[b], P, cout[b], T, f.blk[b + 1].np, f.blk[b + 1].ep, 1,
                                    p.SPK + off_out[b], 960, st));
@@ -335,10 +357,10 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
   if (pooled) {
     c5.x_h2 = spk_h2;
     SAPCU_TRY(launch_fill(p.POOL, s * T * f.emb, -INFINITY, st));
-    SAPCU_TRY(g.run(c5, A_PLAIN));
+    SAPCU_TRY(g.L("fd.conv5+maxpool").run(c5, A_PLAIN));
   } else {
     c5.pool = nullptr;
-    SAPCU_TRY(g.run(c5, A_PLAIN));
+    SAPCU_TRY(g.L("fd.conv5").run(c5, A_PLAIN));
     SAPCU_TRY(launch_group_max(p.AGG, s, M, T, f.emb, p.POOL, st));
   }
   SAPCU_TRY(launch_temporal_lif(precise, p.POOL, s, T, f.emb, f.tw, f.snn_fc.np, p.Z, st));
@@ -370,7 +392,7 @@ int check_common(const sapcu_model* m, int kind, const float* patches, int64_t S
   if (!m->finalized) { set_error("forward: model not finalized"); return SAPCU_ESTATE; }
   SAPCU_REQUIRE(S >= 0 && M >= 1 && M <= 128, "forward: need S >= 0 and 1 <= M <= 128 (got S=%lld M=%d)", (long long)S, M);
   SAPCU_REQUIRE(S == 0 || (patches && out && ws), "forward: null pointer");
-  SAPCU_REQUIRE(mode == SAPCU_MODE_FP32 || mode == SAPCU_MODE_TC || mode == SAPCU_MODE_TF32, "forward: unknown mode %d", mode);
+  SAPCU_REQUIRE(mode == SAPCU_MODE_FP32 || mode == SAPCU_MODE_TC || mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST, "forward: unknown mode %d", mode);
   return 0;
 }
 

@@ -49,6 +49,7 @@ struct GemmArgs {
   bool x_h2 = false, out_h2 = false, pos_h2 = false;   // pos_h2: at_pos (fused attention tail) is stored as planes
   bool edge_bias = false;   // tensor-core engines, A_PLAIN: add Q[pt,c] - Kf[nb,c] (per-point products) to the accumulator, see tc_ptx.cuh
   int group = 0;   // 0 or 32
+  const char* label = "gemm";   // kernel label of the live profiler (sapcu_profile_report)
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GTHREADS = 256;

@@ -9,6 +9,9 @@ namespace sapcu {
 // knn_seed.cu
 int launch_knn_seed(const double* cloud, int64_t N, const double* seeds, int64_t S, int K, int32_t* idx,
                     float* cloud32_scratch, float* rmax_scratch, cudaStream_t st);
+int launch_knn_seed_batched(const double* clouds, const int64_t* h_cloud_off, const double* seeds, const int64_t* h_seed_off,
+                            int B, int K, int32_t* idx, float* cloud32_scratch, float* rmax_scratch, int64_t* tab,
+                            cudaStream_t st);
 // patch_ops.cu
 int launch_gather_center_rotate(const double* cloud, const double* seeds, const int32_t* idx, int64_t S, int K,
                                 const float* normals, float* patches, cudaStream_t st);

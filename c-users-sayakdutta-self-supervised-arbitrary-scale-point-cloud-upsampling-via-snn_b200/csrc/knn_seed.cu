@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include <float.h>
 #include <algorithm>
+#include <vector>
 
 namespace sapcu {
 
@@ -36,6 +37,19 @@ __global__ void cloud_to_f32_kernel(const double* __restrict__ cloud, int64_t n,
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(rmax), __float_as_int(m));   // m >= 0
 }
 
+// Batched launches (sapcu_knn_batched): the grid is the concatenation of per-cloud block ranges.  blk_off / cloud_off /
+// seed_off are [B+1] prefix tables (device); a CTA finds its cloud by binary search and works on that cloud's rows and
+// its own seeds only.  B == 0: the single-cloud launch (whole arrays).  Emitted indices are rows of the CONCATENATED
+// cloud array, so the gather that follows needs no per-cloud bookkeeping.
+struct KnnSegs { const int64_t* blk_off; const int64_t* cloud_off; const int64_t* seed_off; int B; };
+__device__ __forceinline__ void knn_resolve(const KnnSegs& g, int per_block, int64_t& c0, int64_t& N, int64_t& s0, int64_t& s_end) {
+  if (g.B == 0) { c0 = 0; s0 = (int64_t)blockIdx.x * per_block; return; }      // N, s_end stay as passed
+  int lo = 0, hi = g.B;                                      // last b with blk_off[b] <= blockIdx.x
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (g.blk_off[mid] <= (int64_t)blockIdx.x) lo = mid; else hi = mid; }
+  c0 = g.cloud_off[lo]; N = g.cloud_off[lo + 1] - c0;
+  s0 = g.seed_off[lo] + ((int64_t)blockIdx.x - g.blk_off[lo]) * per_block; s_end = g.seed_off[lo + 1];
+}
+
 __device__ __forceinline__ bool key_less(double da, int ia, double db, int ib) {
   return da < db || (da == db && ia < ib);
 }
@@ -43,9 +57,12 @@ __device__ __forceinline__ bool key_less(double da, int ia, double db, int ib) {
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_seed_kernel(const double* __restrict__ cloud, const float4* __restrict__ cloud32, int64_t N,
                 const double* __restrict__ seeds, int64_t S, int K, const float* __restrict__ rmax_p,
-                int32_t* __restrict__ out_idx) {
+                int32_t* __restrict__ out_idx, const KnnSegs segs) {
   __shared__ float4 tile[KNN_TILE];
-  const int64_t s = (int64_t)blockIdx.x * KNN_THREADS + threadIdx.x;
+  int64_t c0, sb;
+  knn_resolve(segs, KNN_THREADS, c0, N, sb, S);
+  cloud += 3 * c0; cloud32 += c0;
+  const int64_t s = sb + threadIdx.x;
   const bool active = s < S;
   const float rmax = *rmax_p;
   double sx = 0, sy = 0, sz = 0;
@@ -127,7 +144,7 @@ knn_seed_kernel(const double* __restrict__ cloud, const float4* __restrict__ clo
     hd[pos] = d; hi[pos] = gi;
     hd[n - 1] = md; hi[n - 1] = mi;
   }
-  for (int j = 0; j < K; ++j) out_idx[s * K + j] = hi[j];
+  for (int j = 0; j < K; ++j) out_idx[s * K + j] = hi[j] + (int)c0;
 }
 
 // ---- small clouds: one WARP per seed.  Each lane tests one cloud point per iteration; survivors are queued and merged
@@ -141,7 +158,7 @@ constexpr int KNNW_QCAP = 64;
 __global__ void __launch_bounds__(KNNW_WARPS * 32)
 knn_seed_warp_kernel(const double* __restrict__ cloud, const float4* __restrict__ cloud32, int64_t N,
                 const double* __restrict__ seeds, int64_t S, int K, const float* __restrict__ rmax_p,
-                int32_t* __restrict__ out_idx) {
+                int32_t* __restrict__ out_idx, const KnnSegs segs) {
   __shared__ float tx[KNNW_TILE], ty[KNNW_TILE], tz[KNNW_TILE];
   __shared__ double ld[KNNW_WARPS][2][KNN_KMAX];
   __shared__ int li[KNNW_WARPS][2][KNN_KMAX];
@@ -149,7 +166,10 @@ knn_seed_warp_kernel(const double* __restrict__ cloud, const float4* __restrict_
   __shared__ int qi[KNNW_WARPS][KNNW_QCAP];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * KNNW_WARPS + warp;
+  int64_t c0, sb;
+  knn_resolve(segs, KNNW_WARPS, c0, N, sb, S);
+  cloud += 3 * c0; cloud32 += c0;
+  const int64_t s = sb + warp;
   const bool active = s < S;
   const float rmax = *rmax_p;
 
@@ -233,7 +253,7 @@ knn_seed_warp_kernel(const double* __restrict__ cloud, const float4* __restrict_
   }
   if (active) {
     if (qn) flush();
-    for (int j = lane; j < K; j += 32) out_idx[s * K + j] = li[warp][cur][j];
+    for (int j = lane; j < K; j += 32) out_idx[s * K + j] = li[warp][cur][j] + (int)c0;
   }
 }
 
@@ -252,10 +272,55 @@ int launch_knn_seed(const double* cloud, int64_t N, const double* seeds, int64_t
   SAPCU_LAUNCH_CHECK();
   if (N < (1 << 20))  // measured on B200 (N=1e5: 11 vs 30 ms; N=2e6: 165 vs 114 ms) (tools/knn_microbench.py): survivors dominate below, the scan above
     knn_seed_warp_kernel<<<(unsigned)ceil_div(S, KNNW_WARPS), KNNW_WARPS * 32, 0, st>>>(cloud, reinterpret_cast<const float4*>(cloud32_scratch), N,
-                                                                                       seeds, S, K, rmax_scratch, idx);
+                                                                                       seeds, S, K, rmax_scratch, idx, KnnSegs{nullptr, nullptr, nullptr, 0});
   else
     knn_seed_kernel<<<(unsigned)ceil_div(S, KNN_THREADS), KNN_THREADS, 0, st>>>(cloud, reinterpret_cast<const float4*>(cloud32_scratch), N,
-                                                                               seeds, S, K, rmax_scratch, idx);
+                                                                               seeds, S, K, rmax_scratch, idx, KnnSegs{nullptr, nullptr, nullptr, 0});
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+// B independent (cloud, seed set) problems in ONE launch.  h_cloud_off / h_seed_off: [B+1] host prefix tables over the
+// concatenated arrays; tab: device scratch for 3*(B+1) int64.  The kernel flavour is chosen from the largest cloud.
+int launch_knn_seed_batched(const double* clouds, const int64_t* h_cloud_off, const double* seeds, const int64_t* h_seed_off,
+                            int B, int K, int32_t* idx, float* cloud32_scratch, float* rmax_scratch, int64_t* tab,
+                            cudaStream_t st) {
+  SAPCU_REQUIRE(K >= 1 && K <= KNN_KMAX, "sapcu_knn_batched: K=%d outside [1,%d]", K, KNN_KMAX);
+  SAPCU_REQUIRE(B >= 1 && h_cloud_off && h_seed_off && h_cloud_off[0] == 0 && h_seed_off[0] == 0, "sapcu_knn_batched: bad offset tables");
+  const int64_t Ntot = h_cloud_off[B], Stot = h_seed_off[B];
+  SAPCU_REQUIRE(Ntot < (int64_t)INT32_MAX / 3, "sapcu_knn_batched: too many cloud rows for int32 indices");
+  int64_t nmax = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = h_cloud_off[b + 1] - h_cloud_off[b], s = h_seed_off[b + 1] - h_seed_off[b];
+    SAPCU_REQUIRE(s >= 0 && n >= 0, "sapcu_knn_batched: offsets must be non-decreasing");
+    SAPCU_REQUIRE(s == 0 || n >= K, "sapcu_knn_batched: cloud %d has %lld points < K=%d", b, (long long)n, K);
+    nmax = n > nmax ? n : nmax;
+  }
+  if (Stot == 0) return 0;
+  const bool warp_kernel = nmax < (1 << 20);
+  const int per_block = warp_kernel ? KNNW_WARPS : KNN_THREADS;
+  std::vector<int64_t> h(3 * (size_t)(B + 1));
+  int64_t* blk = h.data(); int64_t* co = blk + (B + 1); int64_t* so = co + (B + 1);
+  blk[0] = 0;
+  for (int b = 0; b < B; ++b) blk[b + 1] = blk[b] + ceil_div(h_seed_off[b + 1] - h_seed_off[b], per_block);
+  for (int b = 0; b <= B; ++b) { co[b] = h_cloud_off[b]; so[b] = h_seed_off[b]; }
+  SAPCU_REQUIRE(blk[B] < (int64_t)INT32_MAX, "sapcu_knn_batched: grid too large");
+  SAPCU_CUDA_CHECK(cudaMemcpyAsync(tab, h.data(), h.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  SAPCU_CUDA_CHECK(cudaStreamSynchronize(st));               // `h` is a pageable temporary
+  SAPCU_CUDA_CHECK(cudaMemsetAsync(rmax_scratch, 0, sizeof(float), st));
+  const int blocks = (int)std::min<int64_t>(ceil_div(Ntot, 256), 148 * 8);
+  cloud_to_f32_kernel<<<blocks, 256, 0, st>>>(clouds, Ntot, reinterpret_cast<float4*>(cloud32_scratch), rmax_scratch);
+  SAPCU_LAUNCH_CHECK();
+  const int sblocks = (int)std::min<int64_t>(ceil_div(Stot, 256), 148 * 8);
+  cloud_to_f32_kernel<<<sblocks, 256, 0, st>>>(seeds, Stot, nullptr, rmax_scratch);
+  SAPCU_LAUNCH_CHECK();
+  const KnnSegs segs{tab, tab + (B + 1), tab + 2 * (B + 1), B};
+  if (warp_kernel)
+    knn_seed_warp_kernel<<<(unsigned)blk[B], KNNW_WARPS * 32, 0, st>>>(clouds, reinterpret_cast<const float4*>(cloud32_scratch), 0, seeds, 0, K,
+                                                                      rmax_scratch, idx, segs);
+  else
+    knn_seed_kernel<<<(unsigned)blk[B], KNN_THREADS, 0, st>>>(clouds, reinterpret_cast<const float4*>(cloud32_scratch), 0, seeds, 0, K,
+                                                             rmax_scratch, idx, segs);
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

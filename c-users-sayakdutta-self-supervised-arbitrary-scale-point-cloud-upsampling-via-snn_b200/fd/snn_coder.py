@@ -107,17 +107,18 @@ class EnhancedSNNDistanceEstimation(NativeModel):
             x = x.reshape(B * Np, M, 3)
         if x.ndim != 3:
             raise N.SapcuError("fd forward expects a 3-D or 4-D tensor, got shape %s" % (tuple(Xc_rotated.shape),))
-        if x.shape[1] == 3 and x.shape[2] != 3:
-            x = x.transpose(1, 2).contiguous()       # reference fd/snn_coder.py:393-394 treats [B,3,M] as channel-first
+        if x.shape[1] == 3:
+            x = x.transpose(1, 2).contiguous()       # reference fd/snn_coder.py:393-394: shape[1] == 3 IS channel-first [B,3,M] (also for [B,3,3])
         if x.shape[2] != 3:
             raise N.SapcuError("fd forward: last dimension must be 3, got %s" % (tuple(x.shape),))
         S, M = x.shape[0], x.shape[1]
         out = torch.empty(S, dtype=torch.float32, device=x.device)
         if S:
-            h = self._ensure_handle()
-            ws = self._workspace(S, M, x.device)
-            if forced_idx is not None:
-                forced_idx = forced_idx.to(device=x.device, dtype=torch.int32).contiguous()
-            N.check(N.lib().sapcu_fd_forward(h, N.ptr(x), S, M, N.ptr(out), N.ptr(forced_idx), N.ptr(ws), ws.numel(),
-                                             self.mode, N.stream_ptr()), "sapcu_fd_forward")
+            with torch.cuda.device(x.device):        # weights, workspace, stream and launches all on the input's device
+                h = self._ensure_handle(x.device)
+                ws = self._workspace(S, M, x.device)
+                if forced_idx is not None:
+                    forced_idx = forced_idx.to(device=x.device, dtype=torch.int32).contiguous()
+                N.check(N.lib().sapcu_fd_forward(h, N.ptr(x), S, M, N.ptr(out), N.ptr(forced_idx), N.ptr(ws), ws.numel(),
+                                                 self.mode, N.stream_ptr(x.device)), "sapcu_fd_forward")
         return out.view(*lead) if lead else out

@@ -117,8 +117,9 @@ class ImprovedSNNNormalEstimation(NativeModel):
         S, M = x.shape[0], x.shape[1]
         out = torch.empty(S, 3, dtype=torch.float32, device=x.device)
         if S:
-            h = self._ensure_handle()
-            ws = self._workspace(S, M, x.device)
-            N.check(N.lib().sapcu_fn_forward(h, N.ptr(x), S, M, N.ptr(out), N.ptr(ws), ws.numel(), self.mode,
-                                             N.stream_ptr()), "sapcu_fn_forward")
+            with torch.cuda.device(x.device):        # weights, workspace, stream and launches all on the input's device
+                h = self._ensure_handle(x.device)
+                ws = self._workspace(S, M, x.device)
+                N.check(N.lib().sapcu_fn_forward(h, N.ptr(x), S, M, N.ptr(out), N.ptr(ws), ws.numel(), self.mode,
+                                                 N.stream_ptr(x.device)), "sapcu_fn_forward")
         return out.view(*lead, 3) if lead else out

@@ -28,7 +28,8 @@ def farthest_point_sample(xyz, npoint, device="cuda"):
     n = d.shape[0]
     out = torch.empty(int(npoint), dtype=torch.int32, device=d.device)
     ws = torch.zeros(32, dtype=torch.uint8, device=d.device)
-    N.check(L.sapcu_fps(N.ptr(d), n, int(npoint), n // 2, N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr()), "sapcu_fps")
+    with torch.cuda.device(d.device):
+        N.check(L.sapcu_fps(N.ptr(d), n, int(npoint), n // 2, N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr(d.device)), "sapcu_fps")
     return out.cpu().numpy().astype(np.int64)
 
 

@@ -32,6 +32,20 @@ def rotation_matrix_from_vectors(vec1, vec2):
     return np.eye(3) + k + k.dot(k) * ((1 - c) / (s ** 2))
 
 
+def _on_device(fn):
+    """Run a Generator3D6 method with the generator's CUDA device current (launches, allocations and the stream the
+    C ABI receives all belong to that device, whichever device the calling thread had selected)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        if self.device.type != "cuda":
+            raise N.SapcuError("Generator3D6 needs a CUDA device (no CPU fallback)")
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class Generator3D6(object):
     def __init__(self, model1, model2, device, k_neighbors=100, dense_spacing=0.004,
                  outlier_threshold=1.5, batch_size=400, seeds_per_pass=None, remove_outliers=True, seed_source="gpu"):
@@ -73,7 +87,8 @@ class Generator3D6(object):
             self._bufs[key] = buf
         return buf[:n].view(*shape)
 
-    def displace_host(self, cloud, seeds):
+    @_on_device
+    def displace_host(self, cloud, seeds, batch=None):
         """cloud [N,3] f64, seeds [S,3] f64 (host) -> displaced points [S,3] f64 (host).
         Timed end to end by bench.py: includes the H2D copies of its inputs and the D2H copy of the result."""
         if self.device.type != "cuda":
@@ -84,46 +99,77 @@ class Generator3D6(object):
         h_seeds.copy_(torch.from_numpy(seeds))
         d_cloud = h_cloud.to(self.device, non_blocking=True)
         d_seeds = h_seeds.to(self.device, non_blocking=True)
-        d_out = self.displace_device(d_cloud, d_seeds)
+        d_out = self.displace_device(d_cloud, d_seeds, batch=batch)
         h_out = self._pinned("out", seeds.shape, torch.float64)
-        h_out.copy_(d_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.device(self.device):
+            h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
         return h_out.numpy().copy()
 
     @torch.no_grad()
-    def displace_device(self, d_cloud, d_seeds, return_parts=False):
-        """Device-resident pipeline: cloud [N,3] f64, seeds [S,3] f64 (cuda) -> [S,3] f64 (cuda)."""
+    def displace_device(self, d_cloud, d_seeds, return_parts=False, batch=None):
+        """Device-resident pipeline: cloud [N,3] f64, seeds [S,3] f64 (cuda) -> [S,3] f64 (cuda).
+        batch = (cloud_off, seed_off): host prefix tables ([B+1] ints) when d_cloud / d_seeds are the concatenation of
+        B independent (cloud, seed set) problems -- one batched kNN launch, then the same per-seed pipeline."""
         L = N.lib()
         K = self.k_neighbors
         Ncl, S = d_cloud.shape[0], d_seeds.shape[0]
         dev = d_cloud.device
-        st = N.stream_ptr()
-        out = torch.empty(S, 3, dtype=torch.float64, device=dev)
-        normals = torch.empty(S, 3, dtype=torch.float32, device=dev)
-        dist = torch.empty(S, dtype=torch.float32, device=dev)
-        idx = torch.empty(S, K, dtype=torch.int32, device=dev)
-        kws = torch.empty(L.sapcu_knn_workspace_bytes(Ncl), dtype=torch.uint8, device=dev)
-        N.check(L.sapcu_knn(N.ptr(d_cloud), Ncl, N.ptr(d_seeds), S, K, N.ptr(idx), N.ptr(kws), kws.numel(), st), "sapcu_knn")
-        step = S if not self.seeds_per_pass else int(self.seeds_per_pass)
-        step = max(step, 1)
-        patches = torch.empty(min(S, step), K, 3, dtype=torch.float32, device=dev)
-        for s0 in range(0, S, step):
-            s1 = min(S, s0 + step)
-            n = s1 - s0
-            p = patches[:n]
-            N.check(L.sapcu_gather_center_rotate(N.ptr(d_cloud), Ncl, N.ptr(d_seeds[s0:]), N.ptr(idx[s0:]), n, K, None,
-                                                 N.ptr(p), st), "gather_center")
-            normals[s0:s1] = self.model1(p)
-            N.check(L.sapcu_renormalize(N.ptr(normals[s0:]), n, st), "renormalize")
-            N.check(L.sapcu_gather_center_rotate(N.ptr(d_cloud), Ncl, N.ptr(d_seeds[s0:]), N.ptr(idx[s0:]), n, K,
-                                                 N.ptr(normals[s0:]), N.ptr(p), st), "gather_center_rotate")
-            dist[s0:s1] = self.model2(p)
-        N.check(L.sapcu_displace(N.ptr(d_seeds), N.ptr(normals), N.ptr(dist), S, N.ptr(out), st), "displace")
+        with torch.cuda.device(dev):              # every launch below goes to the tensors' device and its current stream
+            st = N.stream_ptr(dev)
+            out = torch.empty(S, 3, dtype=torch.float64, device=dev)
+            normals = torch.empty(S, 3, dtype=torch.float32, device=dev)
+            dist = torch.empty(S, dtype=torch.float32, device=dev)
+            idx = torch.empty(S, K, dtype=torch.int32, device=dev)
+            if batch is None:
+                kws = torch.empty(L.sapcu_knn_workspace_bytes(Ncl), dtype=torch.uint8, device=dev)
+                N.check(L.sapcu_knn(N.ptr(d_cloud), Ncl, N.ptr(d_seeds), S, K, N.ptr(idx), N.ptr(kws), kws.numel(), st), "sapcu_knn")
+            else:
+                co = np.ascontiguousarray(batch[0], dtype=np.int64)
+                so = np.ascontiguousarray(batch[1], dtype=np.int64)
+                B = co.shape[0] - 1
+                if so.shape[0] != B + 1 or co[-1] != Ncl or so[-1] != S:
+                    raise ValueError("batch offsets do not match the concatenated arrays")
+                kws = torch.empty(L.sapcu_knn_batched_workspace_bytes(Ncl, B), dtype=torch.uint8, device=dev)
+                N.check(L.sapcu_knn_batched(N.ptr(d_cloud), co.ctypes.data, N.ptr(d_seeds), so.ctypes.data, B, K, N.ptr(idx),
+                                            N.ptr(kws), kws.numel(), st), "sapcu_knn_batched")
+            step = S if not self.seeds_per_pass else int(self.seeds_per_pass)
+            step = max(step, 1)
+            patches = torch.empty(min(S, step), K, 3, dtype=torch.float32, device=dev)
+            for s0 in range(0, S, step):
+                s1 = min(S, s0 + step)
+                n = s1 - s0
+                p = patches[:n]
+                N.check(L.sapcu_gather_center_rotate(N.ptr(d_cloud), Ncl, N.ptr(d_seeds[s0:]), N.ptr(idx[s0:]), n, K, None,
+                                                     N.ptr(p), st), "gather_center")
+                normals[s0:s1] = self.model1(p)
+                N.check(L.sapcu_renormalize(N.ptr(normals[s0:]), n, st), "renormalize")
+                N.check(L.sapcu_gather_center_rotate(N.ptr(d_cloud), Ncl, N.ptr(d_seeds[s0:]), N.ptr(idx[s0:]), n, K,
+                                                     N.ptr(normals[s0:]), N.ptr(p), st), "gather_center_rotate")
+                dist[s0:s1] = self.model2(p)
+            N.check(L.sapcu_displace(N.ptr(d_seeds), N.ptr(normals), N.ptr(dist), S, N.ptr(out), st), "displace")
         if return_parts:
             return out, idx, normals, dist
         return out
 
+    def upsample_batch(self, clouds, seeds):
+        """A batch of independent clouds in one device pipeline (the per-file loop of the reference's generate.py:135-160
+        as ONE call): clouds / seeds are lists of [N_b,3] / [S_b,3] arrays; returns the list of displaced [S_b,3] f64
+        arrays (outlier-filtered per cloud when remove_outliers is set)."""
+        clouds = [np.ascontiguousarray(np.asarray(c, dtype=np.float64).reshape(-1, 3)) for c in clouds]
+        seeds = [np.ascontiguousarray(np.asarray(s, dtype=np.float64)[:, :3]) for s in seeds]
+        if len(clouds) != len(seeds):
+            raise ValueError("upsample_batch: one seed array per cloud")
+        co = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+        so = np.concatenate([[0], np.cumsum([s.shape[0] for s in seeds])]).astype(np.int64)
+        out = self.displace_host(np.concatenate(clouds, 0), np.concatenate(seeds, 0), batch=(co, so))
+        res = [out[so[b]:so[b + 1]] for b in range(len(clouds))]
+        if self.remove_outliers:
+            res = [self._outlier_filter(r) for r in res]
+        return res
+
     # ------------------------------------------------------------------ host-side steps outside the hot path
+    @_on_device
     def gpu_seeds(self, data, cap=None, quirk_origin=True, round6=True):
         """Seeds of dense.cpp computed on the device (csrc/seedgen.cu): same set, same order as `./dense`."""
         import ctypes
@@ -136,7 +182,7 @@ class Generator3D6(object):
             out = torch.empty(cap, 3, dtype=torch.float64, device=self.device)
             cnt = ctypes.c_int64(0)
             N.check(L.sapcu_seedgen(N.ptr(d_cloud), n, float(self.dense_spacing), int(quirk_origin), int(round6), N.ptr(out), cap,
-                                    ctypes.byref(cnt), N.ptr(ws), ws.numel(), N.stream_ptr()), "sapcu_seedgen")
+                                    ctypes.byref(cnt), N.ptr(ws), ws.numel(), N.stream_ptr(self.device)), "sapcu_seedgen")
             if cnt.value <= cap:
                 return out[:cnt.value].cpu().numpy()
             cap = int(cnt.value)
@@ -151,6 +197,7 @@ class Generator3D6(object):
         os.system(cmd)
         return np.loadtxt("target.xyz")[:, 0:3]
 
+    @_on_device
     def _outlier_filter(self, xyz):
         """generation.py:176-183 on the device: self-kNN (k = 30) with sapcu_knn, mean neighbour distance per point,
         keep the points below outlier_threshold x the global mean."""
@@ -158,7 +205,7 @@ class Generator3D6(object):
         S = xyz.shape[0]
         if S < 30:
             raise ValueError("k must be less than or equal to the number of training points")   # as sklearn does
-        st = N.stream_ptr()
+        st = N.stream_ptr(self.device)
         d_pts = torch.from_numpy(np.ascontiguousarray(xyz, dtype=np.float64)).to(self.device)
         idx = torch.empty(S, 30, dtype=torch.int32, device=self.device)
         kws = torch.empty(L.sapcu_knn_workspace_bytes(S), dtype=torch.uint8, device=self.device)

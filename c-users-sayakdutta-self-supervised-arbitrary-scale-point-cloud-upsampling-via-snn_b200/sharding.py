@@ -31,21 +31,64 @@ def all_gather_rows(local, S, group=None):
         return local
     bounds = shard_bounds(S, world)
     pad = max(hi - lo for lo, hi in bounds)
-    buf = torch.zeros(pad, *local.shape[1:], dtype=local.dtype, device=local.device)
-    buf[: local.shape[0]] = local
+    even = all(hi - lo == pad for lo, hi in bounds)
+    if even:
+        buf = local.contiguous()                      # equal shards: gather straight into the result, no padding copy
+    else:
+        buf = torch.zeros(pad, *local.shape[1:], dtype=local.dtype, device=local.device)
+        buf[: local.shape[0]] = local
     out = torch.empty(world * pad, *local.shape[1:], dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, buf, group=group) if local.is_cuda else \
         dist.all_gather(list(out.view(world, pad, *local.shape[1:]).unbind(0)), buf, group=group)
+    if even:
+        return out
     out = out.view(world, pad, *local.shape[1:])
     return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(bounds)], dim=0)
 
 
-def upsample_sharded(generator, d_cloud, d_seeds, group=None):
+def shard_batch_offsets(seed_off, lo, hi):
+    """Prefix table of a batched problem restricted to the flat seed range [lo, hi): cloud b keeps the seeds
+    [max(seed_off[b], lo), min(seed_off[b+1], hi)) -- possibly none -- and the clouds stay replicated."""
+    import numpy as np
+    so = np.clip(np.asarray(seed_off, dtype=np.int64), lo, hi) - lo
+    return so
+
+
+def upsample_sharded(generator, d_cloud, d_seeds, group=None, batch=None):
     """Run Generator3D6.displace_device on this rank's seed range and all-gather the result.
-    d_cloud [N,3] f64 and d_seeds [S,3] f64 are replicated device tensors."""
+    d_cloud [N,3] f64 and d_seeds [S,3] f64 are replicated device tensors; batch = (cloud_off, seed_off) for a batch of
+    independent clouds (the flattened (cloud, seed) list is what gets sharded)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     S = d_seeds.shape[0]
     lo, hi = shard_range(S, rank, world)
-    local = generator.displace_device(d_cloud, d_seeds[lo:hi].contiguous())
+    if batch is not None:
+        batch = (batch[0], shard_batch_offsets(batch[1], lo, hi))
+    local = generator.displace_device(d_cloud, d_seeds[lo:hi].contiguous(), batch=batch)
     return all_gather_rows(local, S, group)
+
+
+def upsample_sharded_host(generator, cloud, seeds, group=None, batch=None):
+    """Host arrays in, host array out, on every rank: pinned H2D of the (replicated) cloud and of THIS rank's seed range,
+    the device pipeline, the all-gather of the displaced points and the D2H copy of the gathered [S,3] result.
+    This is the end-to-end call bench.py times (`e2e`)."""
+    import numpy as np
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    S = seeds.shape[0]
+    lo, hi = shard_range(S, rank, world)
+    dev = generator.device
+    with torch.cuda.device(dev):
+        h_cloud = generator._pinned("cloud", cloud.shape, torch.float64)
+        h_cloud.copy_(torch.from_numpy(np.ascontiguousarray(cloud)))
+        h_seeds = generator._pinned("seeds", (hi - lo, 3), torch.float64)
+        h_seeds.copy_(torch.from_numpy(np.ascontiguousarray(seeds[lo:hi])))
+        d_cloud = h_cloud.to(dev, non_blocking=True)
+        d_seeds = h_seeds.to(dev, non_blocking=True)
+        b = None if batch is None else (batch[0], shard_batch_offsets(batch[1], lo, hi))
+        local = generator.displace_device(d_cloud, d_seeds, batch=b)
+        full = all_gather_rows(local, S, group)
+        h_out = generator._pinned("out_full", (S, 3), torch.float64)
+        h_out.copy_(full, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    return h_out.numpy()

@@ -39,10 +39,14 @@ extern "C" {
 
 /* arithmetic modes of the dense contractions */
 #define SAPCU_MODE_FP32     0   /* fp32 FFMA everywhere: the "fp32 parity mode" */
-#define SAPCU_MODE_TC       1   /* tcgen05 tensor-core contractions, 3xTF32 split (fp32-grade products, fp32 accumulate):
-                                   meets the fp32-parity tolerances; the benchmarked mode */
-#define SAPCU_MODE_TF32     2   /* tcgen05 single-pass TF32 contractions (10-bit mantissa operands): the fast
-                                   tensor-core mode, deviation reported separately */
+#define SAPCU_MODE_TC       1   /* tcgen05 tensor-core contractions with 3 split products per MAC (fp16 hi/lo planes where the
+                                   input is a spike tensor, tf32 hi/lo elsewhere; fp32-grade products, fp32 accumulate):
+                                   meets the fp32-parity tolerances; the mode configs[1] is benchmarked in */
+#define SAPCU_MODE_TF32     2   /* tcgen05 single-pass TF32 contractions (10-bit mantissa operands), fp32-grade neuron;
+                                   deviation reported separately */
+#define SAPCU_MODE_FAST     3   /* the fast tensor-core mode: ONE fp16 product per MAC on fp16 spike tensors (single-pass
+                                   TF32 where the input is not a spike tensor), reduced-MUFU / tabulated LIF^T chains;
+                                   deviation reported separately (profiles/, tests/test_gpu_parity.py) */
 
 const char* sapcu_last_error(void);
 int         sapcu_abi_version(void);
@@ -54,6 +58,10 @@ int64_t     sapcu_launch_count(void);
  * returns their summed duration, the algorithmic FLOPs (2*R*K*N per launch) and the launch count since enable. */
 int sapcu_profile(int enable);
 int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+/* Per-kernel report of the same recording as JSON text: [{"label", "launches", "ms", "flops", "lif_elsteps", "bytes"}, ...]
+ * (one entry per kernel label of the fn / fd forwards; algorithmic work per label, summed durations).  Writes at most
+ * cap bytes (NUL-terminated) and returns the size needed, or a negative error code. */
+int64_t sapcu_profile_report(char* h_buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------
  * K1  seed -> input-cloud kNN.  Replaces sklearn KDTree(data).query(chunk, K)
@@ -64,6 +72,17 @@ int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launch
 size_t sapcu_knn_workspace_bytes(int64_t N);   /* fp32 copy of the cloud + one scalar */
 int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S, int K,
               int32_t* d_idx, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Batched form: B independent (cloud, seed set) problems in ONE launch -- the per-file loop of generate.py:135-160
+ * (one KDTree per input file) for a batch of small clouds.  d_clouds / d_seeds are the concatenated [N_total,3] /
+ * [S_total,3] fp64 arrays, h_cloud_off / h_seed_off HOST prefix tables of B+1 entries (first 0, last the total).
+ * Seeds of problem b see only cloud b; d_idx[s*K + j] is a row of the CONCATENATED cloud array (cloud-local index +
+ * h_cloud_off[b]), so sapcu_gather_center_rotate runs on the concatenated arrays unchanged.  Same exactness and
+ * tie-break as sapcu_knn; every non-empty problem needs N_b >= K.  Synchronises the stream once (offset upload). */
+size_t sapcu_knn_batched_workspace_bytes(int64_t N_total, int B);
+int sapcu_knn_batched(const double* d_clouds, const int64_t* h_cloud_off, const double* d_seeds,
+                      const int64_t* h_seed_off, int B, int K, int32_t* d_idx,
+                      void* d_ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K2  gather + centre (+ rotate).  Replaces data[idx] - seed and the per-seed Rodrigues

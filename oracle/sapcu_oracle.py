@@ -109,7 +109,7 @@ def intra_knn(x, k):
 def gather_points(points, idx):
     """`index_points` (fn/snn_coder.py:19-29): points [B,N,C], idx [B,N,k] -> [B,N,k,C]."""
     B = points.shape[0]
-    bidx = torch.arange(B).view(B, *([1] * (idx.dim() - 1))).expand_as(idx)
+    bidx = torch.arange(B, device=idx.device).view(B, *([1] * (idx.dim() - 1))).expand_as(idx)
     return points[bidx, idx, :]
 
 
@@ -226,7 +226,7 @@ def fd_encoder(sd, patches, cfg=None, schedule="faithful", taps=None, forced_idx
             if t == 0:
                 pre_act[0] = u
         else:
-            u = torch.zeros(B, 64, M)          # multiplied by the closed gate: value is irrelevant
+            u = torch.zeros(B, 64, M, device=x.device)          # multiplied by the closed gate: value is irrelevant
         s, states[0] = step_fns[0](u, prms[0], states[0])                                   # :432-443
         feats.append(s)
         cur = s
@@ -242,7 +242,7 @@ def fd_encoder(sd, patches, cfg=None, schedule="faithful", taps=None, forced_idx
                 if t == 0:
                     pre_act[b] = u
             else:
-                u = torch.zeros(B, prms[b]["threshold_base"].numel(), M)
+                u = torch.zeros(B, prms[b]["threshold_base"].numel(), M, device=x.device)
             s, states[b] = step_fns[b](u, prms[b], states[b])
             feats.append(s)
             cur = s
@@ -329,19 +329,24 @@ def displace(seeds, normals, dist):
     return seeds + normals * np.tile(np.expand_dims(dist, 1), (1, 3))
 
 
-def pipeline(sd_fn, sd_fd, cloud, seeds, K=100, batch=256, cfg_fn=None, cfg_fd=None, schedule="faithful"):
-    """generation.py:122-172 with injected seeds: returns (points [S,3] f64, idx, normals f32, dist f32)."""
+def pipeline(sd_fn, sd_fd, cloud, seeds, K=100, batch=256, cfg_fn=None, cfg_fd=None, schedule="faithful", device=None):
+    """generation.py:122-172 with injected seeds: returns (points [S,3] f64, idx, normals f32, dist f32).
+    device: where the two model forwards run, exactly as in the reference (`.to(device)` per batch, generation.py:137,168;
+    kNN, gather and the rotations stay on the host); None = CPU.  On CUDA the caller disables TF32."""
     cfg_fd = cfg_fd or dict(k=32, time_steps_enc=7, k_scales=[8, 16, 32, 48], num_heads=8)
+    if device is not None:
+        sd_fn = {k: v.to(device) for k, v in sd_fn.items()}
+        sd_fd = {k: v.to(device) for k, v in sd_fd.items()}
     idx = knn_seed(cloud, seeds, K)
     normals, dists = [], []
     with torch.no_grad():
         for s0 in range(0, seeds.shape[0], batch):
             sl = slice(s0, min(seeds.shape[0], s0 + batch))
-            p = torch.from_numpy(gather_center(cloud, seeds[sl], idx[sl]))
-            n = F.normalize(fn_forward(sd_fn, p, cfg_fn), dim=-1).numpy()                   # :138-139
+            p = torch.from_numpy(gather_center(cloud, seeds[sl], idx[sl])).to(device)
+            n = F.normalize(fn_forward(sd_fn, p, cfg_fn), dim=-1).cpu().numpy()             # :138-139
             normals.append(n)
-            pr = torch.from_numpy(gather_center(cloud, seeds[sl], idx[sl], n))
-            dists.append(fd_forward(sd_fd, pr, cfg_fd, schedule).numpy())
+            pr = torch.from_numpy(gather_center(cloud, seeds[sl], idx[sl], n)).to(device)
+            dists.append(fd_forward(sd_fd, pr, cfg_fd, schedule).cpu().numpy())
     normals, dists = np.concatenate(normals, 0), np.concatenate(dists, 0)
     return displace(seeds, normals, dists), idx, normals, dists
 

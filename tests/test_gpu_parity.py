@@ -649,3 +649,84 @@ def test_non_yaml_configs_take_the_fallback_paths(lib, sphere):
     rel = np.abs(got_d - ref_d) / np.maximum(np.abs(ref_d), 1e-6)
     print("non-yaml configs: normals %.2e deg, distances %.2e rel" % (_angle_deg(got_n, ref_n).max(), rel.max()))
     assert rel.max() < 1e-3
+
+
+# ----------------------------------------------------------------------------------------- round 2: batched clouds, other configs
+def _knn_batched(lib, clouds, seeds, K):
+    co = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+    so = np.concatenate([[0], np.cumsum([s.shape[0] for s in seeds])]).astype(np.int64)
+    dc = torch.from_numpy(np.concatenate(clouds, 0)).to(DEV)
+    ds = torch.from_numpy(np.concatenate(seeds, 0)).to(DEV) if so[-1] else torch.empty(0, 3, dtype=torch.float64, device=DEV)
+    idx = torch.full((int(so[-1]), K), -1, dtype=torch.int32, device=DEV)
+    ws = torch.empty(lib.sapcu_knn_batched_workspace_bytes(int(co[-1]), len(clouds)), dtype=torch.uint8, device=DEV)
+    N.check(lib.sapcu_knn_batched(N.ptr(dc), co.ctypes.data, N.ptr(ds), so.ctypes.data, len(clouds), K, N.ptr(idx), N.ptr(ws),
+                                  ws.numel(), None), "knn_batched")
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), co, so
+
+
+def test_knn_batched_bit_exact_per_cloud(lib):
+    """BASELINE configs[2] shape: a batch of independent clouds in ONE launch; every cloud's rows must equal the
+    single-cloud exact kNN (oracle_c, fp64, lowest-index ties), shifted by the cloud's offset.  Ragged sizes, an empty
+    seed set, a seed count that is not a multiple of the CTA's 8 seeds, duplicated points."""
+    rng = np.random.default_rng(11)
+    clouds = [syn.cloud(2048, seed=20, shape="boxes"), syn.cloud(300, seed=21), syn.cloud(1000, seed=22, shape="boxes"),
+              rng.normal(size=(64, 3))]
+    clouds[3][10:20] = clouds[3][30:40]                                  # exact ties
+    seeds = [syn.seeds(clouds[0], 0.5, seed=30), np.zeros((0, 3)), syn.seeds(clouds[2], 0.013, seed=32), rng.normal(size=(5, 3))]
+    for K in (48, 64):
+        idx, co, so = _knn_batched(lib, clouds, seeds, K)
+        for b in range(4):
+            if seeds[b].shape[0]:
+                ref = oracle_c.knn(clouds[b], seeds[b], K) + int(co[b])
+                assert np.array_equal(idx[so[b]:so[b + 1]], ref), "cloud %d K=%d" % (b, K)
+    # error behaviour: a non-empty problem whose cloud is smaller than K
+    co = np.array([0, 10], dtype=np.int64); so = np.array([0, 1], dtype=np.int64)
+    dc = torch.zeros(10, 3, dtype=torch.float64, device=DEV); ds = torch.zeros(1, 3, dtype=torch.float64, device=DEV)
+    out = torch.zeros(1, 48, dtype=torch.int32, device=DEV)
+    ws = torch.empty(lib.sapcu_knn_batched_workspace_bytes(10, 1), dtype=torch.uint8, device=DEV)
+    assert lib.sapcu_knn_batched(N.ptr(dc), co.ctypes.data, N.ptr(ds), so.ctypes.data, 1, 48, N.ptr(out), N.ptr(ws), ws.numel(), None) == -1
+    assert b"points < K" in lib.sapcu_last_error()
+
+
+def test_upsample_batch_equals_per_cloud_pipeline(lib):
+    """upsample_batch (one batched kNN + one device pipeline over the flattened (cloud, seed) list) returns, per cloud, exactly
+    the points of the single-cloud pipeline; the sharded form of the batch (any contiguous split of the flat list) too."""
+    from sapcu_b200.generation import Generator3D6
+    from sapcu_b200.sharding import shard_batch_offsets
+    mfn, mfd, _, _ = _models(True)
+    mfn.set_mode("tc"), mfd.set_mode("tc")
+    gen = Generator3D6(mfn, mfd, DEV, k_neighbors=100, remove_outliers=False)
+    clouds = [syn.cloud(2048, seed=40 + b, shape="boxes") for b in range(3)]
+    seeds = [syn.seeds(c, r, seed=50 + b) for b, (c, r) in enumerate(zip(clouds, (0.05, 0.02, 0.031)))]
+    res = gen.upsample_batch(clouds, seeds)
+    single = [gen.upsample(np.expand_dims(c, 0), seeds=s) for c, s in zip(clouds, seeds)]
+    for a, b in zip(res, single):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    co = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+    so = np.concatenate([[0], np.cumsum([s.shape[0] for s in seeds])]).astype(np.int64)
+    d_c = torch.from_numpy(np.concatenate(clouds, 0)).to(DEV)
+    flat = np.concatenate(seeds, 0)
+    full = np.concatenate(single, 0)
+    cut = int(so[1]) + 7                                                     # a shard boundary inside cloud 1
+    parts = []
+    for lo, hi in ((0, cut), (cut, int(so[-1]))):
+        d_s = torch.from_numpy(np.ascontiguousarray(flat[lo:hi])).to(DEV)
+        parts.append(gen.displace_device(d_c, d_s, batch=(co, shard_batch_offsets(so, lo, hi))).cpu().numpy())
+    assert np.array_equal(np.concatenate(parts, 0), full)
+
+
+def test_knn_large_scan_non_integer_ratio(lib):
+    """BASELINE configs[3] shape: a 100,000-point scan at the non-integer ratio 3.7 -> 370,000 seeds; a slice of the seeds
+    is checked bit-exactly against the fp64 oracle, the whole result through size-independent properties."""
+    cloud = syn.cloud(100000, seed=0, shape="boxes")
+    seeds = syn.seeds(cloud, 3.7, seed=1)
+    assert seeds.shape[0] == 370000
+    idx = _knn(lib, cloud, seeds, 100)
+    sl = np.r_[0:64, 184000:184064, 369936:370000]
+    assert np.array_equal(idx[sl], oracle_c.knn(cloud, seeds[sl], 100))
+    assert idx.min() >= 0 and idx.max() < 100000
+    srt = np.sort(idx[::97], axis=1)
+    assert (srt[:, 1:] != srt[:, :-1]).all()
+    dd = np.linalg.norm(cloud[idx[::97]] - seeds[::97, None, :], axis=2)
+    assert (np.diff(dd, axis=1) >= -1e-15).all()

@@ -128,3 +128,17 @@ def test_all_gather_rows_world2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0 and b"ok" in out, out.decode()
+
+
+def test_shard_batch_offsets():
+    """Strong-scaling shards of a batch of clouds: the flat (cloud, seed) list is cut into contiguous ranges; each rank's
+    per-cloud seed offsets are the global prefix table clipped to its range."""
+    from sapcu_b200.sharding import shard_bounds, shard_batch_offsets
+    so = np.array([0, 5, 5, 12, 20], dtype=np.int64)           # 4 clouds, the second without seeds
+    for world in (1, 2, 3, 8):
+        total = np.zeros(4, dtype=np.int64)
+        for lo, hi in shard_bounds(20, world):
+            loc = shard_batch_offsets(so, lo, hi)
+            assert loc[0] == 0 and loc[-1] == hi - lo and (np.diff(loc) >= 0).all()
+            total += np.diff(loc)
+        assert np.array_equal(total, np.diff(so))
