@@ -1,0 +1,171 @@
+// Host-side builder of the tabulated LIF^T chains (see lif_table.cuh).  Runs once per model at sapcu_model_finalize.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <array>
+#include <map>
+#include <thread>
+#include "lif_table.cuh"
+
+namespace sapcu {
+
+// One soft spike (fn/snn_coder.py:135-153) in fp64, clamps included.
+static inline double spike_exact(double v) {
+  const double vc = v < -10.0 ? -10.0 : (v > 10.0 ? 10.0 : v);
+  return 0.5 * exp(-(vc * vc) / 2.0) / 2.5066282746310002 + 0.5 / (1.0 + exp(-10.0 * vc));
+}
+
+double lif_chain_exact_host(double u, double d, double a, double r, double th0, int T) {
+  double m = 0.0, th = th0, rho = 0.0, x = u, s = 0.0;
+  for (int t = 0; t < T; ++t) {
+    x = rho <= 0.0 ? x : 0.0;                       // x * float(rho <= 0)
+    m = m * d * (1.0 - rho) + x;
+    s = spike_exact(m - th);
+    m = m * (1.0 - s);
+    rho = rho * r + s;
+    th = th + a * s;
+    th = th0 + (th - th0) * 0.95;
+    x = s;
+  }
+  return s;
+}
+
+namespace {
+
+struct ChanTab {
+  uint16_t k[LT_NCELL];
+  std::vector<std::array<float, 4>> coef;          // cells in order, segments in order inside a cell
+  double err = 0.0;
+};
+
+// Chebyshev nodes on (0, 1) and the inverse Vandermonde matrix mapping node values to monomial coefficients in t
+struct Cheb {
+  double t[4]; double inv[4][4];
+  Cheb() {
+    for (int i = 0; i < 4; ++i) t[i] = 0.5 * (1.0 + cos((2 * i + 1) * M_PI / 8.0));
+    double V[4][8];
+    for (int i = 0; i < 4; ++i) {
+      double p = 1.0;
+      for (int j = 0; j < 4; ++j) { V[i][j] = p; p *= t[i]; V[i][4 + j] = i == j ? 1.0 : 0.0; }
+    }
+    for (int c = 0; c < 4; ++c) {                  // Gauss-Jordan with partial pivoting
+      int piv = c;
+      for (int r = c + 1; r < 4; ++r) if (fabs(V[r][c]) > fabs(V[piv][c])) piv = r;
+      for (int j = 0; j < 8; ++j) std::swap(V[c][j], V[piv][j]);
+      const double d = V[c][c];
+      for (int j = 0; j < 8; ++j) V[c][j] /= d;
+      for (int r = 0; r < 4; ++r) if (r != c) { const double f = V[r][c]; for (int j = 0; j < 8; ++j) V[r][j] -= f * V[c][j]; }
+    }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) inv[i][j] = V[i][4 + j];
+  }
+};
+static const Cheb g_cheb;
+
+// cubic on [y0, y0 + w) of side `sgn`; returns the largest deviation from the exact chain at 9 check points
+double fit_segment(double sgn, double y0, double w, double d, double a, double r, double th0, int T, float (&c)[4]) {
+  double f[4];
+  for (int i = 0; i < 4; ++i) f[i] = lif_chain_exact_host(th0 + sgn * (y0 + w * g_cheb.t[i] - 1.0), d, a, r, th0, T);
+  double co[4];
+  double wp = 1.0;
+  for (int j = 0; j < 4; ++j) {
+    double s = 0.0;
+    for (int i = 0; i < 4; ++i) s += g_cheb.inv[j][i] * f[i];
+    co[j] = s / wp; wp *= w;
+    c[j] = (float)co[j];
+  }
+  double worst = 0.0;
+  for (int q = 0; q <= 8; ++q) {
+    const float tau = (float)(w * (q == 8 ? 0.999999 : q / 8.0));
+    const float p = fmaf(fmaf(fmaf(c[3], tau, c[2]), tau, c[1]), tau, c[0]);     // the device's Horner form, in fp32
+    const double e = fabs((double)p - lif_chain_exact_host(th0 + sgn * (y0 + (double)tau - 1.0), d, a, r, th0, T));
+    worst = e > worst ? e : worst;
+  }
+  return worst;
+}
+
+void build_channel(double d, double a, double r, double th0, int T, ChanTab* out) {
+  out->coef.clear(); out->err = 0.0;
+  std::vector<std::array<float, 4>> best;
+  for (int side = 0; side < 2; ++side) {
+    const double sgn = side ? -1.0 : 1.0;
+    for (int e = 0; e < LT_NB; ++e) {
+      const double y0 = ldexp(1.0, e), cw = y0;       // cell [2^e, 2^(e+1))
+      int k = 0; double kerr = 0.0;
+      for (; k <= LT_KMAX; ++k) {
+        const int n = 1 << k;
+        const double w = cw / n;
+        best.assign(n, std::array<float, 4>());
+        kerr = 0.0;
+        bool ok = true;
+        for (int j = 0; j < n; ++j) {
+          float c[4];
+          const double e1 = fit_segment(sgn, y0 + j * w, w, d, a, r, th0, T, c);
+          kerr = e1 > kerr ? e1 : kerr;
+          if (e1 > LT_TOL && k < LT_KMAX) { ok = false; break; }
+          best[j] = {c[0], c[1], c[2], c[3]};
+        }
+        if (ok) break;
+      }
+      if (k > LT_KMAX) k = LT_KMAX;
+      out->k[side * LT_NB + e] = (uint16_t)k;
+      out->err = kerr > out->err ? kerr : out->err;
+      out->coef.insert(out->coef.end(), best.begin(), best.end());
+    }
+  }
+}
+
+}  // namespace
+
+void lif_table_build(const float* np4, int C, int T, LifTableHost* out) {
+  out->C = C; out->T = T; out->blocks.clear(); out->image.clear(); out->max_err = 0.0; out->max_block_bytes = 0; out->usable = true;
+  // identical parameter tuples (every channel of a default-initialised layer) share one fit
+  std::map<std::array<float, 4>, int> uniq;
+  std::vector<int> which(C);
+  std::vector<std::array<float, 4>> keys;
+  for (int c = 0; c < C; ++c) {
+    const std::array<float, 4> key = {np4[c], np4[C + c], np4[2 * C + c], np4[3 * C + c]};
+    auto it = uniq.find(key);
+    if (it == uniq.end()) { it = uniq.emplace(key, (int)keys.size()).first; keys.push_back(key); }
+    which[c] = it->second;
+  }
+  std::vector<ChanTab> tabs(keys.size());
+  const int nthr = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32u));
+  auto work = [&](int t0) {
+    for (size_t i = t0; i < keys.size(); i += nthr) build_channel(keys[i][0], keys[i][1], keys[i][2], keys[i][3], T, &tabs[i]);
+  };
+  if (keys.size() < 4 || nthr == 1) { for (int t = 0; t < nthr; ++t) work(t); }
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthr; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  const int nblk = (C + LT_CH - 1) / LT_CH;
+  for (int b = 0; b < nblk; ++b) {
+    LifTableBlock blk;
+    blk.off_bytes = (out->image.size() + 255) / 256 * 256;
+    uint32_t nseg = 0;
+    for (int cl = 0; cl < LT_CH && b * LT_CH + cl < C; ++cl) nseg += (uint32_t)tabs[which[b * LT_CH + cl]].coef.size();
+    blk.nseg = nseg;
+    blk.bytes = LT_DESC_BYTES + nseg * 16u;
+    out->image.resize(blk.off_bytes + blk.bytes, 0);
+    uint16_t* desc = reinterpret_cast<uint16_t*>(out->image.data() + blk.off_bytes);
+    float* coef = reinterpret_cast<float*>(out->image.data() + blk.off_bytes + LT_DESC_BYTES);
+    uint32_t base = 0;
+    for (int cl = 0; cl < LT_CH && b * LT_CH + cl < C; ++cl) {
+      const ChanTab& t = tabs[which[b * LT_CH + cl]];
+      out->max_err = t.err > out->max_err ? t.err : out->max_err;
+      for (int cell = 0; cell < LT_NCELL; ++cell) {
+        if (base > 0x1FFFu) out->usable = false;
+        desc[cl * LT_NCELL + cell] = (uint16_t)((t.k[cell] << 13) | (base & 0x1FFFu));
+        base += 1u << t.k[cell];
+      }
+      memcpy(coef, t.coef.data(), t.coef.size() * 16);
+      coef += t.coef.size() * 4;
+    }
+    if (blk.bytes > LT_SMEM_BUDGET) out->usable = false;
+    out->max_block_bytes = blk.bytes > out->max_block_bytes ? blk.bytes : out->max_block_bytes;
+    out->blocks.push_back(blk);
+  }
+}
+
+}  // namespace sapcu
