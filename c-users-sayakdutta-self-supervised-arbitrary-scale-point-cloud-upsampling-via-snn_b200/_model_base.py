@@ -112,5 +112,9 @@ class NativeModel(nn.Module):
             n = rows.value * cols.value
             h = self._ws.view(torch.float16)[2 * off.value: 2 * off.value + 2 * n].view(2, rows.value, cols.value)
             return (h[0].float() + h[1].float()) / 8192.0
+        if fmt == 2:      # fast mode: ONE fp16 plane of x * 2^13
+            n = rows.value * cols.value
+            h = self._ws.view(torch.float16)[2 * off.value: 2 * off.value + n].view(rows.value, cols.value)
+            return h.float() / 8192.0
         flat = self._ws.view(torch.float32) if dtype == torch.float32 else self._ws.view(torch.int32)
         return flat[off.value: off.value + rows.value * ld.value].view(rows.value, ld.value)[:, :cols.value]

@@ -140,7 +140,7 @@ edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __
         const __half2 hv = __floats2half2_rn(y0, y1);
         const float2 hf = __half22float2(hv);
         *reinterpret_cast<__half2*>(hp) = hv;
-        *reinterpret_cast<__half2*>(hp + plane) = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+        if (plane) *reinterpret_cast<__half2*>(hp + plane) = __floats2half2_rn(y0 - hf.x, y1 - hf.y);   // plane == 0: hi plane only (fast mode)
         if (t == 0) *reinterpret_cast<float2*>(spk0 + (patch0 + i0 + a) * (int64_t)ldo + choff + c) = make_float2(v0, v1);
       } else {
         *reinterpret_cast<float2*>(spk + (patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c) = make_float2(v0, v1);
@@ -205,7 +205,8 @@ __global__ void neuron_unroll_kernel(const float* __restrict__ U, int64_t ldu, i
       __half* hp = reinterpret_cast<__half*>(out) + (row * T + t) * ldo + choff + c;
       const float ys = s * 8192.0f;
       const __half hv = __float2half_rn(ys);
-      hp[0] = hv; hp[plane] = __float2half_rn(ys - __half2float(hv));
+      hp[0] = hv;
+      if (plane) hp[plane] = __float2half_rn(ys - __half2float(hv));   // plane == 0: hi plane only (fast mode)
       if (t == 0) out0[row * ldo + choff + c] = s;
     } else if (all_steps) o[(int64_t)t * ldo] = s;
   }

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "neuron.cuh"
+#include "lif_table.cuh"
 
 namespace sapcu {
 
@@ -126,6 +127,80 @@ edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ i
       }
     }
     __syncthreads();
+  }
+}
+
+
+// SAPCU_MODE_FAST flavour of edge_pos_lif: fc_delta (K = 3) + BN + LIF^T on the edge offsets, one fp16 plane of y * 2^13 out.
+// Persistent CTAs (grid.y = 128-channel block, grid.x strides over the patches): the block's tabulated LIF^T chain
+// (lif_table.cuh) is copied to shared memory once; per patch the coordinates and the graph are staged, the Mpts*kk edge
+// offsets are expanded into shared memory, and 4 threads per channel walk the edges (lane = channel, so a warp's 32 stores
+// of a row are 64 contiguous bytes).  LTAB = 0: no usable table -- the reduced-MUFU recurrence instead.
+constexpr int EPF_THREADS = 512;
+template <int LTAB>
+__global__ void __launch_bounds__(EPF_THREADS)
+edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts, int C,
+                         int64_t S, const float* __restrict__ W, const float* __restrict__ bias,
+                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ np,
+                         int T, __half* __restrict__ out, const uint8_t* __restrict__ tab, uint32_t tab_stride) {
+  extern __shared__ __align__(16) uint8_t epf_sm[];
+  const int EP = Mpts * kk;
+  float4* pd = reinterpret_cast<float4*>(epf_sm);                               // [EP] edge offsets (w unused)
+  float* xs = reinterpret_cast<float*>(epf_sm + (size_t)EP * 16);              // [Mpts][3]
+  uint8_t* tsm = epf_sm + (((size_t)EP * 16 + (size_t)Mpts * 12 + 15) & ~(size_t)15);
+  const int tid = threadIdx.x;
+  const int cl = tid & 127, part = tid >> 7;                                   // channel inside the block, edge phase 0..3
+  const int c = blockIdx.y * 128 + cl;
+  const bool cv = c < C;
+  const int cc = cv ? c : 0;
+  if (LTAB) {
+    const uint4* src = reinterpret_cast<const uint4*>(tab + (size_t)blockIdx.y * tab_stride);
+    uint4* dst = reinterpret_cast<uint4*>(tsm);
+    for (uint32_t i = tid; i < tab_stride / 16; i += EPF_THREADS) dst[i] = src[i];
+  }
+  const uint16_t* lt_desc = reinterpret_cast<const uint16_t*>(tsm) + cl * LT_NCELL;
+  const float4* lt_coef = reinterpret_cast<const float4*>(tsm + LT_DESC_BYTES);
+  // y = ((w.d + b) * sc + sh) folded into one affine map of the offset
+  const float sc = scale[cc];
+  const float w0 = W[3 * cc] * sc, w1 = W[3 * cc + 1] * sc, w2 = W[3 * cc + 2] * sc;
+  const float b0 = fmaf(bias[cc], sc, shift[cc]);
+  const NeuronParams p{np[cc], np[C + cc], np[2 * C + cc], np[3 * C + cc]};
+  for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    const int64_t patch0 = s * Mpts;
+    __syncthreads();                                                           // previous patch fully consumed (and the table landed)
+    for (int i = tid; i < 3 * Mpts; i += EPF_THREADS) xs[i] = xyz[3 * patch0 + i];
+    __syncthreads();
+    for (int e = tid; e < EP; e += EPF_THREADS) {
+      const int pt = e / kk, j = e - pt * kk;
+      const int nb = idx[(patch0 + pt) * ldi + j];
+      pd[e] = make_float4(__fsub_rn(xs[3 * pt], xs[3 * nb]), __fsub_rn(xs[3 * pt + 1], xs[3 * nb + 1]),
+                          __fsub_rn(xs[3 * pt + 2], xs[3 * nb + 2]), 0.0f);
+    }
+    __syncthreads();
+    if (!cv) continue;
+    __half* o = out + patch0 * kk * (int64_t)C + c;
+#pragma unroll 1
+    for (int e0 = part * 4; e0 < EP; e0 += 16) {                               // 4 consecutive edges per thread and round
+      float u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 d = pd[(e0 + j) < EP ? (e0 + j) : (EP - 1)];
+        u[j] = fmaf(w2, d.z, fmaf(w1, d.y, fmaf(w0, d.x, b0)));
+      }
+      if (LTAB) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float sj;
+          if (!lif_table_eval(u[j], p.th0, lt_desc, lt_coef, sj)) sj = lif_chain<false>(u[j], p, T);
+          u[j] = sj;
+        }
+      } else {
+        lif_chain_vec_fast2<4>(u, p, T);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e0 + j < EP) o[(int64_t)(e0 + j) * C] = __float2half_rn(u[j] * 8192.0f);
+    }
   }
 }
 
@@ -286,6 +361,40 @@ int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32
     if (precise) pointwise3_lif_kernel<false, true><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
     else         pointwise3_lif_kernel<false, false><<<grid, 256, 0, st>>>(xyz, idx, kk, ldi, Mpts, rows, C, W, bias, scale, shift, np, T, out);
   }
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+// fast mode: single fp16 plane out, tabulated chain when `tab` is usable
+int launch_edge_pos_lif_fast(const float* xyz, const int32_t* idx, int kk, int ldi, int Mpts, int64_t rows, int C,
+                             const float* W, const float* bias, const float* scale, const float* shift, const float* np, int T,
+                             float* out_h, const float* tab, uint32_t tab_stride, cudaStream_t st) {
+  if (rows == 0) return 0;
+  SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256 && kk >= 1 && rows % ((int64_t)Mpts * kk) == 0, "edge_pos_lif_fast: edge rows must be whole patches of <= 256 points");
+  const int64_t S = rows / ((int64_t)Mpts * kk);
+  const bool lt = tab != nullptr && tab_stride > 0 && tab_stride <= LT_SMEM_BUDGET;
+  const size_t smem = (((size_t)Mpts * kk * 16 + (size_t)Mpts * 12 + 15) & ~(size_t)15) + (lt ? tab_stride : 0);
+  SAPCU_REQUIRE(smem <= 220 * 1024, "edge_pos_lif_fast: patch of %d x %d edges does not fit shared memory", Mpts, kk);
+  static bool done[64] = {};
+  int dev = 0;
+  SAPCU_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !done[dev]) {
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    done[dev] = true;
+  }
+  const int nblk = (int)ceil_div(C, 128);
+  int occ = 1;
+  if (lt) SAPCU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, edge_pos_lif_fast_kernel<1>, EPF_THREADS, smem));
+  else SAPCU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, edge_pos_lif_fast_kernel<0>, EPF_THREADS, smem));
+  if (occ < 1) occ = 1;
+  int64_t gx = ((int64_t)kNumSMs * occ + nblk - 1) / nblk;
+  if (gx > S) gx = S;
+  dim3 grid((unsigned)gx, (unsigned)nblk);
+  if (lt) edge_pos_lif_fast_kernel<1><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T,
+                                                                     reinterpret_cast<__half*>(out_h), reinterpret_cast<const uint8_t*>(tab), tab_stride);
+  else edge_pos_lif_fast_kernel<0><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T,
+                                                                  reinterpret_cast<__half*>(out_h), nullptr, 0);
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

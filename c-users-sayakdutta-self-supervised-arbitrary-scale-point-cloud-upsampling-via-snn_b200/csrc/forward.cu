@@ -181,6 +181,7 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     return 0;
   };
   static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
+  static const bool use_tables = !(getenv("SAPCU_FAST_LIF_TABLES") && atoi(getenv("SAPCU_FAST_LIF_TABLES")) == 0);   // 0: reduced-MUFU chains (A/B)
   // fp16-plane hand-overs: 0 off; 1 (default) pos-enc layer 1 -> fc_delta2 and fc_gamma -> fc_gamma2; 2 / 3 only the first /
   // second; 4 only pos (fc_delta2 -> fc_gamma + attention tail); 5 all three.  The pos planes are measured slower (the
   // attention tail then issues two 2-byte loads per operand instead of one 4-byte load) and stay off.
@@ -198,6 +199,47 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
     SAPCU_TRY(g.L("fn.fc1+lif").layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
     SAPCU_TRY(g.L("fn.qkv+lif").layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
     if (mode == SAPCU_MODE_FP32) { g_tap_gamma_h2 = 0; g_tap_delta2_h2 = 0; SAPCU_TRY(edge_pos(b, Xb, st, 1, false)); }
+    if (mode == SAPCU_MODE_FAST) {
+      // Fast schedule: every per-edge spike tensor of the block is ONE fp16 plane of x * 2^13, every edge contraction one fp16
+      // product per MAC (2-CTA kernel, HM = 3), every LIF^T chain a table lookup where the layer's table fits shared memory.
+      GemmArgs a;
+      {
+        const Layer& L = k.fc_delta2;
+        a.A = Xb; a.lda = D; a.R = E; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
+        a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_delta2.np;
+        a.Y = p.E2; a.ldc = D; a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true; a.tc_passes = 1;
+        a.fast = true; a.x_h2 = true; a.out_h2 = true;
+        if (use_tables && k.snn_delta2.tab_ok) { a.lif_tab = k.snn_delta2.tab; a.lif_tab_stride = k.snn_delta2.tab_stride; }
+      }
+      GemmArgs a1 = gamma_args(b, p.E2, Xb, p.E3), a2 = gamma2_args(b, Xb, p.E2);
+      a1.tc_passes = a2.tc_passes = 1;
+      a1.fast = true; a1.x_h2 = true; a1.out_h2 = true;
+      if (use_tables && k.snn_gamma.tab_ok) { a1.lif_tab = k.snn_gamma.tab; a1.lif_tab_stride = k.snn_gamma.tab_stride; }
+      a2.fast = true; a2.x_h2 = true; a2.pos_h2 = true;
+      const bool blk_fast = factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_fast(a) &&
+                            gemm_tc2_supported(a1, A_PLAIN) && gemm_tc2_fast(a1) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fast(a2);
+      if (blk_fast) {
+        if (b == 2) { g_tap_gamma_h2 = 2; g_tap_delta2_h2 = 2; }
+        {
+          ProfWork w; w.elsteps = (double)E * D * 4; w.bytes = (double)E * D * 2.0;
+          const bool lt = use_tables && k.snn_delta.tab_ok;
+          SAPCU_PROF(st, "fn.fc_delta(K=3)+lif (edge_pos_lif)", w,
+                     launch_edge_pos_lif_fast(xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias, k.fc_delta.scale,
+                                              k.fc_delta.shift, k.snn_delta.np, 4, Xb, lt ? k.snn_delta.tab : nullptr,
+                                              lt ? k.snn_delta.tab_stride : 0, st));
+        }
+        SAPCU_TRY(g.L("fn.fc_delta2+lif").run(a, A_PLAIN));
+        Layer Lw = k.fc_gamma;
+        Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;
+        SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV, 3 * D, P, p.E3, 2 * D, ACT_NONE));
+        SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV + D, 3 * D, P, p.E3 + D, 2 * D, ACT_NONE));
+        SAPCU_TRY(g.L("fn.fc_gamma+edge_bias+lif").run(a1, A_PLAIN));
+        SAPCU_TRY(g.L("fn.fc_gamma2+softmax+sum(attention tail)").run(a2, A_PLAIN));
+        SAPCU_TRY(g.L("fn.out_proj").layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
+        SAPCU_TRY(g.L("fn.fc2+residual").layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
+        continue;
+      }
+    }
     if (mode != SAPCU_MODE_FP32) {
       // fc_delta2 on the pos-enc layer-1 spikes.  When it runs on the fp16x3 path, edge_pos_lif hands the spikes over as
       // fp16 (hi, lo) planes of x * 2^13 (same bytes as fp32) and the contraction loads them without converting.
@@ -316,9 +358,11 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
   // When conv5 runs on the fp16x3 path the spike tensor is stored as fp16 (hi, lo) planes of s * 2^13 (rows = point*T + t)
   // that it loads without converting; the step-0 spikes, which the graphs and EdgeConvs of the next block read, are
   // also kept in fp32 (SPK0, [P, 960]).
-  const bool spk_h2 = pooled && spk_planes && gemm_tc2_fp16x3(c5);
-  g_tap_spk_h2 = spk_h2 ? 1 : 0;
-  const int64_t plane = P * T * 960;
+  bool spk_fast = false;
+  if (mode == SAPCU_MODE_FAST && pooled && spk_planes) { c5.fast = true; spk_fast = gemm_tc2_fast(c5); c5.fast = spk_fast; }
+  const bool spk_h2 = pooled && spk_planes && (spk_fast || gemm_tc2_fp16x3(c5));
+  g_tap_spk_h2 = spk_fast ? 2 : (spk_h2 ? 1 : 0);
+  const int64_t plane = spk_fast ? 0 : P * T * 960;         // fast mode: hi plane only
   const float* S0 = spk_h2 ? p.SPK0 : p.SPK;                     // step-0 spikes: row stride ld0
   const int64_t ld0 = spk_h2 ? 960 : ldspk;
   if (spk_h2) SAPCU_TRY(launch_neuron_unroll(true, precise, p.U0, 64, P, 64, T, f.blk[0].np, f.blk[0].ep, 1, p.SPK, 960, st, true, p.SPK0, plane, 0));

@@ -47,6 +47,9 @@ struct GemmArgs {
   // fp16 (hi, lo) plane format of x * 2^13 ([R, K] halfs each, hi plane first): x_h2 = A is stored that way (consumed by the
   // fp16x3 kernel without conversion), out_h2 = the LIF epilogue writes Y that way; both need ld == row length
   bool x_h2 = false, out_h2 = false, pos_h2 = false;   // pos_h2: at_pos (fused attention tail) is stored as planes
+  // SAPCU_MODE_FAST (2-CTA tensor-core engine): ONE fp16 product per MAC; x_h2 / out_h2 / pos_h2 then mean a single fp16 plane
+  // of x * 2^13; lif_tab: tabulated LIF^T chain of the epilogue's neuron (nullptr: reduced-MUFU recurrence)
+  bool fast = false; const float* lif_tab = nullptr; uint32_t lif_tab_stride = 0;
   bool edge_bias = false;   // tensor-core engines, A_PLAIN: add Q[pt,c] - Kf[nb,c] (per-point products) to the accumulator, see tc_ptx.cuh
   int group = 0;   // 0 or 32
   const char* label = "gemm";   // kernel label of the live profiler (sapcu_profile_report)

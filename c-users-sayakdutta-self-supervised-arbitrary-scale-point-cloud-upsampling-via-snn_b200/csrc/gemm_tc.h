@@ -15,4 +15,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st);
 // true when launch_gemm_tc2 would run this problem on the fp16x3 operand path (needed to agree on the fp16-plane
 // activation format between the kernel that writes a tensor and the one that reads it)
 bool gemm_tc2_fp16x3(const GemmArgs& g);
+// true when launch_gemm_tc2 would run this problem on the single-product fp16 path of SAPCU_MODE_FAST (input and, for LIF
+// layers, output are single fp16 planes of x * 2^13)
+bool gemm_tc2_fast(const GemmArgs& g);
 }  // namespace sapcu

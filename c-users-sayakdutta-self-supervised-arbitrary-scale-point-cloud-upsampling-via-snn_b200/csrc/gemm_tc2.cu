@@ -23,6 +23,7 @@
 #include "gemm_tc.h"
 #include "neuron.cuh"
 #include "tc_ptx.cuh"
+#include "lif_table.cuh"
 
 namespace sapcu {
 
@@ -80,7 +81,11 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives
 // splitter turns the raw fp32 activation tile into fp16 (hi, lo) of x * x_scale, and 12 kind::f16 MMAs per 64-wide
 // k-block (hi*hi + hi*lo + lo*hi, fp32 accumulate) replace 24 kind::tf32 ones: the same 22-bit products at twice the
 // tensor-pipe rate and 2/3 of the operand bytes.  Stage = W_hi, W_lo, X_hi, X_lo (16 KiB each) + 32 KiB raw X; 2 stages.
-template <int ACT, int EXTRA, int KK, int HM = 0>
+// HM == 3 (SAPCU_MODE_FAST): ONE fp16 product per MAC.  W = the hi half of the fp16 split, activations = a single fp16 plane of
+// x * 2^13 written by the producing epilogue: two TMA loads and 4 kind::f16 MMAs per 64-wide k-block, 32 KiB per stage.
+// LT (with ACT_LIF): the LIF^T chain of the epilogue is read from the per-channel piecewise-cubic table (lif_table.cuh) that
+// the epilogue warps copy into shared memory once per CTA (a CTA pair keeps its channel block for its whole life).
+template <int ACT, int EXTRA, int KK, int HM = 0, int LT = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((T2_EPI_WARP0 + T2_EPI) * 32, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                 const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2, const TcParams p) {
@@ -88,8 +93,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   // stored as fp16 (hi, lo) planes of x * 2^13 by the kernel that produced them (map_x = hi plane, map_x2 = lo plane): four
   // TMA loads per stage, no conversion, no raw staging -- a third less shared-memory traffic per k-block
   constexpr bool H16 = HM != 0;
-  constexpr int T2_STAGES = HM == 1 ? 2 : 3;
-  constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : 4) * TC_TILE_BYTES;
+  constexpr int T2_STAGES = HM == 1 ? 2 : (HM == 3 && !LT) ? 4 : 3;
+  constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : HM == 3 ? 2 : 4) * TC_TILE_BYTES;
+  constexpr uint32_t X_TILE = HM == 3 ? 1 : 2;              // position of the activation (hi) tile inside a stage
   constexpr int BKE = H16 ? 64 : TC_BK;                    // k elements per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -149,7 +155,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
-          if (HM == 2) {
+          if (HM == 3) {
+            mbar_expect_tx(bar_raw(s), 2 * TC_TILE_BYTES);
+            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // two fp16 tiles: 64 halfs x 128 rows
+            tma_load_2d(st + TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
+          } else if (HM == 2) {
             mbar_expect_tx(bar_raw(s), 4 * TC_TILE_BYTES);
             tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // four fp16 tiles: 64 halfs x 128 rows
             tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * BKE, wrow);
@@ -184,8 +194,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           tc_fence_after();
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
           const uint64_t w_hi = umma_desc_sw128(st), w_lo = umma_desc_sw128(st + TC_TILE_BYTES);
-          const uint64_t x_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
-          if (H16) {
+          const uint64_t x_hi = umma_desc_sw128(st + X_TILE * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+          if (HM == 3) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16_2cta(tmem_d, w_hi + (uint64_t)(ks * 2), x_hi + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
+          } else if (H16) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {                       // 16 halfs = 32 B = 2 x 16 B along the swizzled row
               const uint64_t adv = (uint64_t)(ks * 2);
@@ -220,7 +234,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
       for (int kb = 0; kb < nk; ++kb) {
         if (!(ok = mbar_wait(bar_raw(s), ph, p.err))) break;
         uint8_t* st = smem_gen + s * T2_STAGE_BYTES;
-        if (HM == 2) {                                            // operands arrive ready-made: forward the arrival
+        if (HM >= 2) {                                            // operands arrive ready-made: forward the arrival
           if (rank == 0) mbar_arrive(bar_split(s)); else mbar_arrive_cluster(bar_split(s), 0);
           if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
           continue;
@@ -283,6 +297,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     constexpr int CHUNKS = (T2_BN / 32) / (T2_EPI / 4);
     const int part = (warp - T2_EPI_WARP0) >> 2;
     int a = 0; uint32_t aph = 0; bool ok = true;
+    // LT: this CTA's 128-channel block of the tabulated LIF^T chain -> shared memory (behind the barriers), once
+    const uint16_t* lt_desc = nullptr; const float4* lt_coef = nullptr;
+    if (LT) {
+      const int blk = (int)(pair % p.m_tiles) * 2 + (int)rank;        // the host keeps npairs a multiple of m_tiles: fixed channel block
+      uint8_t* tsm = smem_gen + T2_STAGES * T2_STAGE_BYTES + 256;
+      const uint4* src = reinterpret_cast<const uint4*>(p.lif_tab + (size_t)blk * p.lif_tab_stride);
+      uint4* dst = reinterpret_cast<uint4*>(tsm);
+      for (uint32_t i = threadIdx.x - T2_EPI_WARP0 * 32; i < p.lif_tab_stride / 16; i += T2_EPI * 32) dst[i] = src[i];
+      asm volatile("bar.sync 1, %0;" ::"r"(T2_EPI * 32) : "memory");
+      lt_desc = reinterpret_cast<const uint16_t*>(tsm) + (q * 32 + lane) * LT_NCELL;
+      lt_coef = reinterpret_cast<const float4*>(tsm + LT_DESC_BYTES);
+    }
     for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
       const int m_t = (int)(t % p.m_tiles);
       const int64_t n_t = t / p.m_tiles;
@@ -307,7 +333,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             for (int i = (warp - T2_EPI_WARP0) * 32 + lane; i < TR * 4; i += T2_EPI * 32) {
               const int64_t row = row0 + (i >> 2);
               if (row >= p.R) continue;
-              if (p.pos_h2) prefetch_l2(reinterpret_cast<const __half*>(p.at_pos) + ((i & 2) ? p.R * (int64_t)p.N : 0) + row * p.N + cb + (i & 1) * 64);
+              if (p.pos_h2 == 2) { if (!(i & 2)) prefetch_l2(reinterpret_cast<const __half*>(p.at_pos) + row * p.N + cb + (i & 1) * 64); }
+              else if (p.pos_h2) prefetch_l2(reinterpret_cast<const __half*>(p.at_pos) + ((i & 2) ? p.R * (int64_t)p.N : 0) + row * p.N + cb + (i & 1) * 64);
               else prefetch_l2(p.at_pos + row * p.N + cb + (i & 3) * 32);
             }
           }
@@ -349,9 +376,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           if (nrows > 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j] + bia, sc, sh);
-            lif_chain_vec_fast<8>(u, np, p.T);
+            if (LT) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float sj;
+                if (!lif_table_eval(u[j], np.th0, lt_desc, lt_coef, sj)) sj = lif_chain<false>(u[j], np, p.T);   // |u - th0| >= 255
+                u[j] = sj;
+              }
+            } else if (HM == 3) lif_chain_vec_fast2<8>(u, np, p.T);
+            else lif_chain_vec_fast<8>(u, np, p.T);
             float* yp = p.Y + r0 * p.ldc + c;
-            if (p.out_h2) {                                       // fp16 (hi, lo) planes of y * 2^13 for a fp16x3 consumer
+            if (HM == 3 && p.out_h2 == 2) {                       // fast mode: ONE fp16 plane of y * 2^13
+              __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nrows) hp[(int64_t)j * p.ldc] = __float2half_rn(u[j] * 8192.0f);
+            } else if (p.out_h2) {                                // fp16 (hi, lo) planes of y * 2^13 for a fp16x3 consumer
               __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
               __half* lp = hp + p.R * p.ldc;
 #pragma unroll
@@ -502,31 +542,55 @@ bool gemm_tc2_fp16x3(const GemmArgs& g) {
          (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool) || g.act == ACT_NONE);
 }
 
-int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
-  SAPCU_REQUIRE(gemm_tc2_supported(g, A_PLAIN), "gemm_tc2: unsupported problem");
-  static bool attr_done = false;
-  if (!attr_done) {
+// SAPCU_MODE_FAST operands: one fp16 product per MAC on a single fp16 plane (the producer wrote x * 2^13 as halfs)
+bool gemm_tc2_fast(const GemmArgs& g) {
+  return g.fast && g.x_unit && g.Wh && g.K % 64 == 0 && !g.residual &&
+         (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool));
+}
+
+namespace {
+constexpr size_t t2_smem_fast(bool lt, uint32_t tab_stride) {
+  return (size_t)(lt ? 3 : 4) * 2 * TC_TILE_BYTES + 1024 + 256 + (lt ? tab_stride : 0);
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per device
+int t2_set_attrs() {
+  static bool done[64] = {};
+  int dev = 0;
+  SAPCU_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || done[dev]) return 0;
 #define SAPCU_T2_ATTR(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LIF, 2, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
-    SAPCU_T2_ATTR(ACT_NONE, 3, 12); SAPCU_T2_ATTR(ACT_NONE, 3, 18); SAPCU_T2_ATTR(ACT_NONE, 3, 24);
+  SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LIF, 2, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
+  SAPCU_T2_ATTR(ACT_NONE, 3, 12); SAPCU_T2_ATTR(ACT_NONE, 3, 18); SAPCU_T2_ATTR(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR
 #define SAPCU_T2_ATTR_H(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR_H(ACT_LIF, 0, 1); SAPCU_T2_ATTR_H(ACT_LIF, 2, 1); SAPCU_T2_ATTR_H(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_H(ACT_NONE, 0, 1);
-    SAPCU_T2_ATTR_H(ACT_NONE, 3, 12); SAPCU_T2_ATTR_H(ACT_NONE, 3, 18); SAPCU_T2_ATTR_H(ACT_NONE, 3, 24);
+  SAPCU_T2_ATTR_H(ACT_LIF, 0, 1); SAPCU_T2_ATTR_H(ACT_LIF, 2, 1); SAPCU_T2_ATTR_H(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_H(ACT_NONE, 0, 1);
+  SAPCU_T2_ATTR_H(ACT_NONE, 3, 12); SAPCU_T2_ATTR_H(ACT_NONE, 3, 18); SAPCU_T2_ATTR_H(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_H
 #define SAPCU_T2_ATTR_P(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
-    SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_LIF, 2, 1); SAPCU_T2_ATTR_P(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
+  SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_LIF, 2, 1); SAPCU_T2_ATTR_P(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_P
-    attr_done = true;
-  }
+#define SAPCU_T2_ATTR_F(A, X, KQ, LTQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 3, LTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_fast(LTQ != 0, LT_SMEM_BUDGET)))
+  SAPCU_T2_ATTR_F(ACT_LIF, 0, 1, 0); SAPCU_T2_ATTR_F(ACT_LIF, 0, 1, 1); SAPCU_T2_ATTR_F(ACT_LIF, 2, 1, 0); SAPCU_T2_ATTR_F(ACT_LIF, 2, 1, 1);
+  SAPCU_T2_ATTR_F(ACT_LEAKY, 4, 1, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 12, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 18, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 24, 0);
+#undef SAPCU_T2_ATTR_F
+  done[dev] = true;
+  return 0;
+}
+}  // namespace
+
+int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
+  SAPCU_REQUIRE(gemm_tc2_supported(g, A_PLAIN), "gemm_tc2: unsupported problem");
+  { const int rc = t2_set_attrs(); if (rc) return rc; }
   int* err = tc_err_flag();
   SAPCU_REQUIRE(err != nullptr, "gemm_tc2: cannot allocate the watchdog flag");
   static int l2pf = -1;
   if (l2pf < 0) { const char* f = getenv("SAPCU_TC_L2PF"); l2pf = f ? atoi(f) : 4; }
   const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : T2_BN;
-  const bool h16 = gemm_tc2_fp16x3(g);
+  const bool fast = gemm_tc2_fast(g);
+  SAPCU_REQUIRE(!fast || (g.x_h2 && g.lda == g.K && (!g.out_h2 || (g.act == ACT_LIF && g.ldc == g.N))), "gemm_tc2(fast): needs a single-plane fp16 input with lda == K");
+  const bool h16 = fast || gemm_tc2_fp16x3(g);
   const bool pre = h16 && g.x_h2;                            // activations already stored as fp16 (hi, lo) planes
-  SAPCU_REQUIRE(!g.x_h2 || (h16 && g.lda == g.K && (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool))), "gemm_tc2: fp16-plane input needs the fp16x3 path and lda == K");
+  SAPCU_REQUIRE(fast || !g.x_h2 || (h16 && g.lda == g.K && (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool))), "gemm_tc2: fp16-plane input needs the fp16x3 path and lda == K");
   SAPCU_REQUIRE(!g.out_h2 || (g.act == ACT_LIF && g.ldc == g.N), "gemm_tc2: fp16-plane output is a LIF epilogue with ldc == N");
   CUtensorMap mw, mwlo, mx, mx2;
   int rc = h16 ? tc_make_map_f16(&mw, g.Wh, g.N, g.K, 128) : tc_make_map(&mw, g.Whi, g.N, g.K, g.K, 128);
@@ -537,8 +601,9 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     const uint16_t* hp = reinterpret_cast<const uint16_t*>(g.A);
     rc = tc_make_map_f16(&mx, hp, g.R, g.K, T2_BN / 2);
     if (rc) return rc;
-    rc = tc_make_map_f16(&mx2, hp + g.R * g.K, g.R, g.K, T2_BN / 2);
+    rc = fast ? 0 : tc_make_map_f16(&mx2, hp + g.R * g.K, g.R, g.K, T2_BN / 2);
     if (rc) return rc;
+    if (fast) mx2 = mx;
   } else {
     rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, T2_BN / 2);
     if (rc) return rc;
@@ -552,10 +617,31 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
   p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   p.out_h2 = g.out_h2 ? 1 : 0; p.pos_h2 = g.pos_h2 ? 1 : 0;
+  p.lif_tab = nullptr; p.lif_tab_stride = 0;
   p.x_scale = h16 ? 8192.0f : 1.0f;                         // soft spikes lie in (0, 0.7): x * 2^13 < 2^13, residual * 2^13 >= fp16's normal range
   p.acc_scale = h16 ? g.winv / 8192.0f : 1.0f;
   const int64_t total = p.n_tiles * p.m_tiles;
   int pairs = (int)(total < kNumSMs / 2 ? total : kNumSMs / 2);
+  if (fast) {
+    // one fp16 product per MAC: map_w = the hi half of the fp16 weight split, map_x = the single activation plane
+    const bool lt = g.act == ACT_LIF && g.lif_tab != nullptr && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET;
+    if (lt) pairs = (pairs / p.m_tiles) * p.m_tiles;          // a pair keeps one channel block: its table is loaded once
+    SAPCU_REQUIRE(pairs >= 1, "gemm_tc2(fast): empty grid");
+    p.lif_tab = reinterpret_cast<const uint8_t*>(g.lif_tab); p.lif_tab_stride = g.lif_tab_stride;
+    p.out_h2 = g.out_h2 ? 2 : 0; p.pos_h2 = g.pos_h2 ? 2 : 0;
+    p.x_scale = 8192.0f; p.acc_scale = g.winv / 8192.0f;
+    const size_t smem = t2_smem_fast(lt, g.lif_tab_stride);
+    const int gridf = 2 * pairs;
+#define SAPCU_T2_LAUNCH_F(A, X, KQ, LTQ) gemm_tc2_kernel<A, X, KQ, 3, LTQ><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p)
+    if (g.at_pos) {
+      if (g.kk == 12) SAPCU_T2_LAUNCH_F(ACT_NONE, 3, 12, 0); else if (g.kk == 18) SAPCU_T2_LAUNCH_F(ACT_NONE, 3, 18, 0); else SAPCU_T2_LAUNCH_F(ACT_NONE, 3, 24, 0);
+    } else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH_F(ACT_LEAKY, 4, 1, 0);
+    else if (g.edge_bias) { if (lt) SAPCU_T2_LAUNCH_F(ACT_LIF, 2, 1, 1); else SAPCU_T2_LAUNCH_F(ACT_LIF, 2, 1, 0); }
+    else { if (lt) SAPCU_T2_LAUNCH_F(ACT_LIF, 0, 1, 1); else SAPCU_T2_LAUNCH_F(ACT_LIF, 0, 1, 0); }
+#undef SAPCU_T2_LAUNCH_F
+    SAPCU_LAUNCH_CHECK();
+    return 0;
+  }
   const int grid = 2 * pairs;
 #define SAPCU_T2_LAUNCH_H(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 1><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
 #define SAPCU_T2_LAUNCH_P(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 2><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)

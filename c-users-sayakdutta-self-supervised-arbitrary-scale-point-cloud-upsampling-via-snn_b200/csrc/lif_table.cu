@@ -144,23 +144,27 @@ void lif_table_build(const float* np4, int C, int T, LifTableHost* out) {
     LifTableBlock blk;
     blk.off_bytes = (out->image.size() + 255) / 256 * 256;
     uint32_t nseg = 0;
-    for (int cl = 0; cl < LT_CH && b * LT_CH + cl < C; ++cl) nseg += (uint32_t)tabs[which[b * LT_CH + cl]].coef.size();
+    std::map<int, uint32_t> first;                   // unique fit -> first segment inside this block
+    for (int cl = 0; cl < LT_CH && b * LT_CH + cl < C; ++cl) {
+      const int w = which[b * LT_CH + cl];
+      if (first.find(w) == first.end()) { first[w] = nseg; nseg += (uint32_t)tabs[w].coef.size(); }
+    }
     blk.nseg = nseg;
     blk.bytes = LT_DESC_BYTES + nseg * 16u;
     out->image.resize(blk.off_bytes + blk.bytes, 0);
     uint16_t* desc = reinterpret_cast<uint16_t*>(out->image.data() + blk.off_bytes);
     float* coef = reinterpret_cast<float*>(out->image.data() + blk.off_bytes + LT_DESC_BYTES);
-    uint32_t base = 0;
     for (int cl = 0; cl < LT_CH && b * LT_CH + cl < C; ++cl) {
-      const ChanTab& t = tabs[which[b * LT_CH + cl]];
+      const int w = which[b * LT_CH + cl];
+      const ChanTab& t = tabs[w];
       out->max_err = t.err > out->max_err ? t.err : out->max_err;
+      uint32_t base = first[w];
       for (int cell = 0; cell < LT_NCELL; ++cell) {
         if (base > 0x1FFFu) out->usable = false;
         desc[cl * LT_NCELL + cell] = (uint16_t)((t.k[cell] << 13) | (base & 0x1FFFu));
         base += 1u << t.k[cell];
       }
-      memcpy(coef, t.coef.data(), t.coef.size() * 16);
-      coef += t.coef.size() * 4;
+      memcpy(coef + 4 * (size_t)first[w], t.coef.data(), t.coef.size() * 16);
     }
     if (blk.bytes > LT_SMEM_BUDGET) out->usable = false;
     out->max_block_bytes = blk.bytes > out->max_block_bytes ? blk.bytes : out->max_block_bytes;

@@ -10,7 +10,8 @@
 // cell is split into 2^k equal segments, k in [0, 7] chosen per cell on the host so that the cubic (Chebyshev-node
 // interpolant of the exact fp64 chain) stays within LT_TOL of the exact chain.  The float bits of y give cell, segment and
 // the local coordinate without any transcendental:  cell = exponent(y), segment = top k mantissa bits, tau = y - floor_k(y).
-// |x| >= 2^LT_NB - 1 (never seen with sane BatchNorm statistics) takes the exact MUFU chain.
+// |x| >= 2^LT_NB - 1 = 255 (not seen behind a BatchNorm with sane statistics) takes the exact MUFU chain.  Channels of a
+// block with identical neuron parameters (every channel of a default-initialised layer) share their segments.
 //
 // Memory image of one 128-channel block (copied verbatim to shared memory by the kernels):
 //   uint16 desc[128][LT_NCELL]   (k << 13) | first segment of the cell (relative to the block's coefficient array)
@@ -22,7 +23,7 @@
 
 namespace sapcu {
 
-constexpr int LT_NB = 12;                    // binades per side: |x| < 4095
+constexpr int LT_NB = 8;                     // binades per side: |x| < 255
 constexpr int LT_NCELL = 2 * LT_NB;
 constexpr int LT_KMAX = 7;                   // up to 128 segments per cell
 constexpr int LT_CH = 128;                   // channels per block (= UMMA M per CTA)
@@ -51,7 +52,7 @@ __device__ __forceinline__ bool lif_table_eval(float u, float th0, const uint16_
                                                const float4* __restrict__ coef, float& s) {
   const float x = u - th0;
   const float y = fabsf(x) + 1.0f;
-  if (!(y < 4096.0f)) return false;                                    // also NaN
+  if (!(y < 256.0f)) return false;                                       // also NaN
   const uint32_t yb = __float_as_uint(y);
   const uint32_t cell = (yb >> 23) - 127u + (__float_as_uint(x) >> 31) * (uint32_t)LT_NB;
   const uint32_t d = desc_c[cell];

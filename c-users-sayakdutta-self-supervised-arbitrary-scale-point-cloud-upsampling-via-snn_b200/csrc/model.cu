@@ -10,6 +10,7 @@
 #include <string.h>
 #include "../../include/sapcu_b200.h"
 #include "model.h"
+#include "lif_table.cuh"
 
 using namespace sapcu;
 
@@ -139,7 +140,8 @@ struct Builder {
   }
   static float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
   // neuron parameter block(s) concatenated along the channel axis: np = [4][C_total]
-  void neuron(Neuron& nr, const std::vector<std::string>& names, int C_each, bool eif) {
+  // tab_T > 0: also tabulate the T-step chain from the zero state (LIF only) for the fast mode
+  void neuron(Neuron& nr, const std::vector<std::string>& names, int C_each, bool eif, int tab_T = 0) {
     const int n = (int)names.size(), C = C_each * n;
     nr.C = C;
     std::vector<float> np(4 * (size_t)C), ep(2 * (size_t)C);
@@ -166,6 +168,17 @@ struct Builder {
     if (!ok) return;
     put(np.data(), np.size(), &nr.np);
     if (eif) put(ep.data(), ep.size(), &nr.ep);
+    if (tab_T > 0 && !eif) {
+      LifTableHost t;
+      lif_table_build(np.data(), C, tab_T, &t);
+      // re-pack with one fixed stride per block so a kernel finds its block from (base, stride, block index) alone
+      const uint32_t stride = (t.max_block_bytes + 255u) / 256u * 256u;
+      std::vector<float> img((size_t)stride / 4 * t.blocks.size(), 0.0f);
+      for (size_t b = 0; b < t.blocks.size(); ++b)
+        memcpy(reinterpret_cast<uint8_t*>(img.data()) + b * stride, t.image.data() + t.blocks[b].off_bytes, t.blocks[b].bytes);
+      put(img.data(), img.size(), &nr.tab);
+      nr.tab_stride = stride; nr.tab_T = tab_T; nr.tab_ok = t.usable; nr.tab_err = (float)t.max_err;
+    }
   }
   void raw(const std::string& name, size_t n, const float** dst) {
     if (auto* v = get(name, n)) put(v->data(), n, dst);
@@ -177,7 +190,7 @@ void build_fn(Builder& B) {
   const auto& c = B.m->cfg;
   f.kvals[0] = c[0]; f.kvals[1] = c[1]; f.kvals[2] = c[2]; f.emb = c[3]; f.T_enc = c[4]; f.heads = c[5];
   B.layer(f.conv1, "encoder.conv1.0", "encoder.conv1.1", 64, 3, true);
-  B.neuron(f.snn_init, {"encoder.snn_init"}, 64, false);
+  B.neuron(f.snn_init, {"encoder.snn_init"}, 64, false, f.T_enc);
   const int Ds[3] = {128, 256, 512};
   for (int b = 0; b < 3; ++b) {
     FnBlock& k = f.blk[b];
@@ -185,22 +198,22 @@ void build_fn(Builder& B) {
     const int D = k.D;
     const std::string p = "encoder.trans" + std::to_string(b + 1) + ".";
     B.layer(k.fc1, p + "fc1.0", p + "fc1.1", D, 64, true);
-    B.neuron(k.snn1, {p + "snn1"}, D, false);
+    B.neuron(k.snn1, {p + "snn1"}, D, false, 4);
     // q, k, v share their input: one [3D, D] contraction with concatenated weights / BN / neuron rows
     B.layer_cat(k.qkv, {p + "w_qs", p + "w_ks", p + "w_vs"}, D, D);
-    B.neuron(k.snn_qkv, {p + "snn_q", p + "snn_k", p + "snn_v"}, D, false);
+    B.neuron(k.snn_qkv, {p + "snn_q", p + "snn_k", p + "snn_v"}, D, false, 4);
     B.layer(k.fc_delta, p + "fc_delta.0", p + "fc_delta.1", D, 3, true);
-    B.neuron(k.snn_delta, {p + "snn_delta"}, D, false);
+    B.neuron(k.snn_delta, {p + "snn_delta"}, D, false, 4);
     B.layer(k.fc_delta2, p + "fc_delta2.0", p + "fc_delta2.1", D, D, true);
-    B.neuron(k.snn_delta2, {p + "snn_delta2"}, D, false);
+    B.neuron(k.snn_delta2, {p + "snn_delta2"}, D, false, 4);
     B.layer(k.fc_gamma, p + "fc_gamma.0", p + "fc_gamma.1", D, D, true);
-    B.neuron(k.snn_gamma, {p + "snn_gamma"}, D, false);
+    B.neuron(k.snn_gamma, {p + "snn_gamma"}, D, false, 4);
     B.layer(k.fc_gamma2, p + "fc_gamma2.0", p + "fc_gamma2.1", D, D, true);
     B.layer(k.out_proj, p + "out_proj.0", p + "out_proj.1", D, D, true);
     B.layer(k.fc2, p + "fc2.0", p + "fc2.1", 64, D, true);
   }
   B.layer(f.conv_final, "encoder.conv_final.0", "encoder.conv_final.1", f.emb, 192, true);
-  B.neuron(f.snn_final, {"encoder.snn_final"}, f.emb, false);
+  B.neuron(f.snn_final, {"encoder.snn_final"}, f.emb, false, f.T_enc);
   B.layer(f.fc_out, "encoder.fc_out", "", 2048, f.emb, true);
   B.layer(f.mlp[0], "decoder.mlp.0", "decoder.mlp.1", 1024, 2048, true);
   B.layer(f.mlp[1], "decoder.mlp.4", "decoder.mlp.5", 512, 1024, true);

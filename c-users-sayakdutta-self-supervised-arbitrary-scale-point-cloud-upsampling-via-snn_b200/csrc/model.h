@@ -18,6 +18,8 @@ struct Layer {     // 1x1 conv / Linear (+ folded eval BatchNorm):  y = (x W^T +
 };
 struct Neuron {    // clamped per-channel parameters: np = [4][C] (d, a, r, th0); ep = [2][C] (dT, th_rh) for EIF
   const float* np = nullptr; const float* ep = nullptr; int C = 0;
+  // SAPCU_MODE_FAST: tabulated LIF^T chain (lif_table.cuh), one image of `tab_stride` bytes per 128-channel block
+  const float* tab = nullptr; uint32_t tab_stride = 0; int tab_T = 0; bool tab_ok = false; float tab_err = 0.0f;
 };
 
 struct FnBlock {

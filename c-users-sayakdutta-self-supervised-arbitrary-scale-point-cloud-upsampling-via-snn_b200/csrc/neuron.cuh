@@ -225,6 +225,45 @@ __device__ __forceinline__ void lif_chain_vec_fast(float (&u)[NV], const NeuronP
   }
 }
 
+// SAPCU_MODE_FAST flavour of lif_chain_vec_fast: 0.5*sigmoid(10v) = 0.25 + 0.25*tanh(5v) with MUFU.TANH (tanh.approx.f32,
+// relative error 2^-11) -- 2 MUFU operations per element-step instead of 3, 11 FP instead of 12.  Deviation from the exact
+// chain <= 1.5e-4 absolute per step (reported with the fast mode's other deviations).
+__device__ __forceinline__ float tanh_approx_ord(float x) {
+  float y;
+  asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int NV>
+__device__ __forceinline__ void lif_chain_vec_fast2(float (&u)[NV], const NeuronParams& p, int T) {
+  float m[NV], th[NV], rho[NV];
+  const float c_g = 0.5f / 2.5066282746310002f, k_g = -0.5f * 1.4426950408889634f;
+  const float a95 = 0.95f * p.a, c05 = 0.05f * p.th0;
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    float mm[NV], g[NV], e[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (t == 0) { mm[i] = u[i]; th[i] = p.th0; rho[i] = 0.0f; }
+      else { const float md = m[i] * p.d; mm[i] = fmaf(-md, rho[i], md); }
+      const float v = mm[i] - th[i];
+      g[i] = (k_g * v) * v;
+      e[i] = 5.0f * v;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) e[i] = tanh_approx_ord(e[i]);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) g[i] = exp2f_approx_ord(g[i]);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float s = fmaf(c_g, g[i], fmaf(0.25f, e[i], 0.25f));
+      m[i] = fmaf(-mm[i], s, mm[i]);
+      rho[i] = fmaf(rho[i], p.r, s);
+      th[i] = fmaf(0.95f, th[i], fmaf(a95, s, c05));
+      u[i] = s;
+    }
+  }
+}
+
 // One re-associated step (fast-math flavour of neuron_step) for kernels that need every step's spike.
 // FIRST: the step from the zero state (m = 0, th = th0, rho = 0) with input u; later steps take no input
 // (closed refractory gate).  Derived constants are passed in `k`.

@@ -191,8 +191,10 @@ struct TcParams {
   // EXTRA == 4 (fd conv5, 2-CTA kernel): rows are (point*T + t); the epilogue keeps one running maximum per step and
   // merges them into pool[(patch*T + t), c] with float atomic max -- the [P*T, N] activation never reaches HBM
   float* pool; int pool_T; int64_t pool_rows;     // pool_rows = points per patch * T
-  int pos_h2;                 // EXTRA == 3: at_pos is stored as fp16 (hi, lo) planes of pos * 2^13 ([R, N] halfs each)
-  int out_h2;                 // LIF epilogue of the 2-CTA kernel: write Y as fp16 (hi, lo) planes of y * 2^13 (ldc == N, [R, N] each)
+  int pos_h2;                 // EXTRA == 3: at_pos is stored as fp16 (hi, lo) planes of pos * 2^13 ([R, N] halfs each); 2 = hi plane only (fast mode)
+  int out_h2;                 // LIF epilogue of the 2-CTA kernel: write Y as fp16 (hi, lo) planes of y * 2^13 (ldc == N, [R, N] each); 2 = hi plane only (fast mode)
+  // SAPCU_MODE_FAST, LIF epilogue: tabulated chain (lif_table.cuh): image of the 128-channel block b at lif_tab + b * lif_tab_stride
+  const uint8_t* lif_tab; uint32_t lif_tab_stride;
   float acc_scale, x_scale;   // fp16x3 path: operands are W * 2^e and x * x_scale, acc_scale = 2^-e / x_scale undoes both (exact)
   int tile_rows;              // rows a tile advances by: the MMA tile height, or the whole points inside it when EXTRA == 3
   int m_tiles; int64_t n_tiles;
@@ -255,7 +257,11 @@ __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tme
     float vr[KK], pr[KK];
 #pragma unroll
     for (int j = 0; j < KK; ++j) vr[j] = vc[(patch0 + (int64_t)((nbn[j >> 2] >> (8 * (j & 3))) & 255u)) * p.at_ldv];
-    if (p.pos_h2) {
+    if (p.pos_h2 == 2) {                                         // fast mode: one fp16 plane of pos * 2^13
+      const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * (int64_t)p.N + c;
+#pragma unroll
+      for (int j = 0; j < KK; ++j) pr[j] = __half2float(ph[(int64_t)j * p.N]) * (1.0f / 8192.0f);
+    } else if (p.pos_h2) {
       const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * (int64_t)p.N + c;
       const __half* pl = ph + p.R * (int64_t)p.N;
 #pragma unroll

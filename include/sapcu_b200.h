@@ -167,7 +167,8 @@ int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, in
                     int64_t* off_floats, int64_t* rows, int64_t* cols, int64_t* ld);
 /* Storage format the most recent forward used for a tap: 0 = fp32 [rows, ld]; 1 = two consecutive fp16 planes
  * [rows, cols] (hi, then lo) of x * 2^13, i.e. x = (hi + lo) / 8192 -- the hand-over format between an epilogue and the
- * fp16x3 contraction that consumes its spikes (MODE_TC, 'trans3.snn_gamma').  Negative: error code. */
+ * fp16x3 contraction that consumes its spikes (MODE_TC, 'trans3.snn_gamma'); 2 = ONE fp16 plane [rows, cols] of x * 2^13
+ * (MODE_FAST).  Negative: error code. */
 int sapcu_model_tap_format(const sapcu_model* m, const char* name);
 
 /* ------------------------------------------------------------------------------------
