@@ -257,7 +257,7 @@ def run_ours(args):
     L = sapcu_b200.lib()
     cfg = CONFIGS[args.config]
     mode = args.mode or cfg["mode"]
-    mfn, mfd, sd_fn, sd_fd = build_models(dev)
+    mfn, mfd, sd_fn, sd_fd = build_models(dev, stress=args.init == "stress")
     mfn.set_mode(mode), mfd.set_mode(mode)
     cloud, seeds, batch = workload(args.config, world)
     S_total = seeds.shape[0]
@@ -310,6 +310,7 @@ def run_ours(args):
     ms_total = float(t.item())
     value = S_total * args.steps / (ms_total / 1e3)
     assert out.shape == (S_total, 3) and bool(torch.isfinite(out).all())
+    N.check_device("bench")
 
     # ---- end to end through the public host API: every step copies the cloud and the rank's seeds from pinned host memory,
     # runs the pipeline, all-gathers, and copies the gathered [S,3] points back to the host (L2 flushed between steps)
@@ -366,7 +367,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": MODE_TEXT[mode][0], "data": "synthetic",
-            "config": {"workload": workload_text(args.config, mode, world, S_total), "mode": mode,
+            "config": {"workload": workload_text(args.config, mode, world, S_total) + (" [stress-init weights: per-channel neuron parameters spread over their clamp ranges]" if args.init == "stress" else ""), "mode": mode,
                        "seeds_total": S_total, "l2": "256 MiB flush buffer written between timed steps",
                        "collective": "one all-gather of [S,3] f64 per step" if world > 1 else "none"},
             "clocks": sampler.summary(),
@@ -402,6 +403,7 @@ def main():
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
     ap.add_argument("--mode", default=None, choices=["fp32", "tc", "tf32", "fast"])
     ap.add_argument("--seeds-per-pass", type=int, default=262144, help="device-side pass size for large seed sets")
+    ap.add_argument("--init", default="default", choices=["default", "stress"], help="weight init: the yaml random-init (default) or the parity suite's stress init")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     args = ap.parse_args()

@@ -89,6 +89,7 @@ _SIGS = {
     "sapcu_last_error": (ctypes.c_char_p, []),
     "sapcu_abi_version": (ctypes.c_int, []),
     "sapcu_launch_count": (ctypes.c_int64, []),
+    "sapcu_device_status": (ctypes.c_int, []),
     "sapcu_profile": (ctypes.c_int, [ctypes.c_int]),
     "sapcu_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_int64)]),
@@ -164,6 +165,11 @@ def check(rc, what=""):
     if rc != 0:
         msg = lib().sapcu_last_error()
         raise SapcuError("%s failed (%d): %s" % (what or "sapcu call", rc, msg.decode(errors="replace") if msg else ""))
+
+
+def check_device(what="device"):
+    """Raise if a tensor-core kernel's pipeline watchdog fired on the current device (call after a synchronise)."""
+    check(lib().sapcu_device_status(), what + " status")
 
 
 def ptr(t):

@@ -5,6 +5,7 @@
 #include <vector>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/sapcu_b200.h"
 #include "gemm_simt.cuh"
 #include "gemm_tc.h"
@@ -22,6 +23,41 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+const Settings& settings() {
+  static const Settings s = [] {
+    Settings t;
+    t.tc_2cta = env_int("SAPCU_TC_2CTA", 1) != 0;
+    t.fuse_attnout = env_int("SAPCU_TC_FUSE_ATTNOUT", 1) != 0;
+    t.factor_attnin = env_int("SAPCU_TC_FACTOR_ATTNIN", 1) != 0;
+    t.fuse_pool = env_int("SAPCU_TC_FUSE_POOL", 1) != 0;
+    t.fp16x3 = env_int("SAPCU_TC_FP16X3", 1) != 0;
+    t.spike_planes = env_int("SAPCU_TC_SPIKE_PLANES", 1) != 0;
+    t.fast_tables = env_int("SAPCU_FAST_LIF_TABLES", 1) != 0;
+    t.sync_check = env_int("SAPCU_TC_SYNC_CHECK", 0) != 0;
+    t.h2_planes = env_int("SAPCU_TC_H2_PLANES", 1);
+    t.l2pf = env_int("SAPCU_TC_L2PF", 4);
+    t.tc_bn = env_int("SAPCU_TC_BN", 256) == 128 ? 128 : 256;
+    t.tc_epi = env_int("SAPCU_TC_EPI", 16) == 8 ? 8 : 16;
+    t.tc_rawhi = env_int("SAPCU_TC_RAWHI", 1) != 0 ? 1 : 0;
+    return t;
+  }();
+  return s;
+}
+
+static_assert(sizeof(std::mutex) <= 64, "PerDeviceOnce::mu_ too small");
+int PerDeviceOnce::run(int (*f)()) {
+  static std::mutex init_mu;                       // guards the placement of the per-object mutex
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return -2; }
+  if (dev < 0 || dev >= 64) return f();
+  std::lock_guard<std::mutex> lk(init_mu);         // attribute setup is rare: one global lock is enough
+  if (done_[dev]) return 0;
+  const int rc = f();
+  if (rc == 0) done_[dev] = true;
+  return rc;
+}
 
 // ---- optional live timing of the contraction kernels (bench.py roofline)
 static std::mutex g_prof_mu;

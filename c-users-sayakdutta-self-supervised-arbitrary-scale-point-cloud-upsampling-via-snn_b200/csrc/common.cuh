@@ -58,6 +58,22 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;   // B200
 
+// Process-wide A/B switches (environment), read ONCE under C++11 static-initialisation locking and
+// immutable afterwards: concurrent forwards from several threads / streams all see the same values.
+struct Settings {
+  bool tc_2cta, fuse_attnout, factor_attnin, fuse_pool, fp16x3, spike_planes, fast_tables, sync_check;
+  int h2_planes, l2pf, tc_bn, tc_epi, tc_rawhi;
+};
+const Settings& settings();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: run `f` once per CUDA device (thread-safe)
+struct PerDeviceOnce {
+  int run(int (*f)());
+ private:
+  bool done_[64] = {};
+  char mu_[64] = {};     // storage for a std::mutex (kept opaque so this header stays light); see api.cu
+};
+
 // ---- activation codes shared by the GEMM epilogues
 enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_GELU = 2, ACT_LIF = 3 };
 

@@ -169,11 +169,14 @@ int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* i
   SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256, "edge_gather_unroll: M=%d outside [1,256]", Mpts);
   if (S == 0) return 0;
   const size_t smem = sizeof(float) * (size_t)Mpts * 128 + (((size_t)Mpts * kk + 15) & ~(size_t)15);
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_gather_unroll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_gather_unroll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_done = true;
+  static PerDeviceOnce once;
+  {
+    const int rc = once.run([]() -> int {
+      SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_gather_unroll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_gather_unroll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      return 0;
+    });
+    if (rc) return rc;
   }
   SAPCU_REQUIRE(smem <= 160 * 1024, "edge_gather_unroll: patch too large for shared memory");
   dim3 grid((unsigned)S, (unsigned)(C / 128));

@@ -137,13 +137,14 @@ edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ i
 // offsets are expanded into shared memory, and 4 threads per channel walk the edges (lane = channel, so a warp's 32 stores
 // of a row are 64 contiguous bytes).  LTAB = 0: no usable table -- the reduced-MUFU recurrence instead.
 constexpr int EPF_THREADS = 512;
-template <int LTAB>
+template <int LTAB, int CT>     // CT: compile-time channel count (row stride of the output: store offsets become immediates), 0 = run-time
 __global__ void __launch_bounds__(EPF_THREADS)
-edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts, int C,
+edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts, int C_rt,
                          int64_t S, const float* __restrict__ W, const float* __restrict__ bias,
                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ np,
                          int T, __half* __restrict__ out, const uint8_t* __restrict__ tab, uint32_t tab_stride) {
   extern __shared__ __align__(16) uint8_t epf_sm[];
+  const int C = CT ? CT : C_rt;
   const int EP = Mpts * kk;
   float4* pd = reinterpret_cast<float4*>(epf_sm);                               // [EP] edge offsets (w unused)
   float* xs = reinterpret_cast<float*>(epf_sm + (size_t)EP * 16);              // [Mpts][3]
@@ -158,13 +159,13 @@ edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restric
     uint4* dst = reinterpret_cast<uint4*>(tsm);
     for (uint32_t i = tid; i < tab_stride / 16; i += EPF_THREADS) dst[i] = src[i];
   }
-  const uint16_t* lt_desc = reinterpret_cast<const uint16_t*>(tsm) + cl * LT_NCELL;
+  const uint2* lt_desc = reinterpret_cast<const uint2*>(tsm) + cl;
   const float4* lt_coef = reinterpret_cast<const float4*>(tsm + LT_DESC_BYTES);
   // y = ((w.d + b) * sc + sh) folded into one affine map of the offset
   const float sc = scale[cc];
   const float w0 = W[3 * cc] * sc, w1 = W[3 * cc + 1] * sc, w2 = W[3 * cc + 2] * sc;
-  const float b0 = fmaf(bias[cc], sc, shift[cc]);
   const NeuronParams p{np[cc], np[C + cc], np[2 * C + cc], np[3 * C + cc]};
+  const float b0 = fmaf(bias[cc], sc, shift[cc]) - (LTAB ? p.th0 : 0.0f);     // table flavour: straight to x = u - theta0
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
     const int64_t patch0 = s * Mpts;
     __syncthreads();                                                           // previous patch fully consumed (and the table landed)
@@ -178,29 +179,35 @@ edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restric
     }
     __syncthreads();
     if (!cv) continue;
-    __half* o = out + patch0 * kk * (int64_t)C + c;
-#pragma unroll 1
-    for (int e0 = part * 4; e0 < EP; e0 += 16) {                               // 4 consecutive edges per thread and round
+    __half* o = out + patch0 * kk * (int64_t)C + c + (int64_t)(part * 4) * C;   // this thread's first row; rounds advance it by 16 rows
+    auto group = [&](int e0, bool full) {                                      // 4 consecutive edges of this thread's channel
       float u[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 d = pd[(e0 + j) < EP ? (e0 + j) : (EP - 1)];
+        const float4 d = pd[(full || (e0 + j) < EP) ? (e0 + j) : (EP - 1)];
         u[j] = fmaf(w2, d.z, fmaf(w1, d.y, fmaf(w0, d.x, b0)));
       }
       if (LTAB) {
+        float x0[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float sj;
-          if (!lif_table_eval(u[j], p.th0, lt_desc, lt_coef, sj)) sj = lif_chain<false>(u[j], p, T);
-          u[j] = sj;
+        for (int j = 0; j < 4; ++j) x0[j] = u[j];
+        const uint32_t oob = lif_table_eval_vec<4>(u, lt_desc, lt_coef);
+        if (oob) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (oob & (1u << j)) u[j] = lif_chain<false>(x0[j] + p.th0, p, T);
         }
       } else {
         lif_chain_vec_fast2<4>(u, p, T);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (e0 + j < EP) o[(int64_t)(e0 + j) * C] = __float2half_rn(u[j] * 8192.0f);
-    }
+        if (full || e0 + j < EP) o[j * C] = __float2half_rn(u[j] * 8192.0f);
+      o += 16 * C;
+    };
+    const int EPfull = EP & ~15;                                               // whole rounds of 4 phases x 4 edges: no bounds checks
+#pragma unroll 1
+    for (int e0 = part * 4; e0 < EPfull; e0 += 16) group(e0, true);
+    if (EPfull + part * 4 < EP) group(EPfull + part * 4, false);
   }
 }
 
@@ -375,26 +382,35 @@ int launch_edge_pos_lif_fast(const float* xyz, const int32_t* idx, int kk, int l
   const bool lt = tab != nullptr && tab_stride > 0 && tab_stride <= LT_SMEM_BUDGET;
   const size_t smem = (((size_t)Mpts * kk * 16 + (size_t)Mpts * 12 + 15) & ~(size_t)15) + (lt ? tab_stride : 0);
   SAPCU_REQUIRE(smem <= 220 * 1024, "edge_pos_lif_fast: patch of %d x %d edges does not fit shared memory", Mpts, kk);
-  static bool done[64] = {};
-  int dev = 0;
-  SAPCU_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !done[dev]) {
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    done[dev] = true;
+  static PerDeviceOnce once;
+  {
+    const int rc = once.run([]() -> int {
+#define SAPCU_EPF_ATTR(L, CQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<L, CQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024))
+      SAPCU_EPF_ATTR(0, 0); SAPCU_EPF_ATTR(1, 0); SAPCU_EPF_ATTR(0, 128); SAPCU_EPF_ATTR(1, 128); SAPCU_EPF_ATTR(0, 256); SAPCU_EPF_ATTR(1, 256);
+      SAPCU_EPF_ATTR(0, 512); SAPCU_EPF_ATTR(1, 512);
+#undef SAPCU_EPF_ATTR
+      return 0;
+    });
+    if (rc) return rc;
   }
   const int nblk = (int)ceil_div(C, 128);
-  int occ = 1;
-  if (lt) SAPCU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, edge_pos_lif_fast_kernel<1>, EPF_THREADS, smem));
-  else SAPCU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, edge_pos_lif_fast_kernel<0>, EPF_THREADS, smem));
-  if (occ < 1) occ = 1;
-  int64_t gx = ((int64_t)kNumSMs * occ + nblk - 1) / nblk;
-  if (gx > S) gx = S;
-  dim3 grid((unsigned)gx, (unsigned)nblk);
-  if (lt) edge_pos_lif_fast_kernel<1><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T,
-                                                                     reinterpret_cast<__half*>(out_h), reinterpret_cast<const uint8_t*>(tab), tab_stride);
-  else edge_pos_lif_fast_kernel<0><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T,
-                                                                  reinterpret_cast<__half*>(out_h), nullptr, 0);
+  const uint8_t* tabp = lt ? reinterpret_cast<const uint8_t*>(tab) : nullptr;
+  const uint32_t tstride = lt ? tab_stride : 0;
+  __half* outp = reinterpret_cast<__half*>(out_h);
+#define SAPCU_EPF_GO(L, CQ)                                                                                             \
+  do {                                                                                                                  \
+    int occ = 1;                                                                                                        \
+    SAPCU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, edge_pos_lif_fast_kernel<L, CQ>, EPF_THREADS, smem)); \
+    if (occ < 1) occ = 1;                                                                                               \
+    int64_t gx = ((int64_t)kNumSMs * occ + nblk - 1) / nblk;                                                            \
+    if (gx > S) gx = S;                                                                                                 \
+    dim3 grid((unsigned)gx, (unsigned)nblk);                                                                            \
+    edge_pos_lif_fast_kernel<L, CQ><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T, \
+                                                                     outp, tabp, tstride);                              \
+  } while (0)
+  if (lt) { if (C == 128) SAPCU_EPF_GO(1, 128); else if (C == 256) SAPCU_EPF_GO(1, 256); else if (C == 512) SAPCU_EPF_GO(1, 512); else SAPCU_EPF_GO(1, 0); }
+  else { if (C == 128) SAPCU_EPF_GO(0, 128); else if (C == 256) SAPCU_EPF_GO(0, 256); else if (C == 512) SAPCU_EPF_GO(0, 512); else SAPCU_EPF_GO(0, 0); }
+#undef SAPCU_EPF_GO
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

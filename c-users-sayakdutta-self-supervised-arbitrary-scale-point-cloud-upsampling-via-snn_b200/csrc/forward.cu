@@ -55,7 +55,7 @@ FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
 }
 
 struct FdPlan {
-  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *PQ, *SPK, *SPK0, *AGG, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
+  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *PQ, *SPK, *SPK0, *AGG, *EDGE, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
   size_t bytes; int k, kmax0;
 };
 FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
@@ -70,6 +70,8 @@ FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
   p.SPK = b.take<float>(P * f.T * 960);
   p.SPK0 = b.take<float>(P * 960);         // fp32 copy of the step-0 spikes when SPK holds fp16 planes (tensor-core modes)
   p.AGG = b.take<float>(P * f.T * f.emb);
+  // MODE_FP32 with a neighbour count other than 32 (the fused 32-row max of the SIMT engine): per-edge EdgeConv activations
+  p.EDGE = p.k != 32 ? b.take<float>(P * (int64_t)p.k * 512) : nullptr;
   p.POOL = b.take<float>(s * f.T * f.emb); p.Z = b.take<float>(s * f.emb);
   p.D0 = b.take<float>(s * 256); p.T1 = b.take<float>(s * 128); p.R = b.take<float>(s * 128);
   p.D1 = b.take<float>(s * 128); p.D2 = b.take<float>(s * 64); p.QKV = b.take<float>(s * 192);
@@ -125,13 +127,15 @@ struct G {
   }
 };
 
-// layout of the most recent fn forward's fc_gamma spikes of the last block (the 'trans3.snn_gamma' tap): 1 = fp16 (hi, lo)
-// planes of x * 2^13, 0 = fp32
-static int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0, g_tap_spk_h2 = 0;
+// The storage format of the tapped spike tensors (0 fp32, 1 fp16 (hi, lo) planes, 2 one fp16 plane) is recorded in the
+// handle by every forward (sapcu_model::tap_*): debug information for the parity tests, relaxed atomics.
 
 #define SAPCU_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
-int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals, const FnPlan& p, int mode, cudaStream_t st) {
+int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* normals, const FnPlan& p, int mode, cudaStream_t st) {
+  const FnNet& f = mdl->fn;
+  int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0;
+  struct TapPublish { const sapcu_model* m; int* g; int* d; ~TapPublish() { m->tap_gamma.store(*g, std::memory_order_relaxed); m->tap_delta2.store(*d, std::memory_order_relaxed); } } tap_publish{mdl, &g_tap_gamma_h2, &g_tap_delta2_h2};
   const int64_t P = s * M;
   const bool precise = mode == SAPCU_MODE_FP32;
   const G g{mode, st};
@@ -180,12 +184,12 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
                                      k.fc_delta.scale, k.fc_delta.shift, k.snn_delta.np, 4, out, s_, nsplit, h2));
     return 0;
   };
-  static const bool factorise = !(getenv("SAPCU_TC_FACTOR_ATTNIN") && atoi(getenv("SAPCU_TC_FACTOR_ATTNIN")) == 0);
-  static const bool use_tables = !(getenv("SAPCU_FAST_LIF_TABLES") && atoi(getenv("SAPCU_FAST_LIF_TABLES")) == 0);   // 0: reduced-MUFU chains (A/B)
+  const bool factorise = settings().factor_attnin;
+  const bool use_tables = settings().fast_tables;       // 0: reduced-MUFU chains (A/B)
   // fp16-plane hand-overs: 0 off; 1 (default) pos-enc layer 1 -> fc_delta2 and fc_gamma -> fc_gamma2; 2 / 3 only the first /
   // second; 4 only pos (fc_delta2 -> fc_gamma + attention tail); 5 all three.  The pos planes are measured slower (the
   // attention tail then issues two 2-byte loads per operand instead of one 4-byte load) and stay off.
-  static const int h2_env = getenv("SAPCU_TC_H2_PLANES") ? atoi(getenv("SAPCU_TC_H2_PLANES")) : 1;
+  const int h2_env = settings().h2_planes;
   const bool h2_delta = h2_env == 1 || h2_env == 2 || h2_env == 5, h2_gamma = h2_env == 1 || h2_env == 3 || h2_env == 5,
              h2_pos = h2_env == 4 || h2_env == 5;
   for (int b = 0; b < 3; ++b) {
@@ -323,8 +327,11 @@ int fn_chunk(const FnNet& f, const float* xyz, int64_t s, int M, float* normals,
   return 0;
 }
 
-int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, const int32_t* const forced[3],
+int fd_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* dist, const int32_t* const forced[3],
              const FdPlan& p, int mode, cudaStream_t st) {
+  const FdNet& f = mdl->fd;
+  int g_tap_spk_h2 = 0;
+  struct TapPublish { const sapcu_model* m; int* g; ~TapPublish() { m->tap_spk.store(*g, std::memory_order_relaxed); } } tap_publish{mdl, &g_tap_spk_h2};
   const int64_t P = s * M;
   const bool precise = mode == SAPCU_MODE_FP32;
   const G g{mode, st};
@@ -352,8 +359,7 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
     c5.Wh = L.Wh; c5.Wl = L.Wl; c5.winv = L.winv; c5.x_unit = true;                   // the spike tensor
     c5.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
   }
-  static const bool fuse_pool = !(getenv("SAPCU_TC_FUSE_POOL") && atoi(getenv("SAPCU_TC_FUSE_POOL")) == 0);
-  static const bool spk_planes = !(getenv("SAPCU_TC_SPIKE_PLANES") && atoi(getenv("SAPCU_TC_SPIKE_PLANES")) == 0);
+  const bool fuse_pool = settings().fuse_pool, spk_planes = settings().spike_planes;
   const bool pooled = mode != SAPCU_MODE_FP32 && fuse_pool && gemm_tc2_supported(c5, A_PLAIN);
   // When conv5 runs on the fp16x3 path the spike tensor is stored as fp16 (hi, lo) planes of s * 2^13 (rows = point*T + t)
   // that it loads without converting; the step-0 spikes, which the graphs and EdgeConvs of the next block read, are
@@ -393,6 +399,11 @@ int fd_chunk(const FdNet& f, const float* xyz, int64_t s, int M, float* dist, co
       a.F = p.SPK + off_in[b]; a.ldf = ldspk; a.C = cin[b];
       a.W = f.conv[b].W; a.N = cout[b]; a.scale = f.conv[b].scale; a.shift = f.conv[b].shift;
       a.act = ACT_LEAKY; a.group = 32; a.Y = U[b]; a.ldc = cout[b];
+      if (p.k != 32) {     // e.g. the constructor default k = 20, or patches of fewer than 32 points: max over k in a second pass
+        a.group = 0; a.Y = p.EDGE;
+        SAPCU_TRY(g.L("fd.edgeconv(per-edge)").run(a, A_EDGECAT));
+        SAPCU_TRY(launch_group_max(p.EDGE, P, p.k, 1, cout[b], U[b], st));
+      } else
       SAPCU_TRY(g.L("fd.edgeconv(per-edge)").run(a, A_EDGECAT));
     }
     SAPCU_TRY(launch_neuron_unroll(b == 0, precise, U[b], cout[b], P, cout[b], T, f.blk[b + 1].np, f.blk[b + 1].ep, 1,
@@ -462,7 +473,7 @@ int sapcu_fn_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
   for (int64_t s0 = 0; s0 < S; s0 += chunk) {
     const int64_t s = (S - s0) < chunk ? (S - s0) : chunk;
     const FnPlan p = fn_plan(m->fn, s, M, d_ws);
-    SAPCU_TRY(fn_chunk(m->fn, d_patches + s0 * M * 3, s, M, d_normals + s0 * 3, p, mode, st));
+    SAPCU_TRY(fn_chunk(m, d_patches + s0 * M * 3, s, M, d_normals + s0 * 3, p, mode, st));
   }
   if (mode != SAPCU_MODE_FP32) SAPCU_TRY(gemm_tc_check(st));
   return 0;
@@ -473,7 +484,6 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
   SAPCU_TRY(check_common(m, SAPCU_MODEL_FD, d_patches, S, M, d_dist, d_ws, mode));
   if (S == 0) return 0;
   const int k = m->fd.k < M ? m->fd.k : M;
-  SAPCU_REQUIRE(k == 32 || mode != SAPCU_MODE_FP32, "fd_forward(fp32): the fused EdgeConv max-pool is built for min(k, M) == 32 (got %d)", k);
   const int64_t chunk = pick_chunk(m, S, M, ws_bytes);
   if (chunk < 1) { set_error("fd_forward: workspace of %zu bytes cannot hold one patch (need %zu)", ws_bytes, sapcu_model_workspace_bytes(m, 1, M)); return SAPCU_EWORKSPACE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -483,17 +493,22 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
     const int32_t* forced[3] = {nullptr, nullptr, nullptr};
     if (d_forced_idx)
       for (int b = 0; b < 3; ++b) forced[b] = d_forced_idx + ((int64_t)b * S + s0) * M * k;
-    SAPCU_TRY(fd_chunk(m->fd, d_patches + s0 * M * 3, s, M, d_dist + s0, forced, p, mode, st));
+    SAPCU_TRY(fd_chunk(m, d_patches + s0 * M * 3, s, M, d_dist + s0, forced, p, mode, st));
   }
   if (mode != SAPCU_MODE_FP32) SAPCU_TRY(gemm_tc_check(st));
   return 0;
 }
 
+int sapcu_device_status(void) {
+  // watchdog flag of the current device, read from host-visible memory (no stream is touched): call after synchronising
+  return gemm_tc_check(nullptr) ? SAPCU_ECUDA : 0;
+}
+
 int sapcu_model_tap_format(const sapcu_model* m, const char* name) {
   SAPCU_REQUIRE(m && name, "model_tap_format: bad argument");
-  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_gamma") return g_tap_gamma_h2;
-  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_delta2") return g_tap_delta2_h2;
-  if (m->kind == SAPCU_MODEL_FD && std::string(name) == "spikes") return g_tap_spk_h2;
+  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_gamma") return m->tap_gamma.load(std::memory_order_relaxed);
+  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_delta2") return m->tap_delta2.load(std::memory_order_relaxed);
+  if (m->kind == SAPCU_MODEL_FD && std::string(name) == "spikes") return m->tap_spk.load(std::memory_order_relaxed);
   return 0;
 }
 

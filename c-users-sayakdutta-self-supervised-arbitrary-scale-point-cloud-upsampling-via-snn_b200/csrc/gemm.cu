@@ -24,6 +24,10 @@ int launch_gemm_simt(const GemmArgs& g, int amode, bool precise, cudaStream_t st
     SAPCU_REQUIRE(g.kk == 32 && (g.C % 8) == 0 && g.K == 2 * g.C, "gemm(edgecat): needs k=32, C%%8==0, K=2C");
     return launch_gemm_simt_t<A_EDGECAT, ACT_LEAKY, 32, true>(g, st);
   }
+  if (amode == A_EDGECAT && g.group == 0 && g.act == ACT_LEAKY) {      // any k: per-edge activations out, max over k by the caller
+    SAPCU_REQUIRE(g.kk >= 1 && (g.C % 8) == 0 && g.K == 2 * g.C, "gemm(edgecat): needs C%%8==0, K=2C");
+    return launch_gemm_simt_t<A_EDGECAT, ACT_LEAKY, 0, true>(g, st);
+  }
   if (amode == A_ATTNIN && g.group == 0 && g.act == ACT_LIF) SAPCU_G(A_ATTNIN, ACT_LIF, 0);
 #undef SAPCU_G
   set_error("gemm: unsupported combination amode=%d act=%d group=%d", amode, g.act, g.group);

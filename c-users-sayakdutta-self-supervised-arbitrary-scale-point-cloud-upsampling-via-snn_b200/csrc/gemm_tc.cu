@@ -32,6 +32,7 @@
 // element-step, 16/clk/SM) and overlaps the MMA stream.
 #include <cuda.h>
 #include <stdlib.h>
+#include <mutex>
 #include "gemm_tc.h"
 #include "neuron.cuh"
 #include "tc_ptx.cuh"
@@ -385,13 +386,25 @@ int tc_make_map_f16(CUtensorMap* m, const void* base, int64_t rows, int K, int b
   return 0;
 }
 
-int* tc_err_flag() {       // one device word per process, zero-initialised
-  static int* flag = nullptr;
-  if (!flag) {
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(flag, 0, sizeof(int));
+// Pipeline-watchdog flag of the CURRENT device: one word of mapped pinned host memory per device (kernels of that device
+// write it, the host reads it without touching any stream), allocated on first use.
+namespace {
+std::mutex g_flag_mu;
+int* g_flag_host[64] = {};
+int* g_flag_dev[64] = {};
+}
+int* tc_err_flag() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_flag_mu);
+  if (!g_flag_dev[dev]) {
+    int* h = nullptr; int* d = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    *h = 0;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) { cudaFreeHost(h); return nullptr; }
+    g_flag_host[dev] = h; g_flag_dev[dev] = d;
   }
-  return flag;
+  return g_flag_dev[dev];
 }
 
 bool gemm_tc_supported(const GemmArgs& g, int amode) {
@@ -414,8 +427,9 @@ bool gemm_tc_supported(const GemmArgs& g, int amode) {
 
 int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   SAPCU_REQUIRE(gemm_tc_supported(g, amode), "gemm_tc: unsupported problem");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  {
+    const int rc_attr = once.run([]() -> int {
 #define SAPCU_TC_ATTR1(A, RS, E, B) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<A, RS, E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES))
 #define SAPCU_TC_ATTR(A, RS) SAPCU_TC_ATTR1(A, RS, 8, 128); SAPCU_TC_ATTR1(A, RS, 8, 256); SAPCU_TC_ATTR1(A, RS, 16, 128); SAPCU_TC_ATTR1(A, RS, 16, 256)
     SAPCU_TC_ATTR(ACT_LIF, 0); SAPCU_TC_ATTR(ACT_LIF, 2); SAPCU_TC_ATTR(ACT_LEAKY, 0); SAPCU_TC_ATTR(ACT_GELU, 0); SAPCU_TC_ATTR(ACT_NONE, 1); SAPCU_TC_ATTR(ACT_NONE, 0);
@@ -424,21 +438,13 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
     SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE, 3, 16, 256, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
 #undef SAPCU_TC_ATTR
 #undef SAPCU_TC_ATTR1
-    attr_done = true;
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
   }
   int* err = tc_err_flag();
   SAPCU_REQUIRE(err != nullptr, "gemm_tc: cannot allocate the watchdog flag");
-  static int epi_warps = 0, raw_hi = 0, bn = 0, l2pf = 0;
-  if (!epi_warps) {
-    const char* e = getenv("SAPCU_TC_EPI");
-    epi_warps = (e && atoi(e) == 8) ? 8 : 16;
-    const char* r = getenv("SAPCU_TC_RAWHI");
-    raw_hi = (r && atoi(r) == 0) ? 0 : 1;
-    const char* b = getenv("SAPCU_TC_BN");
-    bn = (b && atoi(b) == 128) ? 128 : 256;
-    const char* f = getenv("SAPCU_TC_L2PF");
-    l2pf = f ? atoi(f) : 4;
-  }
+  const int epi_warps = settings().tc_epi, raw_hi = settings().tc_rawhi, bn = settings().tc_bn, l2pf = settings().l2pf;
   const bool presplit = g.Whi != nullptr && g.Wlo != nullptr;
   CUtensorMap mw, mwlo, mx;
   int rc = tc_make_map(&mw, presplit ? g.Whi : g.W, g.N, g.K, g.K, TC_BM);
@@ -483,14 +489,21 @@ int launch_gemm_tc(const GemmArgs& g, int amode, cudaStream_t st) {
   return 0;
 }
 
-// watchdog status (0 = fine); synchronises the stream
+// Watchdog status of the current device (0 = fine).  The flag is host-visible, so this never touches a stream unless
+// SAPCU_TC_SYNC_CHECK=1 asks for the old behaviour (synchronise `st` first: the check then covers the launches just
+// enqueued, at the price of serialising the caller).  Without it a stall of THIS call's kernels is reported by the next
+// entry point (or by sapcu_device_status after the caller synchronised).
 int gemm_tc_check(cudaStream_t st) {
-  int* err = tc_err_flag();
-  if (!err) return 0;
-  int h = 0;
-  SAPCU_CUDA_CHECK(cudaMemcpyAsync(&h, err, sizeof(int), cudaMemcpyDeviceToHost, st));
-  SAPCU_CUDA_CHECK(cudaStreamSynchronize(st));
-  if (h) { cudaMemset(err, 0, sizeof(int)); set_error("gemm_tc: pipeline watchdog fired (mbarrier protocol stall)"); return -2; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (settings().sync_check) SAPCU_CUDA_CHECK(cudaStreamSynchronize(st));
+  int* h;
+  { std::lock_guard<std::mutex> lk(g_flag_mu); h = g_flag_host[dev]; }
+  if (h && *reinterpret_cast<volatile int*>(h)) {
+    *reinterpret_cast<volatile int*>(h) = 0;
+    set_error("gemm_tc: pipeline watchdog fired (mbarrier protocol stall)");
+    return -2;
+  }
   return 0;
 }
 

@@ -298,7 +298,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     const int part = (warp - T2_EPI_WARP0) >> 2;
     int a = 0; uint32_t aph = 0; bool ok = true;
     // LT: this CTA's 128-channel block of the tabulated LIF^T chain -> shared memory (behind the barriers), once
-    const uint16_t* lt_desc = nullptr; const float4* lt_coef = nullptr;
+    const uint2* lt_desc = nullptr; const float4* lt_coef = nullptr;
     if (LT) {
       const int blk = (int)(pair % p.m_tiles) * 2 + (int)rank;        // the host keeps npairs a multiple of m_tiles: fixed channel block
       uint8_t* tsm = smem_gen + T2_STAGES * T2_STAGE_BYTES + 256;
@@ -306,7 +306,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
       uint4* dst = reinterpret_cast<uint4*>(tsm);
       for (uint32_t i = threadIdx.x - T2_EPI_WARP0 * 32; i < p.lif_tab_stride / 16; i += T2_EPI * 32) dst[i] = src[i];
       asm volatile("bar.sync 1, %0;" ::"r"(T2_EPI * 32) : "memory");
-      lt_desc = reinterpret_cast<const uint16_t*>(tsm) + (q * 32 + lane) * LT_NCELL;
+      lt_desc = reinterpret_cast<const uint2*>(tsm) + (q * 32 + lane);
       lt_coef = reinterpret_cast<const float4*>(tsm + LT_DESC_BYTES);
     }
     for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
@@ -374,23 +374,37 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             }
           }
           if (nrows > 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j] + bia, sc, sh);
             if (LT) {
+              // one multiply-add from the (scaled) accumulator straight to the table coordinate x = BN(acc + bias) - theta0
+              const float bx = fmaf(bia, sc, sh) - np.th0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float sj;
-                if (!lif_table_eval(u[j], np.th0, lt_desc, lt_coef, sj)) sj = lif_chain<false>(u[j], np, p.T);   // |u - th0| >= 255
-                u[j] = sj;
+              for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j], sc, bx);
+              float x0[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x0[j] = u[j];
+              const uint32_t oob = lif_table_eval_vec<8>(u, lt_desc, lt_coef);
+              if (oob) {                                          // |x| >= 255: the exact chain
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (oob & (1u << j)) u[j] = lif_chain<false>(x0[j] + np.th0, np, p.T);
               }
-            } else if (HM == 3) lif_chain_vec_fast2<8>(u, np, p.T);
-            else lif_chain_vec_fast<8>(u, np, p.T);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j] + bia, sc, sh);
+              if (HM == 3) lif_chain_vec_fast2<8>(u, np, p.T);
+              else lif_chain_vec_fast<8>(u, np, p.T);
+            }
             float* yp = p.Y + r0 * p.ldc + c;
             if (HM == 3 && p.out_h2 == 2) {                       // fast mode: ONE fp16 plane of y * 2^13
               __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
+              const uint32_t ld = (uint32_t)p.ldc;                 // one 64-bit multiply-add (IMAD.WIDE) per row address
+              if (nrows == 8) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (j < nrows) hp[(int64_t)j * p.ldc] = __float2half_rn(u[j] * 8192.0f);
+                for (int j = 0; j < 8; ++j) hp[(uint32_t)j * ld] = __float2half_rn(u[j] * 8192.0f);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j < nrows) hp[(uint32_t)j * ld] = __float2half_rn(u[j] * 8192.0f);
+              }
             } else if (p.out_h2) {                                // fp16 (hi, lo) planes of y * 2^13 for a fp16x3 consumer
               __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
               __half* lp = hp + p.R * p.ldc;
@@ -513,8 +527,7 @@ int launch_fill(float* p, int64_t n, float v, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------ host side
 bool gemm_tc2_supported(const GemmArgs& g, int amode) {
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("SAPCU_TC_2CTA"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool enabled = settings().tc_2cta;
   const bool fuse = tc_fuse_attn_out_enabled();
   GemmArgs base = g;
   base.at_pos = nullptr; base.pool = nullptr; base.x_h2 = false; base.out_h2 = false; base.pos_h2 = false;
@@ -536,9 +549,7 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
 // fp16x3 operands: only where the activations are LIF outputs, the weights carry their half split and the epilogue
 // flavour is instantiated
 bool gemm_tc2_fp16x3(const GemmArgs& g) {
-  static int h16_env = -1;
-  if (h16_env < 0) { const char* e = getenv("SAPCU_TC_FP16X3"); h16_env = (e && atoi(e) == 0) ? 0 : 1; }
-  return h16_env && g.x_unit && g.Wh && g.Wl && g.K % 64 == 0 && g.tc_passes != 1 && !g.residual &&
+  return settings().fp16x3 && g.x_unit && g.Wh && g.Wl && g.K % 64 == 0 && g.tc_passes != 1 && !g.residual &&
          (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool) || g.act == ACT_NONE);
 }
 
@@ -553,11 +564,7 @@ constexpr size_t t2_smem_fast(bool lt, uint32_t tab_stride) {
   return (size_t)(lt ? 3 : 4) * 2 * TC_TILE_BYTES + 1024 + 256 + (lt ? tab_stride : 0);
 }
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per device
-int t2_set_attrs() {
-  static bool done[64] = {};
-  int dev = 0;
-  SAPCU_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || done[dev]) return 0;
+int t2_set_attrs_impl() {
 #define SAPCU_T2_ATTR(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
   SAPCU_T2_ATTR(ACT_LIF, 0, 1); SAPCU_T2_ATTR(ACT_LIF, 2, 1); SAPCU_T2_ATTR(ACT_LEAKY, 0, 1); SAPCU_T2_ATTR(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR(ACT_NONE, 1, 1); SAPCU_T2_ATTR(ACT_NONE, 0, 1);
   SAPCU_T2_ATTR(ACT_NONE, 3, 12); SAPCU_T2_ATTR(ACT_NONE, 3, 18); SAPCU_T2_ATTR(ACT_NONE, 3, 24);
@@ -573,8 +580,11 @@ int t2_set_attrs() {
   SAPCU_T2_ATTR_F(ACT_LIF, 0, 1, 0); SAPCU_T2_ATTR_F(ACT_LIF, 0, 1, 1); SAPCU_T2_ATTR_F(ACT_LIF, 2, 1, 0); SAPCU_T2_ATTR_F(ACT_LIF, 2, 1, 1);
   SAPCU_T2_ATTR_F(ACT_LEAKY, 4, 1, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 12, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 18, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 24, 0);
 #undef SAPCU_T2_ATTR_F
-  done[dev] = true;
   return 0;
+}
+int t2_set_attrs() {
+  static PerDeviceOnce once;
+  return once.run(&t2_set_attrs_impl);
 }
 }  // namespace
 
@@ -583,8 +593,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   { const int rc = t2_set_attrs(); if (rc) return rc; }
   int* err = tc_err_flag();
   SAPCU_REQUIRE(err != nullptr, "gemm_tc2: cannot allocate the watchdog flag");
-  static int l2pf = -1;
-  if (l2pf < 0) { const char* f = getenv("SAPCU_TC_L2PF"); l2pf = f ? atoi(f) : 4; }
+  const int l2pf = settings().l2pf;
   const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : T2_BN;
   const bool fast = gemm_tc2_fast(g);
   SAPCU_REQUIRE(!fast || (g.x_h2 && g.lda == g.K && (!g.out_h2 || (g.act == ACT_LIF && g.ldc == g.N))), "gemm_tc2(fast): needs a single-plane fp16 input with lda == K");

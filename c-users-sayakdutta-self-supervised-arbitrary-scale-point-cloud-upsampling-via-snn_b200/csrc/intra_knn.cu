@@ -152,10 +152,13 @@ int launch_intra_knn(const float* feat, int64_t ld, int64_t S, int M, int C, int
   SAPCU_REQUIRE(((M + 3) / 4) * ((M + 3) / 4 + 1) / 2 <= IK_ROUNDS * IK_THREADS, "intra_knn: M too large");
   if (S == 0) return 0;
   const size_t smem = intra_knn_smem(M, C);
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAPCU_CUDA_CHECK(cudaFuncSetAttribute(intra_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_done = true;
+  static PerDeviceOnce once;
+  {
+    const int rc = once.run([]() -> int {
+      SAPCU_CUDA_CHECK(cudaFuncSetAttribute(intra_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      return 0;
+    });
+    if (rc) return rc;
   }
   intra_knn_kernel<<<(unsigned)S, IK_THREADS, smem, st>>>(feat, ld, M, C, k, idx);
   SAPCU_LAUNCH_CHECK();

@@ -147,12 +147,15 @@ void lif_table_build(const float* np4, int C, int T, LifTableHost* out) {
     std::map<int, uint32_t> first;                   // unique fit -> first segment inside this block
     for (int cl = 0; cl < LT_CH && b * LT_CH + cl < C; ++cl) {
       const int w = which[b * LT_CH + cl];
-      if (first.find(w) == first.end()) { first[w] = nseg; nseg += (uint32_t)tabs[w].coef.size(); }
+      if (first.find(w) == first.end()) {
+        nseg += ((uint32_t)(cl & 7) + 8u - (nseg & 7u)) & 7u;          // stagger: first segment congruent to the channel mod 8
+        first[w] = nseg; nseg += (uint32_t)tabs[w].coef.size();
+      }
     }
     blk.nseg = nseg;
     blk.bytes = LT_DESC_BYTES + nseg * 16u;
     out->image.resize(blk.off_bytes + blk.bytes, 0);
-    uint16_t* desc = reinterpret_cast<uint16_t*>(out->image.data() + blk.off_bytes);
+    uint32_t* desc = reinterpret_cast<uint32_t*>(out->image.data() + blk.off_bytes);
     float* coef = reinterpret_cast<float*>(out->image.data() + blk.off_bytes + LT_DESC_BYTES);
     for (int cl = 0; cl < LT_CH && b * LT_CH + cl < C; ++cl) {
       const int w = which[b * LT_CH + cl];
@@ -160,9 +163,11 @@ void lif_table_build(const float* np4, int C, int T, LifTableHost* out) {
       out->max_err = t.err > out->max_err ? t.err : out->max_err;
       uint32_t base = first[w];
       for (int cell = 0; cell < LT_NCELL; ++cell) {
-        if (base > 0x1FFFu) out->usable = false;
-        desc[cl * LT_NCELL + cell] = (uint16_t)((t.k[cell] << 13) | (base & 0x1FFFu));
-        base += 1u << t.k[cell];
+        // bits(y) >> (23 - k) = (E << k) + segment-in-cell with E = 127 + binade: fold -(E << k) into the byte offset
+        const int k = t.k[cell], E = 127 + cell % LT_NB;
+        desc[2 * (cell * LT_CH + cl)] = (uint32_t)(23 - k);
+        desc[2 * (cell * LT_CH + cl) + 1] = (uint32_t)(16 * ((int)base - (E << k)));
+        base += 1u << k;
       }
       memcpy(coef + 4 * (size_t)first[w], t.coef.data(), t.coef.size() * 16);
     }

@@ -2,6 +2,7 @@
 // of the fn / fd forwards.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -54,4 +55,6 @@ struct sapcu_model {
   size_t dev_floats = 0;
   sapcu::FnNet fn;
   sapcu::FdNet fd;
+  // storage format of the tapped spike tensors in the most recent forward on this handle (sapcu_model_tap_format)
+  mutable std::atomic<int> tap_gamma{0}, tap_delta2{0}, tap_spk{0};
 };

@@ -45,7 +45,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 1023) == 0) {
       if (*reinterpret_cast<volatile int*>(err) != 0) return false;
-      if (clock64() - t0 > TC_WATCHDOG_CLOCKS) { atomicExch(err, 1); return false; }
+      if (clock64() - t0 > TC_WATCHDOG_CLOCKS) { *reinterpret_cast<volatile int*>(err) = 1; __threadfence_system(); return false; }
     }
   }
   return true;
@@ -299,10 +299,6 @@ inline int tc_fused_tile_rows(int kk) {
   if (kk == 12 || kk == 18 || kk == 24) return (256 / kk) * kk;
   return 0;
 }
-inline bool tc_fuse_attn_out_enabled() {
-  static int fuse = -1;
-  if (fuse < 0) { const char* e = getenv("SAPCU_TC_FUSE_ATTNOUT"); fuse = (e && atoi(e) == 0) ? 0 : 1; }
-  return fuse == 1;
-}
+inline bool tc_fuse_attn_out_enabled() { return settings().fuse_attnout; }
 
 }  // namespace sapcu

@@ -104,6 +104,7 @@ class Generator3D6(object):
         with torch.cuda.device(self.device):
             h_out.copy_(d_out, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
+            N.check_device("displace_host")
         return h_out.numpy().copy()
 
     @torch.no_grad()

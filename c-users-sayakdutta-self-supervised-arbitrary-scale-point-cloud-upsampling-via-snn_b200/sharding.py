@@ -91,4 +91,6 @@ def upsample_sharded_host(generator, cloud, seeds, group=None, batch=None):
         h_out = generator._pinned("out_full", (S, 3), torch.float64)
         h_out.copy_(full, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
+        from . import _native as N
+        N.check_device("upsample_sharded_host")
     return h_out.numpy()

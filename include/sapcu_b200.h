@@ -56,6 +56,14 @@ int64_t     sapcu_launch_count(void);
 /* Live kernel timing for bench.py's roofline line: when enabled, every contraction launch (the dominant kernel
  * family) is bracketed by CUDA events on its launch stream.  sapcu_profile_read synchronises those events and
  * returns their summed duration, the algorithmic FLOPs (2*R*K*N per launch) and the launch count since enable. */
+/* Pipeline-watchdog status of the CURRENT CUDA device.  Every mbarrier wait of the tensor-core kernels carries a clock
+ * watchdog: a protocol stall makes the kernel exit and raises a host-visible flag instead of hanging the GPU.  The
+ * forwards poll that flag (no stream synchronisation) on entry and exit, so a stall is reported at the latest by the next
+ * call; after synchronising the stream the caller can ask directly: 0 = fine, SAPCU_ECUDA = a kernel stalled since the
+ * last query (results of the affected call are invalid).  SAPCU_TC_SYNC_CHECK=1 restores a synchronising check inside
+ * every forward. */
+int sapcu_device_status(void);
+
 int sapcu_profile(int enable);
 int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 /* Per-kernel report of the same recording as JSON text: [{"label", "launches", "ms", "flops", "lif_elsteps", "bytes"}, ...]
@@ -136,7 +144,10 @@ int sapcu_fps(const float* d_xyz, int64_t N, int64_t npoint, int64_t start, int3
  * state_dict (host fp32 pointers, names = state_dict keys).
  *   fn cfg ints : { k0, k1, k2, emb_dims, time_steps_enc, num_heads }
  *   fd cfg ints : { k, emb_dims, time_steps_enc, num_heads, n_scales, k_scale_0 .. }
- * After finalize the handle is immutable and may be used from several streams.
+ * After finalize the handle is immutable (weights, folded parameters, LIF tables) and may be used from several host
+ * threads / streams concurrently, each call with its own workspace; per-device kernel attributes and the watchdog flag are
+ * set up under a lock on first use of a device, the A/B environment switches are read once per process.  A handle's
+ * weights live on the CUDA device that was current at finalize.
  * ---------------------------------------------------------------------------------- */
 typedef struct sapcu_model sapcu_model;
 

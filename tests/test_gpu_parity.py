@@ -814,3 +814,75 @@ import test_gpu_parity as T
 cloud = syn.cloud(2048, seed=0, shape="sphere")
 print(json.dumps(T._fast_mode_measure((cloud, syn.seeds(cloud, 4, seed=1)))))
 """
+
+
+def test_concurrent_forwards_two_threads_two_streams(lib, sphere):
+    """include/sapcu_b200.h: a finalized handle is immutable and usable from several host threads / streams, each call with
+    its own workspace.  Two threads drive the SAME fn and fd handles on their own streams and workspaces, in different
+    arithmetic modes, several times; every result must be bit-identical to the single-threaded one."""
+    import threading
+    cloud, seeds = sphere
+    mfn, mfd, _, _ = _models(True)
+    B = 48
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx)).to(DEV)
+    hfn, hfd = mfn._ensure_handle(torch.device(DEV)), mfd._ensure_handle(torch.device(DEV))
+
+    def run(mode, stream, reps, out):
+        with torch.cuda.stream(stream):
+            ws_fn = torch.empty(lib.sapcu_model_workspace_bytes(hfn, B, 100), dtype=torch.uint8, device=DEV)
+            ws_fd = torch.empty(lib.sapcu_model_workspace_bytes(hfd, B, 100), dtype=torch.uint8, device=DEV)
+            for _ in range(reps):
+                n = torch.empty(B, 3, dtype=torch.float32, device=DEV)
+                d = torch.empty(B, dtype=torch.float32, device=DEV)
+                N.check(lib.sapcu_fn_forward(hfn, N.ptr(p), B, 100, N.ptr(n), N.ptr(ws_fn), ws_fn.numel(), mode, ctypes.c_void_p(stream.cuda_stream)))
+                N.check(lib.sapcu_fd_forward(hfd, N.ptr(p), B, 100, N.ptr(d), None, N.ptr(ws_fd), ws_fd.numel(), mode, ctypes.c_void_p(stream.cuda_stream)))
+                stream.synchronize()
+                out.append((n.cpu().numpy(), d.cpu().numpy()))
+
+    ref = {}
+    for mode in (N.MODE_TC, N.MODE_FAST):
+        o = []
+        run(mode, torch.cuda.Stream(device=DEV), 1, o)
+        ref[mode] = o[0]
+    outs = {N.MODE_TC: [], N.MODE_FAST: []}
+    errs = []
+
+    def worker(mode):
+        try:
+            torch.cuda.set_device(0)
+            run(mode, torch.cuda.Stream(device=DEV), 4, outs[mode])
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=worker, args=(m,)) for m in (N.MODE_TC, N.MODE_FAST)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    N.check_device("concurrent forwards")
+    for mode, res in outs.items():
+        assert len(res) == 4
+        for n, d in res:
+            assert np.array_equal(n, ref[mode][0]) and np.array_equal(d, ref[mode][1])
+
+
+def test_fd_fp32_any_neighbour_count(lib, sphere):
+    """MODE_FP32 (the shim's default mode) with the reference constructor's default k = 20 and with patches of fewer than 32
+    points: the EdgeConv max over k is no longer tied to 32-row groups."""
+    from sapcu_b200.fd.snn_coder import EnhancedSNNDistanceEstimation
+    cloud, seeds = sphere
+    m = EnhancedSNNDistanceEstimation()                     # k=20, emb 512, T=5, heads 4, k_scales (10, 20, 40): constructor defaults
+    syn.init_weights(m, seed=7, stress=True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    cfg = dict(k=20, time_steps_enc=5, k_scales=[10, 20, 40], num_heads=4)
+    m = m.to(DEV)
+    for M in (100, 24):
+        idx = oracle_c.knn(cloud, seeds[:6], M)
+        rng = np.random.default_rng(3)
+        p = torch.from_numpy(orc.gather_center(cloud, seeds[:6], idx, rng.normal(size=(6, 3)).astype(np.float32)))
+        taps = {}
+        with torch.no_grad():
+            ref = orc.fd_forward(sd, p, cfg, schedule="dce", taps=taps).numpy()
+        forced = torch.stack([gi.to(torch.int32) for gi in taps["graph_idx"]], 0)
+        got = m(p.to(DEV), forced_idx=forced).cpu().numpy()
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
+        assert rel.max() < 1e-3, (M, rel)
