@@ -113,6 +113,11 @@ _SIGS = {
     "sapcu_outlier_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
     "sapcu_outlier_mask": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "sapcu_knn_mean_dist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "sapcu_outlier_mask_from_means": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                     ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                     ctypes.c_void_p]),
     "sapcu_fps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "sapcu_model_create": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),

@@ -211,6 +211,28 @@ edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restric
   }
 }
 
+// byte-packed copy of a patch-local graph (indices < 256): word w of point pt holds neighbours 4w .. 4w+3
+__global__ void pack_idx_u8_kernel(const int32_t* __restrict__ idx, int ldi, int64_t P, int words, uint32_t* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= P * words) return;
+  const int64_t pt = e / words;
+  const int w = (int)(e - pt * words);
+  uint32_t v = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int j = 4 * w + b;
+    if (j < ldi) v |= ((uint32_t)idx[pt * ldi + j] & 255u) << (8 * b);
+  }
+  out[e] = v;
+}
+int launch_pack_idx_u8(const int32_t* idx, int ldi, int64_t P, uint32_t* out, cudaStream_t st) {
+  if (P == 0) return 0;
+  const int words = (ldi + 3) / 4;
+  pack_idx_u8_kernel<<<(unsigned)ceil_div(P * words, 256), 256, 0, st>>>(idx, ldi, P, words, out);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
 constexpr int ATT_KMAX = 32;
 
 // softmax over the k neighbours + weighted sum.  CTA = 128 channels x APB points; KK is the compile-time

@@ -30,7 +30,7 @@ struct Bump {
 };
 
 struct FnPlan {
-  int32_t* idx; float *F0, *FCAT, *X, *QKV, *E1, *E2, *E3, *RES, *R1, *G, *GM, *H0, *H1, *H2, *H3;
+  int32_t* idx; uint32_t* idx8; float *F0, *FCAT, *X, *QKV, *E1, *E2, *E3, *RES, *R1, *G, *GM, *H0, *H1, *H2, *H3;
   size_t bytes; int kmax; int Dl, kl;
 };
 FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
@@ -43,6 +43,7 @@ FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
     emax = (size_t)k * f.blk[i].D > emax ? (size_t)k * f.blk[i].D : emax;
   }
   p.idx = b.take<int32_t>(P * p.kmax);
+  p.idx8 = b.take<uint32_t>(P * ((p.kmax + 3) / 4));       // byte-packed copy of the graph for the fused attention tails
   p.F0 = b.take<float>(P * 64); p.FCAT = b.take<float>(P * 192);
   p.X = b.take<float>(P * 512); p.QKV = b.take<float>(P * 1536);
   p.E1 = b.take<float>(P * emax); p.E2 = b.take<float>(P * emax); p.E3 = b.take<float>(P * emax);
@@ -55,7 +56,7 @@ FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
 }
 
 struct FdPlan {
-  int32_t *idx0, *idxf; float *F0, *U0, *U1, *U2, *U3, *PQ, *SPK, *SPK0, *AGG, *EDGE, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
+  int32_t *idx0, *idxf[3]; float *F0, *U0, *U1, *U2, *U3, *PQ, *SPK, *SPK0, *AGG, *EDGE, *POOL, *Z, *D0, *T1, *R, *D1, *D2, *QKV, *O, *AO, *LN, *HH;
   size_t bytes; int k, kmax0;
 };
 FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
@@ -63,7 +64,8 @@ FdPlan fd_plan(const FdNet& f, int64_t s, int M, void* base) {
   const int64_t P = s * M;
   p.k = f.k < M ? f.k : M;
   p.kmax0 = f.kscales[f.nscales - 1] < M ? f.kscales[f.nscales - 1] : M;
-  p.idx0 = b.take<int32_t>(P * p.kmax0); p.idxf = b.take<int32_t>(P * p.k);
+  p.idx0 = b.take<int32_t>(P * p.kmax0);
+  for (int i = 0; i < 3; ++i) p.idxf[i] = b.take<int32_t>(P * p.k);     // the feature-space graph of every block stays available (parity taps)
   p.F0 = b.take<float>(P * 64 * f.nscales);
   p.U0 = b.take<float>(P * 64); p.U1 = b.take<float>(P * 128); p.U2 = b.take<float>(P * 256); p.U3 = b.take<float>(P * 512);
   p.PQ = b.take<float>(P * 1024);          // factorised EdgeConv (P | Q) rows, tensor-core mode
@@ -123,6 +125,10 @@ struct G {
     g.A = X; g.lda = lda; g.R = R; g.K = L.K; g.W = L.W; g.Whi = L.Whi; g.Wlo = L.Wlo; g.N = L.N; g.bias = L.bias; g.scale = L.scale; g.shift = L.shift;
     g.Wh = L.Wh; g.Wl = L.Wl; g.winv = L.winv; g.x_unit = x_unit;
     g.act = act; g.T = T; g.nparams = nr ? nr->np : nullptr; g.residual = res; g.ldr = ldr; g.Y = Y; g.ldc = ldc;
+    if (mode == SAPCU_MODE_FAST && act == ACT_LIF && nr) {     // point-level LIF layers: compact single-pass TF32 stages + the layer's LIF table
+      g.fast = true;
+      if (settings().fast_tables && nr->tab_ok && nr->tab_T == T) { g.lif_tab = nr->tab; g.lif_tab_stride = nr->tab_stride; }
+    }
     return run(g, A_PLAIN);
   }
 };
@@ -132,7 +138,7 @@ struct G {
 
 #define SAPCU_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
-int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* normals, const FnPlan& p, int mode, cudaStream_t st) {
+int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* normals, const FnPlan& p, int mode, int stop_block, cudaStream_t st) {
   const FnNet& f = mdl->fn;
   int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0;
   struct TapPublish { const sapcu_model* m; int* g; int* d; ~TapPublish() { m->tap_gamma.store(*g, std::memory_order_relaxed); m->tap_delta2.store(*d, std::memory_order_relaxed); } } tap_publish{mdl, &g_tap_gamma_h2, &g_tap_delta2_h2};
@@ -141,6 +147,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
   const G g{mode, st};
   { ProfWork w; w.flops = (double)s * M * M * 3; w.bytes = (double)P * (12 + 4.0 * p.kmax);
     SAPCU_PROF(st, "fn.intra_knn(xyz)", w, launch_intra_knn(xyz, 3, s, M, 3, p.kmax, p.idx, st)); }
+  if (mode != SAPCU_MODE_FP32 && M <= 256) SAPCU_TRY(launch_pack_idx_u8(p.idx, p.kmax, P, p.idx8, st));
   { ProfWork w; w.elsteps = (double)P * 64 * f.T_enc; w.bytes = (double)P * (12 + 256);
     SAPCU_PROF(st, "fn.conv1+lif", w, launch_pointwise3_lif(false, precise, xyz, nullptr, 0, 0, M, P, 64, f.conv1.W, f.conv1.bias, f.conv1.scale,
                                   f.conv1.shift, f.snn_init.np, f.T_enc, p.F0, st)); }
@@ -169,6 +176,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
     a.A = in; a.lda = D; a.R = P * kk; a.K = D; a.W = L.W; a.Whi = L.Whi; a.Wlo = L.Wlo; a.N = D;
     a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_NONE;
     a.idx = p.idx; a.ldi = p.kmax; a.kk = kk; a.Mpts = M;
+    a.idx8 = mode != SAPCU_MODE_FP32 ? p.idx8 : nullptr; a.ldi8w = (p.kmax + 3) / 4;
     a.at_pos = pos; a.at_v = p.QKV + 2 * D; a.at_ldv = 3 * D; a.at_sqrt = sqrtf((float)(D / f.heads));   // torch divides by the python scalar sqrt(head_dim)
     a.Y = p.RES; a.ldc = D;
     a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;                     // fc_gamma's LIF output
@@ -193,6 +201,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
   const bool h2_delta = h2_env == 1 || h2_env == 2 || h2_env == 5, h2_gamma = h2_env == 1 || h2_env == 3 || h2_env == 5,
              h2_pos = h2_env == 4 || h2_env == 5;
   for (int b = 0; b < 3; ++b) {
+    if (stop_block && b >= stop_block) return 0;            // debug: leave block `stop_block`'s intermediates in the workspace
     const FnBlock& k = f.blk[b];
     const int D = k.D, kk = k.k < M ? k.k : M;
     const float* fin = b == 0 ? p.F0 : p.FCAT + 64 * (b - 1);
@@ -223,7 +232,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
       const bool blk_fast = factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_fast(a) &&
                             gemm_tc2_supported(a1, A_PLAIN) && gemm_tc2_fast(a1) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fast(a2);
       if (blk_fast) {
-        if (b == 2) { g_tap_gamma_h2 = 2; g_tap_delta2_h2 = 2; }
+        g_tap_gamma_h2 = 2; g_tap_delta2_h2 = 2;
         {
           ProfWork w; w.elsteps = (double)E * D * 4; w.bytes = (double)E * D * 2.0;
           const bool lt = use_tables && k.snn_delta.tab_ok;
@@ -262,7 +271,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
                   gemm_tc2_fp16x3(a1) && gemm_tc2_supported(a2, A_PLAIN);
         }
         a.out_h2 = e2_h2;
-        if (b == 2) g_tap_delta2_h2 = e2_h2 ? 1 : 0;
+        g_tap_delta2_h2 = e2_h2 ? 1 : 0;
         SAPCU_TRY(edge_pos(b, Xb, st, 1, a.x_h2));
         SAPCU_TRY(g.L("fn.fc_delta2+lif").run(a, A_PLAIN));
       }
@@ -275,7 +284,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
           xb_h2 = h2_gamma && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fp16x3(a2);
         }
         a.out_h2 = xb_h2; a.x_h2 = e2_h2;
-        if (b == 2) g_tap_gamma_h2 = xb_h2 ? 1 : 0;
+        g_tap_gamma_h2 = xb_h2 ? 1 : 0;
         if (factorise && kk >= 2 && (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN))) {
           Layer Lw = k.fc_gamma;
           Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;
@@ -317,6 +326,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
     SAPCU_TRY(g.L("fn.out_proj").layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
     SAPCU_TRY(g.L("fn.fc2+residual").layer(k.fc2, p.R1, D, P, p.FCAT + 64 * b, 192, ACT_NONE, nullptr, 0, fin, ldin));
   }
+  if (stop_block) return 0;
   SAPCU_TRY(g.L("fn.conv_final+lif").layer(f.conv_final, p.FCAT, 192, P, p.G, f.emb, ACT_LIF, &f.snn_final, f.T_enc));
   SAPCU_TRY(launch_group_max(p.G, s, M, 1, f.emb, p.GM, st));
   SAPCU_TRY(g.L("fn.decoder").layer(f.fc_out, p.GM, f.emb, s, p.H0, 2048, ACT_NONE));
@@ -365,7 +375,7 @@ int fd_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
   // that it loads without converting; the step-0 spikes, which the graphs and EdgeConvs of the next block read, are
   // also kept in fp32 (SPK0, [P, 960]).
   bool spk_fast = false;
-  if (mode == SAPCU_MODE_FAST && pooled && spk_planes) { c5.fast = true; spk_fast = gemm_tc2_fast(c5); c5.fast = spk_fast; }
+  if (mode == SAPCU_MODE_FAST && pooled && spk_planes) { c5.fast = true; c5.x_h2 = true; spk_fast = gemm_tc2_fast(c5); c5.fast = spk_fast; c5.x_h2 = false; }
   const bool spk_h2 = pooled && spk_planes && (spk_fast || gemm_tc2_fp16x3(c5));
   g_tap_spk_h2 = spk_fast ? 2 : (spk_h2 ? 1 : 0);
   const int64_t plane = spk_fast ? 0 : P * T * 960;         // fast mode: hi plane only
@@ -380,8 +390,8 @@ int fd_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
     const int32_t* idx = forced[b];
     if (!idx) {
       ProfWork w; w.flops = (double)s * M * M * cin[b]; w.bytes = (double)P * (4.0 * cin[b] + 4.0 * p.k);
-      SAPCU_PROF(st, "fd.intra_knn(features)", w, launch_intra_knn(S0 + off_in[b], ld0, s, M, cin[b], p.k, p.idxf, st));
-      idx = p.idxf;
+      SAPCU_PROF(st, "fd.intra_knn(features)", w, launch_intra_knn(S0 + off_in[b], ld0, s, M, cin[b], p.k, p.idxf[b], st));
+      idx = p.idxf[b];
     }
     if (mode != SAPCU_MODE_FP32) {
       // factorised EdgeConv: one per-POINT contraction [P, Cin] x [2 Cout, Cin]^T, then gather / BN / LeakyReLU / max_k
@@ -447,7 +457,9 @@ int check_common(const sapcu_model* m, int kind, const float* patches, int64_t S
   if (!m->finalized) { set_error("forward: model not finalized"); return SAPCU_ESTATE; }
   SAPCU_REQUIRE(S >= 0 && M >= 1 && M <= 128, "forward: need S >= 0 and 1 <= M <= 128 (got S=%lld M=%d)", (long long)S, M);
   SAPCU_REQUIRE(S == 0 || (patches && out && ws), "forward: null pointer");
-  SAPCU_REQUIRE(mode == SAPCU_MODE_FP32 || mode == SAPCU_MODE_TC || mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST, "forward: unknown mode %d", mode);
+  const int amode = mode & 0xFF;
+  SAPCU_REQUIRE(amode == SAPCU_MODE_FP32 || amode == SAPCU_MODE_TC || amode == SAPCU_MODE_TF32 || amode == SAPCU_MODE_FAST, "forward: unknown mode %d", mode);
+  SAPCU_REQUIRE((mode >> 8) == 0 || (kind == SAPCU_MODEL_FN && (mode >> 8) <= 3), "forward: bad debug field in mode 0x%x", mode);
   return 0;
 }
 
@@ -473,9 +485,9 @@ int sapcu_fn_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
   for (int64_t s0 = 0; s0 < S; s0 += chunk) {
     const int64_t s = (S - s0) < chunk ? (S - s0) : chunk;
     const FnPlan p = fn_plan(m->fn, s, M, d_ws);
-    SAPCU_TRY(fn_chunk(m, d_patches + s0 * M * 3, s, M, d_normals + s0 * 3, p, mode, st));
+    SAPCU_TRY(fn_chunk(m, d_patches + s0 * M * 3, s, M, d_normals + s0 * 3, p, mode & 0xFF, mode >> 8, st));
   }
-  if (mode != SAPCU_MODE_FP32) SAPCU_TRY(gemm_tc_check(st));
+  if ((mode & 0xFF) != SAPCU_MODE_FP32) SAPCU_TRY(gemm_tc_check(st));
   return 0;
 }
 
@@ -506,8 +518,10 @@ int sapcu_device_status(void) {
 
 int sapcu_model_tap_format(const sapcu_model* m, const char* name) {
   SAPCU_REQUIRE(m && name, "model_tap_format: bad argument");
-  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_gamma") return m->tap_gamma.load(std::memory_order_relaxed);
-  if (m->kind == SAPCU_MODEL_FN && std::string(name) == "trans3.snn_delta2") return m->tap_delta2.load(std::memory_order_relaxed);
+  const std::string nm(name);
+  const bool blk = nm.size() > 7 && nm.compare(0, 5, "trans") == 0 && nm[6] == '.';     // format of the last block the forward executed
+  if (m->kind == SAPCU_MODEL_FN && blk && nm.substr(7) == "snn_gamma") return m->tap_gamma.load(std::memory_order_relaxed);
+  if (m->kind == SAPCU_MODEL_FN && blk && nm.substr(7) == "snn_delta2") return m->tap_delta2.load(std::memory_order_relaxed);
   if (m->kind == SAPCU_MODEL_FD && std::string(name) == "spikes") return m->tap_spk.load(std::memory_order_relaxed);
   return 0;
 }
@@ -522,20 +536,27 @@ int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, in
   };
   if (m->kind == SAPCU_MODEL_FN) {
     const FnPlan p = fn_plan(m->fn, S, M, nullptr);
-    const int D = p.Dl; const int64_t E = P * p.kl;
     if (n == "idx") return set(p.idx, P, p.kmax, p.kmax);            // int32 payload
     if (n == "snn_init") return set(p.F0, P, 64, 64);
     if (n == "fcat") return set(p.FCAT, P, 192, 192);
-    if (n == "trans3.snn1") return set(p.X, P, D, D);
-    if (n == "trans3.snn_qkv") return set(p.QKV, P, 3 * D, 3 * D);
-    if (n == "trans3.snn_delta2") return set(p.E2, E, D, D);
-    // tensor-core mode rotates the edge buffers (the fc_delta2 epilogue emits the attention input into E3)
-    if (n == "trans3.snn_gamma") return set(mode != SAPCU_MODE_FP32 ? p.E1 : p.E3, E, D, D);
-    if (n == "trans3.logits") {   // the tensor-core modes fuse the softmax into the fc_gamma2 epilogue: no logits buffer
-      SAPCU_REQUIRE(mode == SAPCU_MODE_FP32, "model_tap: 'trans3.logits' is only materialised in SAPCU_MODE_FP32");
-      return set(p.E1, E, D, D);
+    if (n.size() > 7 && n.compare(0, 5, "trans") == 0 && n[5] >= '1' && n[5] <= '3' && n[6] == '.') {
+      // intermediates of block b live in buffers every block reuses: valid for the LAST block the forward executed
+      // (block 3, or block b after a forward with the debug field `stop after block b` in its mode argument)
+      const int b = n[5] - '1';
+      const int D = m->fn.blk[b].D, kl = m->fn.blk[b].k < M ? m->fn.blk[b].k : M;
+      const int64_t E = P * kl;
+      const std::string t = n.substr(7);
+      if (t == "snn1") return set(p.X, P, D, D);
+      if (t == "snn_qkv") return set(p.QKV, P, 3 * D, 3 * D);
+      if (t == "snn_delta2") return set(p.E2, E, D, D);
+      // tensor-core modes rotate the edge buffers (fc_gamma's spikes land in E1)
+      if (t == "snn_gamma") return set((mode & 0xFF) != SAPCU_MODE_FP32 ? p.E1 : p.E3, E, D, D);
+      if (t == "logits") {   // the tensor-core modes fuse the softmax into the fc_gamma2 epilogue: no logits buffer
+        SAPCU_REQUIRE((mode & 0xFF) == SAPCU_MODE_FP32, "model_tap: '%s' is only materialised in SAPCU_MODE_FP32", name);
+        return set(p.E1, E, D, D);
+      }
+      if (t == "res") return set(p.RES, P, D, D);
     }
-    if (n == "trans3.res") return set(p.RES, P, D, D);
     if (n == "snn_final") return set(p.G, P, m->fn.emb, m->fn.emb);
     if (n == "gmax") return set(p.GM, S, m->fn.emb, m->fn.emb);
     if (n == "enc_out") return set(p.H0, S, 2048, 2048);
@@ -544,7 +565,9 @@ int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, in
     const FdPlan p = fd_plan(m->fd, S, M, nullptr);
     const int T = m->fd.T;
     if (n == "idx0") return set(p.idx0, P, p.kmax0, p.kmax0);        // int32 payload
-    if (n == "idxf") return set(p.idxf, P, p.k, p.k);                // int32 payload (block 3's graph)
+    if (n == "idxf" || n == "idxf3") return set(p.idxf[2], P, p.k, p.k);     // int32 payload: feature-space graph of block 3
+    if (n == "idxf1") return set(p.idxf[0], P, p.k, p.k);
+    if (n == "idxf2") return set(p.idxf[1], P, p.k, p.k);
     if (n == "f0") return set(p.F0, P, 64 * m->fd.nscales, 64 * m->fd.nscales);
     if (n == "u0") return set(p.U0, P, 64, 64);
     if (n == "u1") return set(p.U1, P, 128, 128);

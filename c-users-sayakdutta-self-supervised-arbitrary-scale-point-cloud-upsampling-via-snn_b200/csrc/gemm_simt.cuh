@@ -27,6 +27,7 @@ struct GemmArgs {
   // A operand
   const float* A = nullptr; int64_t lda = 0; int64_t R = 0; int K = 0;
   const int32_t* idx = nullptr; int ldi = 0; int kk = 0; int Mpts = 0;   // edge loaders: idx[pt*ldi + j]
+  const uint32_t* idx8 = nullptr; int ldi8w = 0;   // optional byte-packed copy of idx (4 indices per word) for the fused attention tail
   const float* F = nullptr; int64_t ldf = 0; int C = 0;       // A_EDGECAT
   const float* Q = nullptr; const float* Kf = nullptr; int64_t ldq = 0;   // A_ATTNIN
   // B operand: W[N,K] row-major

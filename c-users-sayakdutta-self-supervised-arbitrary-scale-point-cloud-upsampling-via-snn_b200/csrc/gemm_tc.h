@@ -18,4 +18,5 @@ bool gemm_tc2_fp16x3(const GemmArgs& g);
 // true when launch_gemm_tc2 would run this problem on the single-product fp16 path of SAPCU_MODE_FAST (input and, for LIF
 // layers, output are single fp16 planes of x * 2^13)
 bool gemm_tc2_fast(const GemmArgs& g);
+bool gemm_tc2_fast_tf32(const GemmArgs& g);
 }  // namespace sapcu

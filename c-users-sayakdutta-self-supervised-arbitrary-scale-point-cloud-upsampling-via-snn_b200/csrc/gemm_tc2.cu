@@ -77,6 +77,22 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives
                : "memory");
 }
 
+// cta_group::1 flavours (CG == 1: the same kernel as a single-CTA "pair" for 128-channel layers, fast mode only)
+__device__ __forceinline__ void umma_f16_1cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int CG> __device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+  if (CG == 2) umma_commit_2cta(bar); else umma_commit(bar);
+}
+template <int CG> __device__ __forceinline__ void cta_group_sync() {
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+}
+
 // H16 = fp16x3 operand format (activations known to be LIF outputs): W arrives as pre-split fp16 (hi, lo) of W * 2^e, the
 // splitter turns the raw fp32 activation tile into fp16 (hi, lo) of x * x_scale, and 12 kind::f16 MMAs per 64-wide
 // k-block (hi*hi + hi*lo + lo*hi, fp32 accumulate) replace 24 kind::tf32 ones: the same 22-bit products at twice the
@@ -85,17 +101,23 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives
 // x * 2^13 written by the producing epilogue: two TMA loads and 4 kind::f16 MMAs per 64-wide k-block, 32 KiB per stage.
 // LT (with ACT_LIF): the LIF^T chain of the epilogue is read from the per-channel piecewise-cubic table (lif_table.cuh) that
 // the epilogue warps copy into shared memory once per CTA (a CTA pair keeps its channel block for its whole life).
-template <int ACT, int EXTRA, int KK, int HM = 0, int LT = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((T2_EPI_WARP0 + T2_EPI) * 32, 1)
+// CG: CTAs per tile.  2 = the CTA pair described above (256 channels per tile).  1 = the same pipeline in one CTA (128
+// channels x 256 rows per tile, cta_group::1 MMAs, no cluster): the 128-channel layers of the first fn block in the fast
+// mode, which then share the single-plane operands, the LIF tables and the fused attention tail with the wide layers.
+template <int ACT, int EXTRA, int KK, int HM = 0, int LT = 0, int CG = 2>
+__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__((T2_EPI_WARP0 + T2_EPI) * 32, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                 const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2, const TcParams p) {
   // HM: 0 = 3xTF32; 1 = fp16x3, raw fp32 activations converted by the splitter warps; 2 = fp16x3, activations already
   // stored as fp16 (hi, lo) planes of x * 2^13 by the kernel that produced them (map_x = hi plane, map_x2 = lo plane): four
   // TMA loads per stage, no conversion, no raw staging -- a third less shared-memory traffic per k-block
-  constexpr bool H16 = HM != 0;
-  constexpr int T2_STAGES = HM == 1 ? 2 : (HM == 3 && !LT) ? 4 : 3;
-  constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : HM == 3 ? 2 : 4) * TC_TILE_BYTES;
-  constexpr uint32_t X_TILE = HM == 3 ? 1 : 2;              // position of the activation (hi) tile inside a stage
+  static_assert(CG == 2 || HM == 3 || HM == 4, "the single-CTA flavour exists for the fast mode's operand formats only");
+  constexpr bool H16 = HM == 1 || HM == 2 || HM == 3;        // fp16 operands (HM == 4: single-pass TF32 on fp32 activations)
+  constexpr int CW = CG * 128;                               // output channels per tile
+  constexpr bool FASTOP = HM == 3 || HM == 4;               // compact stages: one weight tile + one activation tile
+  constexpr int T2_STAGES = HM == 1 ? 2 : (FASTOP && !LT) ? 4 : (FASTOP && CG == 1) ? 2 : 3;
+  constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : FASTOP ? (CG == 2 ? 2 : 3) : 4) * TC_TILE_BYTES;   // HM 3/4: W tile + 128 (pair) or 256 activation rows
+  constexpr uint32_t X_TILE = FASTOP ? 1 : 2;               // position of the activation (hi) tile inside a stage
   constexpr int BKE = H16 ? 64 : TC_BK;                    // k elements per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -110,27 +132,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T2_STAGES * T2_STAGE_BYTES + 8 * (3 * T2_STAGES + 2 * T2_ACC));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();                 // 0 = leader
-  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader
+  const int64_t pair = blockIdx.x / CG, npairs = gridDim.x / CG;
   const int nk = p.K / BKE;
   const int64_t total_tiles = p.n_tiles * p.m_tiles;       // m_tiles = N / 256 (channel pairs), n_tiles = ceil(R / tile_rows)
   const int TR = p.tile_rows;                              // rows a tile advances by (256; whole points only when EXTRA == 3)
-  constexpr int HALF = T2_BN / 2;                          // rows staged by each CTA: the MMA always spans 256 rows
+  constexpr int HALF = T2_BN / CG;                         // rows staged by each CTA: the MMA always spans 256 rows
   // instruction descriptor: D = F32, A = B = TF32 (2) or F16 (0), K-major, M = 256 (pair), N = 256
-  constexpr uint32_t idesc = (1u << 4) | ((H16 ? 0u : 2u) << 7) | ((H16 ? 0u : 2u) << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t idesc = (1u << 4) | ((H16 ? 0u : 2u) << 7) | ((H16 ? 0u : 2u) << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(CW >> 4) << 24);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), 2 * T2_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
-    for (int a = 0; a < T2_ACC; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 2 * T2_EPI); }
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_split(s), CG * T2_SPLIT_WARPS * 32); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < T2_ACC; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), CG * T2_EPI); }
     fence_barrier_init();
     tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_wlo); tma_prefetch_desc(&map_x);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  cluster_sync_all();                                       // barriers of both CTAs initialised before any remote arrive
+  cta_group_sync<CG>();                                     // barriers of both CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -141,7 +168,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
       for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
         const int m_t = (int)(t % p.m_tiles);
         const int64_t n_t = t / p.m_tiles;
-        const int wrow = m_t * 256 + (int)rank * 128;
+        const int wrow = m_t * CW + (int)rank * 128;
         const int xrow = (int)(n_t * TR) + (int)rank * HALF;
         for (int kb = 0; kb < nk; ++kb) {
           if (p.l2_prefetch > 0) {
@@ -155,9 +182,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
           if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
-          if (HM == 3) {
-            mbar_expect_tx(bar_raw(s), 2 * TC_TILE_BYTES);
-            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // two fp16 tiles: 64 halfs x 128 rows
+          if (FASTOP) {
+            mbar_expect_tx(bar_raw(s), T2_STAGE_BYTES);
+            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // fp16 tiles: 64 halfs x 128 weight rows, x HALF activation rows
             tma_load_2d(st + TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
           } else if (HM == 2) {
             mbar_expect_tx(bar_raw(s), 4 * TC_TILE_BYTES);
@@ -195,10 +222,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
           const uint64_t w_hi = umma_desc_sw128(st), w_lo = umma_desc_sw128(st + TC_TILE_BYTES);
           const uint64_t x_hi = umma_desc_sw128(st + X_TILE * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
-          if (HM == 3) {
+          if (HM == 4) {                                         // single-pass TF32 on raw fp32 activations (8 floats = 32 B per MMA)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_f16_2cta(tmem_d, w_hi + (uint64_t)(ks * 2), x_hi + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
+            for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+              if (CG == 2) umma_tf32_2cta(tmem_d, w_hi + (uint64_t)(k8 * 2), x_hi + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+              else umma_tf32(tmem_d, w_hi + (uint64_t)(k8 * 2), x_hi + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+            }
+          } else if (HM == 3) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (CG == 2) umma_f16_2cta(tmem_d, w_hi + (uint64_t)(ks * 2), x_hi + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
+              else umma_f16_1cta(tmem_d, w_hi + (uint64_t)(ks * 2), x_hi + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
+            }
           } else if (H16) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {                       // 16 halfs = 32 B = 2 x 16 B along the swizzled row
@@ -219,8 +254,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
               umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
             }
           }
-          umma_commit_2cta(bar_empty(s));
-          if (kb == nk - 1) umma_commit_2cta(bar_tfull(a));
+          umma_commit_cg<CG>(bar_empty(s));
+          if (kb == nk - 1) umma_commit_cg<CG>(bar_tfull(a));
           if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
         }
         if (++a == T2_ACC) { a = 0; aph ^= 1u; }
@@ -300,7 +335,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     // LT: this CTA's 128-channel block of the tabulated LIF^T chain -> shared memory (behind the barriers), once
     const uint2* lt_desc = nullptr; const float4* lt_coef = nullptr;
     if (LT) {
-      const int blk = (int)(pair % p.m_tiles) * 2 + (int)rank;        // the host keeps npairs a multiple of m_tiles: fixed channel block
+      const int blk = (int)(pair % p.m_tiles) * CG + (int)rank;       // the host keeps npairs a multiple of m_tiles: fixed channel block
       uint8_t* tsm = smem_gen + T2_STAGES * T2_STAGE_BYTES + 256;
       const uint4* src = reinterpret_cast<const uint4*>(p.lif_tab + (size_t)blk * p.lif_tab_stride);
       uint4* dst = reinterpret_cast<uint4*>(tsm);
@@ -312,7 +347,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
       const int m_t = (int)(t % p.m_tiles);
       const int64_t n_t = t / p.m_tiles;
-      const int c = m_t * 256 + (int)rank * 128 + q * 32 + lane;
+      const int c = m_t * CW + (int)rank * 128 + q * 32 + lane;
       const float bia = p.bias ? p.bias[c] : 0.0f;
       const float sc = p.scale ? p.scale[c] : 1.0f;
       const float sh = p.shift ? p.shift[c] : 0.0f;
@@ -329,7 +364,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           const int64_t tn = t + npairs;
           if (tn < total_tiles) {
             const int64_t row0 = (tn / p.m_tiles) * TR;
-            const int cb = (int)(tn % p.m_tiles) * 256 + (int)rank * 128;
+            const int cb = (int)(tn % p.m_tiles) * CW + (int)rank * 128;
             for (int i = (warp - T2_EPI_WARP0) * 32 + lane; i < TR * 4; i += T2_EPI * 32) {
               const int64_t row = row0 + (i >> 2);
               if (row >= p.R) continue;
@@ -390,7 +425,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j] + bia, sc, sh);
-              if (HM == 3) lif_chain_vec_fast2<8>(u, np, p.T);
+              if (FASTOP) lif_chain_vec_fast2<8>(u, np, p.T);
               else lif_chain_vec_fast<8>(u, np, p.T);
             }
             float* yp = p.Y + r0 * p.ldc + c;
@@ -507,10 +542,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     }
   }
   tc_fence_before();
-  cluster_sync_all();                                       // nobody leaves while the peer may still touch its smem / barriers
+  cta_group_sync<CG>();                                     // nobody leaves while the peer may still touch its smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -532,7 +568,8 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   GemmArgs base = g;
   base.at_pos = nullptr; base.pool = nullptr; base.x_h2 = false; base.out_h2 = false; base.pos_h2 = false;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
-  if (g.N % 256 != 0 || g.act == ACT_GELU) return false;
+  if (g.act == ACT_GELU) return false;
+  if (g.N % 256 != 0 && !(g.N % 128 == 0 && (gemm_tc2_fast(g) || gemm_tc2_fast_tf32(g)))) return false;   // single-CTA flavour: fast mode only
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
   if (g.R < 4096) return false;
   if (g.pool) {
@@ -555,13 +592,19 @@ bool gemm_tc2_fp16x3(const GemmArgs& g) {
 
 // SAPCU_MODE_FAST operands: one fp16 product per MAC on a single fp16 plane (the producer wrote x * 2^13 as halfs)
 bool gemm_tc2_fast(const GemmArgs& g) {
-  return g.fast && g.x_unit && g.Wh && g.K % 64 == 0 && !g.residual &&
+  return g.fast && g.x_h2 && g.x_unit && g.Wh && g.K % 64 == 0 && !g.residual &&
          (g.at_pos || g.act == ACT_LIF || (g.act == ACT_LEAKY && g.pool));
+}
+// SAPCU_MODE_FAST, point-level LIF layers (fp32 activations in and out): single-pass TF32 with compact stages, so that the
+// layer's LIF table fits next to the pipeline (HM = 4)
+bool gemm_tc2_fast_tf32(const GemmArgs& g) {
+  return g.fast && !g.x_h2 && !g.out_h2 && g.act == ACT_LIF && !g.edge_bias && !g.residual && !g.at_pos && !g.pool &&
+         g.Whi && g.K % TC_BK == 0;
 }
 
 namespace {
-constexpr size_t t2_smem_fast(bool lt, uint32_t tab_stride) {
-  return (size_t)(lt ? 3 : 4) * 2 * TC_TILE_BYTES + 1024 + 256 + (lt ? tab_stride : 0);
+constexpr size_t t2_smem_fast(bool lt, uint32_t tab_stride, int cg = 2) {
+  return (size_t)(lt ? (cg == 2 ? 3 : 2) : 4) * (cg == 2 ? 2 : 3) * TC_TILE_BYTES + 1024 + 256 + (lt ? tab_stride : 0);
 }
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per device
 int t2_set_attrs_impl() {
@@ -580,6 +623,13 @@ int t2_set_attrs_impl() {
   SAPCU_T2_ATTR_F(ACT_LIF, 0, 1, 0); SAPCU_T2_ATTR_F(ACT_LIF, 0, 1, 1); SAPCU_T2_ATTR_F(ACT_LIF, 2, 1, 0); SAPCU_T2_ATTR_F(ACT_LIF, 2, 1, 1);
   SAPCU_T2_ATTR_F(ACT_LEAKY, 4, 1, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 12, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 18, 0); SAPCU_T2_ATTR_F(ACT_NONE, 3, 24, 0);
 #undef SAPCU_T2_ATTR_F
+#define SAPCU_T2_ATTR_F1(A, X, KQ, LTQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 3, LTQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_fast(LTQ != 0, LT_SMEM_BUDGET, 1)))
+  SAPCU_T2_ATTR_F1(ACT_LIF, 0, 1, 0); SAPCU_T2_ATTR_F1(ACT_LIF, 0, 1, 1); SAPCU_T2_ATTR_F1(ACT_LIF, 2, 1, 0); SAPCU_T2_ATTR_F1(ACT_LIF, 2, 1, 1);
+  SAPCU_T2_ATTR_F1(ACT_NONE, 3, 12, 0); SAPCU_T2_ATTR_F1(ACT_NONE, 3, 18, 0); SAPCU_T2_ATTR_F1(ACT_NONE, 3, 24, 0);
+#undef SAPCU_T2_ATTR_F1
+#define SAPCU_T2_ATTR_T(LTQ, CGQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 0, 1, 4, LTQ, CGQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_fast(LTQ != 0, LT_SMEM_BUDGET, CGQ)))
+  SAPCU_T2_ATTR_T(0, 1); SAPCU_T2_ATTR_T(1, 1); SAPCU_T2_ATTR_T(0, 2); SAPCU_T2_ATTR_T(1, 2);
+#undef SAPCU_T2_ATTR_T
   return 0;
 }
 int t2_set_attrs() {
@@ -595,7 +645,8 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   SAPCU_REQUIRE(err != nullptr, "gemm_tc2: cannot allocate the watchdog flag");
   const int l2pf = settings().l2pf;
   const int tile_rows = g.at_pos ? tc_fused_tile_rows(g.kk) : T2_BN;
-  const bool fast = gemm_tc2_fast(g);
+  const bool fast = gemm_tc2_fast(g), fast_tf32 = !fast && gemm_tc2_fast_tf32(g);
+  const int cg = (g.N % 256 == 0) ? 2 : 1;                   // CTAs per tile: 1 = the single-CTA flavour for 128-channel layers (fast mode)
   SAPCU_REQUIRE(!fast || (g.x_h2 && g.lda == g.K && (!g.out_h2 || (g.act == ACT_LIF && g.ldc == g.N))), "gemm_tc2(fast): needs a single-plane fp16 input with lda == K");
   const bool h16 = fast || gemm_tc2_fp16x3(g);
   const bool pre = h16 && g.x_h2;                            // activations already stored as fp16 (hi, lo) planes
@@ -608,13 +659,13 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   if (rc) return rc;
   if (pre) {
     const uint16_t* hp = reinterpret_cast<const uint16_t*>(g.A);
-    rc = tc_make_map_f16(&mx, hp, g.R, g.K, T2_BN / 2);
+    rc = tc_make_map_f16(&mx, hp, g.R, g.K, T2_BN / cg);
     if (rc) return rc;
     rc = fast ? 0 : tc_make_map_f16(&mx2, hp + g.R * g.K, g.R, g.K, T2_BN / 2);
     if (rc) return rc;
     if (fast) mx2 = mx;
   } else {
-    rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, T2_BN / 2);
+    rc = tc_make_map(&mx, g.A, g.R, g.K, g.lda, T2_BN / cg);
     if (rc) return rc;
     mx2 = mx;
   }
@@ -623,14 +674,30 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
   p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
   p.pool = g.pool; p.pool_T = g.pool_T; p.pool_rows = (int64_t)g.pool_T * g.pool_M;
+  p.idx8 = g.idx8; p.ldi8w = g.ldi8w;
   p.at_pos = g.at_pos; p.at_v = g.at_v; p.at_ldv = g.at_ldv; p.at_sqrt = g.at_sqrt; p.tile_rows = tile_rows;
-  p.m_tiles = g.N / 256; p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
+  p.m_tiles = g.N / (128 * cg); p.n_tiles = ceil_div(g.R, tile_rows); p.err = err; p.split_w = 0; p.raw_hi = 1; p.l2_prefetch = l2pf; p.passes = g.tc_passes == 1 ? 1 : 3;
   p.out_h2 = g.out_h2 ? 1 : 0; p.pos_h2 = g.pos_h2 ? 1 : 0;
   p.lif_tab = nullptr; p.lif_tab_stride = 0;
   p.x_scale = h16 ? 8192.0f : 1.0f;                         // soft spikes lie in (0, 0.7): x * 2^13 < 2^13, residual * 2^13 >= fp16's normal range
   p.acc_scale = h16 ? g.winv / 8192.0f : 1.0f;
   const int64_t total = p.n_tiles * p.m_tiles;
-  int pairs = (int)(total < kNumSMs / 2 ? total : kNumSMs / 2);
+  int pairs = (int)(total < kNumSMs / cg ? total : kNumSMs / cg);
+  if (fast_tf32) {
+    const bool lt = g.lif_tab != nullptr && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET;
+    if (lt) pairs = (pairs / p.m_tiles) * p.m_tiles;
+    SAPCU_REQUIRE(pairs >= 1, "gemm_tc2(fast tf32): empty grid");
+    p.lif_tab = reinterpret_cast<const uint8_t*>(g.lif_tab); p.lif_tab_stride = g.lif_tab_stride;
+    p.passes = 1; p.x_scale = 1.0f; p.acc_scale = 1.0f;
+    const size_t smem = t2_smem_fast(lt, g.lif_tab_stride, cg);
+    const int gridf = cg * pairs;
+#define SAPCU_T2_LAUNCH_T(LTQ, CGQ) gemm_tc2_kernel<ACT_LIF, 0, 1, 4, LTQ, CGQ><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p)
+    if (cg == 2) { if (lt) SAPCU_T2_LAUNCH_T(1, 2); else SAPCU_T2_LAUNCH_T(0, 2); }
+    else { if (lt) SAPCU_T2_LAUNCH_T(1, 1); else SAPCU_T2_LAUNCH_T(0, 1); }
+#undef SAPCU_T2_LAUNCH_T
+    SAPCU_LAUNCH_CHECK();
+    return 0;
+  }
   if (fast) {
     // one fp16 product per MAC: map_w = the hi half of the fp16 weight split, map_x = the single activation plane
     const bool lt = g.act == ACT_LIF && g.lif_tab != nullptr && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET;
@@ -639,12 +706,19 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     p.lif_tab = reinterpret_cast<const uint8_t*>(g.lif_tab); p.lif_tab_stride = g.lif_tab_stride;
     p.out_h2 = g.out_h2 ? 2 : 0; p.pos_h2 = g.pos_h2 ? 2 : 0;
     p.x_scale = 8192.0f; p.acc_scale = g.winv / 8192.0f;
-    const size_t smem = t2_smem_fast(lt, g.lif_tab_stride);
-    const int gridf = 2 * pairs;
-#define SAPCU_T2_LAUNCH_F(A, X, KQ, LTQ) gemm_tc2_kernel<A, X, KQ, 3, LTQ><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p)
+    const size_t smem = t2_smem_fast(lt, g.lif_tab_stride, cg);
+    const int gridf = cg * pairs;
+#define SAPCU_T2_LAUNCH_F(A, X, KQ, LTQ)                                                                                \
+  do {                                                                                                                  \
+    if (cg == 2) gemm_tc2_kernel<A, X, KQ, 3, LTQ><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p);    \
+    else gemm_tc2_kernel<A, X, KQ, 3, LTQ, 1><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p);        \
+  } while (0)
     if (g.at_pos) {
       if (g.kk == 12) SAPCU_T2_LAUNCH_F(ACT_NONE, 3, 12, 0); else if (g.kk == 18) SAPCU_T2_LAUNCH_F(ACT_NONE, 3, 18, 0); else SAPCU_T2_LAUNCH_F(ACT_NONE, 3, 24, 0);
-    } else if (g.act == ACT_LEAKY) SAPCU_T2_LAUNCH_F(ACT_LEAKY, 4, 1, 0);
+    } else if (g.act == ACT_LEAKY) {
+      SAPCU_REQUIRE(cg == 2, "gemm_tc2(fast): the pooled conv5 epilogue needs N %% 256 == 0");
+      gemm_tc2_kernel<ACT_LEAKY, 4, 1, 3, 0><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p);
+    }
     else if (g.edge_bias) { if (lt) SAPCU_T2_LAUNCH_F(ACT_LIF, 2, 1, 1); else SAPCU_T2_LAUNCH_F(ACT_LIF, 2, 1, 0); }
     else { if (lt) SAPCU_T2_LAUNCH_F(ACT_LIF, 0, 1, 1); else SAPCU_T2_LAUNCH_F(ACT_LIF, 0, 1, 0); }
 #undef SAPCU_T2_LAUNCH_F

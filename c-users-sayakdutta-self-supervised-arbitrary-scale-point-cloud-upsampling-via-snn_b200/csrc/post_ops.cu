@@ -15,11 +15,12 @@ namespace cg = cooperative_groups;
 namespace sapcu {
 
 // avg[i] = mean_j sqrt(|p_i - p_idx[i][j]|^2), numpy's pairwise summation order for a row of K doubles
-__global__ void knn_mean_dist_kernel(const double* __restrict__ pts, const int32_t* __restrict__ idx, int64_t S, int K,
-                                     double* __restrict__ avg) {
+// qry: the S query points (== pts for the single-GPU filter; a rank's own rows of the gathered points when sharded)
+__global__ void knn_mean_dist_kernel(const double* __restrict__ pts, const double* __restrict__ qry, const int32_t* __restrict__ idx,
+                                     int64_t S, int K, double* __restrict__ avg) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= S) return;
-  const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  const double x = qry[3 * i], y = qry[3 * i + 1], z = qry[3 * i + 2];
   auto dist = [&](int j) {
     const int64_t p = idx[i * K + j];
     const double dx = pts[3 * p] - x, dy = pts[3 * p + 1] - y, dz = pts[3 * p + 2] - z;
@@ -58,12 +59,13 @@ __global__ void sum_f64_kernel(const double* __restrict__ a, int64_t n, double* 
   if (threadIdx.x == 0) *out = sh[0];
 }
 
-__global__ void outlier_mask_kernel(const double* __restrict__ avg, int64_t S, const double* __restrict__ total, double threshold,
-                                    uint8_t* __restrict__ keep) {
+// rows [lo, lo + n) of the S row means -> keep[0..n)
+__global__ void outlier_mask_kernel(const double* __restrict__ avg, int64_t S, int64_t lo, int64_t n, const double* __restrict__ total,
+                                    double threshold, uint8_t* __restrict__ keep) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= S) return;
+  if (i >= n) return;
   const double avgtotal = *total / (double)S;           // mean over all S*K distances == mean of the row means
-  keep[i] = avg[i] < avgtotal * threshold ? 1 : 0;
+  keep[i] = avg[lo + i] < avgtotal * threshold ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------- FPS
@@ -132,11 +134,34 @@ int sapcu_outlier_mask(const double* d_points, int64_t S, const int32_t* d_idx, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   double* avg = reinterpret_cast<double*>(d_ws);
   double* total = reinterpret_cast<double*>(reinterpret_cast<char*>(d_ws) + align_up((size_t)S * 8, 256));
-  knn_mean_dist_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>(d_points, d_idx, S, K, avg);
+  knn_mean_dist_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>(d_points, d_points, d_idx, S, K, avg);
   SAPCU_LAUNCH_CHECK();
   sum_f64_kernel<<<1, 1024, 0, st>>>(avg, S, total);
   SAPCU_LAUNCH_CHECK();
-  outlier_mask_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(avg, S, total, threshold, d_keep);
+  outlier_mask_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(avg, S, 0, S, total, threshold, d_keep);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int sapcu_knn_mean_dist(const double* d_points, int64_t S, const double* d_query, int64_t rows, const int32_t* d_idx, int K,
+                        double* d_mean, void* stream) {
+  SAPCU_REQUIRE(S >= 1 && rows >= 0 && K >= 1 && d_points && (rows == 0 || (d_query && d_idx && d_mean)), "knn_mean_dist: bad argument");
+  if (rows == 0) return 0;
+  knn_mean_dist_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_points, d_query, d_idx, rows, K, d_mean);
+  SAPCU_LAUNCH_CHECK();
+  return 0;
+}
+
+int sapcu_outlier_mask_from_means(const double* d_mean_all, int64_t S, int64_t row_lo, int64_t rows, double threshold, uint8_t* d_keep,
+                                  void* d_ws, size_t ws_bytes, void* stream) {
+  SAPCU_REQUIRE(S >= 1 && row_lo >= 0 && rows >= 0 && row_lo + rows <= S && d_mean_all && d_ws && (rows == 0 || d_keep), "outlier_mask_from_means: bad argument");
+  SAPCU_REQUIRE(ws_bytes >= 256, "outlier_mask_from_means: workspace of 256 bytes needed");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* total = reinterpret_cast<double*>(d_ws);
+  sum_f64_kernel<<<1, 1024, 0, st>>>(d_mean_all, S, total);          // the same fixed summation order on every rank
+  SAPCU_LAUNCH_CHECK();
+  if (rows == 0) return 0;
+  outlier_mask_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(d_mean_all, S, row_lo, rows, total, threshold, d_keep);
   SAPCU_LAUNCH_CHECK();
   return 0;
 }

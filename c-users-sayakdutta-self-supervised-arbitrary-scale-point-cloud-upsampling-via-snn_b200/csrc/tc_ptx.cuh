@@ -188,6 +188,7 @@ struct TcParams {
   // EXTRA == 3 (fn fc_gamma2, 2-CTA kernel): the epilogue applies softmax over the kk edges of a point to the logits
   // (/ at_sqrt) and writes Y[pt,c] = sum_j a_j (at_v[nb_j,c] + at_pos[e_j,c]) instead of the logits
   const float* at_pos; const float* at_v; int64_t at_ldv; float at_sqrt;
+  const uint32_t* idx8; int ldi8w;   // optional byte-packed copy of the graph (4 patch-local indices per word, ldi8w words per point)
   // EXTRA == 4 (fd conv5, 2-CTA kernel): rows are (point*T + t); the epilogue keeps one running maximum per step and
   // merges them into pool[(patch*T + t), c] with float atomic max -- the [P*T, N] activation never reaches HBM
   float* pool; int pool_T; int64_t pool_rows;     // pool_rows = points per patch * T
@@ -220,12 +221,12 @@ __device__ __forceinline__ void edge_lane_offsets(const TcParams& p, int64_t e0,
 // qv[r] = aq[pt_r, c], kv[r] = ak[nb_r, c] for rows 8*sub .. 8*sub+7 of the warp's current 32-row group: 16 independent
 // loads, consumed by the caller only after its arithmetic on the previous piece (which hides their latency)
 __device__ __forceinline__ void edge_fetch8(const TcParams& p, int my_qo, int my_ko, int sub, int c, float (&qv)[8], float (&kv)[8]) {
-  const float* aq = p.aq + c;
-  const float* ak = p.ak + c;
+  // unsigned 32-bit element offsets from the two uniform bases: one 64-bit multiply-add (IMAD.WIDE, fma pipe) per address
+  // instead of a LEA / LEA.HI.X pair on the ALU pipe, which the LIF-table epilogue saturates
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int qo = __shfl_sync(0xffffffffu, my_qo, sub * 8 + r), ko = __shfl_sync(0xffffffffu, my_ko, sub * 8 + r);
-    qv[r] = aq[qo]; kv[r] = ak[ko];
+    qv[r] = p.aq[(uint32_t)(qo + c)]; kv[r] = p.ak[(uint32_t)(ko + c)];
   }
 }
 
@@ -242,6 +243,12 @@ __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tme
   const float* vc = p.at_v + c;
   uint32_t nbn[(KK + 3) / 4];                                    // graph row of the next point, 4 patch-local indices (< 256) per word
   auto fetch_row = [&](int64_t ptq) {
+    if (p.idx8) {                                                // byte-packed graph: (KK + 3) / 4 word loads, nothing to shift
+      const uint32_t* ip = p.idx8 + (ptq < P_total ? ptq : P_total - 1) * p.ldi8w;
+#pragma unroll
+      for (int w = 0; w < (KK + 3) / 4; ++w) nbn[w] = ip[w];
+      return;
+    }
     const int32_t* ip = p.idx + (ptq < P_total ? ptq : P_total - 1) * p.ldi;
 #pragma unroll
     for (int w = 0; w < (KK + 3) / 4; ++w) nbn[w] = 0u;
@@ -255,12 +262,13 @@ __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tme
     const int64_t patch0 = (pt / p.Mpts) * p.Mpts;
     const float* ps = p.at_pos + (pt * KK) * (int64_t)p.N + c;
     float vr[KK], pr[KK];
+    __half prh[KK];                                              // fast mode: the raw halves, converted only where they are consumed
 #pragma unroll
     for (int j = 0; j < KK; ++j) vr[j] = vc[(patch0 + (int64_t)((nbn[j >> 2] >> (8 * (j & 3))) & 255u)) * p.at_ldv];
     if (p.pos_h2 == 2) {                                         // fast mode: one fp16 plane of pos * 2^13
       const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * (int64_t)p.N + c;
 #pragma unroll
-      for (int j = 0; j < KK; ++j) pr[j] = __half2float(ph[(int64_t)j * p.N]) * (1.0f / 8192.0f);
+      for (int j = 0; j < KK; ++j) prh[j] = ph[(int64_t)j * p.N];
     } else if (p.pos_h2) {
       const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * (int64_t)p.N + c;
       const __half* pl = ph + p.R * (int64_t)p.N;
@@ -283,7 +291,7 @@ __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tme
     const float inv_sum = 1.0f / sum;
     float res = 0.0f;
 #pragma unroll
-    for (int j = 0; j < KK; ++j) res = fmaf(av[j] * inv_sum, vr[j] + pr[j], res);
+    for (int j = 0; j < KK; ++j) res = fmaf(av[j] * inv_sum, vr[j] + (p.pos_h2 == 2 ? __half2float(prh[j]) * (1.0f / 8192.0f) : pr[j]), res);
     p.Y[pt * p.ldc + c] = res;
   }
 }

@@ -100,7 +100,7 @@ class ImprovedSNNNormalEstimation(NativeModel):
         return [int(k) for k in self.k_values] + [int(self.emb_dims), int(self.time_steps_enc), int(self.num_heads)]
 
     @torch.no_grad()
-    def forward(self, point_cloud):
+    def forward(self, point_cloud, _stop_after_block=0):
         """[B,M,3] | [B,3,M] -> [B,3];  [B,Np,M,3] -> [B,Np,3]  (reference fn/snn_coder.py:670-699)."""
         x = self._prep_input(point_cloud)
         lead = None
@@ -120,6 +120,6 @@ class ImprovedSNNNormalEstimation(NativeModel):
             with torch.cuda.device(x.device):        # weights, workspace, stream and launches all on the input's device
                 h = self._ensure_handle(x.device)
                 ws = self._workspace(S, M, x.device)
-                N.check(N.lib().sapcu_fn_forward(h, N.ptr(x), S, M, N.ptr(out), N.ptr(ws), ws.numel(), self.mode,
+                N.check(N.lib().sapcu_fn_forward(h, N.ptr(x), S, M, N.ptr(out), N.ptr(ws), ws.numel(), self.mode | (int(_stop_after_block) << 8),
                                                  N.stream_ptr(x.device)), "sapcu_fn_forward")
         return out.view(*lead, 3) if lead else out

@@ -94,3 +94,53 @@ def upsample_sharded_host(generator, cloud, seeds, group=None, batch=None):
         from . import _native as N
         N.check_device("upsample_sharded_host")
     return h_out.numpy()
+
+
+def outlier_keep_sharded(d_points, threshold=1.5, k=30, group=None, shard=None):
+    """generation.py:176-183 over seeds sharded across ranks.  d_points [S,3] f64: the gathered displaced points (every rank
+    holds all of them).  Each rank queries the k self-neighbours of ITS rows, the row means are all-gathered and summed in
+    the single-GPU order, each rank masks its rows and the masks are all-gathered: returns the full boolean keep mask [S]
+    (cuda), bit-identical to Generator3D6._outlier_filter's for any world size.  `shard` = (rank, world) overrides the
+    process group (single-process emulation of the ranks in tests)."""
+    import ctypes
+    from . import _native as N
+    L = N.lib()
+    S = d_points.shape[0]
+    if S < k:
+        raise ValueError("k must be less than or equal to the number of training points")
+    dev = d_points.device
+    if shard is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ranks = [rank]
+    else:
+        world, ranks = shard[1], list(range(shard[1])) if shard[0] is None else [shard[0]]
+    means = {}
+    with torch.cuda.device(dev):
+        st = N.stream_ptr(dev)
+        kws = torch.empty(L.sapcu_knn_workspace_bytes(S), dtype=torch.uint8, device=dev)
+        for r in ranks:
+            lo, hi = shard_range(S, r, world)
+            q = d_points[lo:hi].contiguous()
+            idx = torch.empty(hi - lo, k, dtype=torch.int32, device=dev)
+            N.check(L.sapcu_knn(N.ptr(d_points), S, N.ptr(q), hi - lo, k, N.ptr(idx), N.ptr(kws), kws.numel(), st), "sapcu_knn(outlier shard)")
+            m = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+            N.check(L.sapcu_knn_mean_dist(N.ptr(d_points), S, N.ptr(q), hi - lo, N.ptr(idx), k, N.ptr(m), st), "sapcu_knn_mean_dist")
+            means[r] = m
+        if shard is None:
+            mean_all = all_gather_rows(means[ranks[0]].view(-1, 1), S, group).view(-1).contiguous()
+        else:
+            mean_all = torch.cat([means[r] for r in range(world)]).contiguous()      # emulated ranks: all shards computed here
+        ws = torch.empty(256, dtype=torch.uint8, device=dev)
+        keeps = {}
+        for r in ranks:
+            lo, hi = shard_range(S, r, world)
+            keep = torch.empty(hi - lo, dtype=torch.uint8, device=dev)
+            N.check(L.sapcu_outlier_mask_from_means(N.ptr(mean_all), S, lo, hi - lo, float(threshold), N.ptr(keep), N.ptr(ws), ws.numel(), st),
+                    "sapcu_outlier_mask_from_means")
+            keeps[r] = keep
+        if shard is None:
+            keep_all = all_gather_rows(keeps[ranks[0]].view(-1, 1), S, group).view(-1)
+        else:
+            keep_all = torch.cat([keeps[r] for r in range(world)])
+    return keep_all.bool()

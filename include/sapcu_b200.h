@@ -130,6 +130,17 @@ size_t sapcu_outlier_workspace_bytes(int64_t S);
 int sapcu_outlier_mask(const double* d_points, int64_t S, const int32_t* d_idx, int K, double threshold,
                        uint8_t* d_keep, void* d_ws, size_t ws_bytes, void* stream);
 
+/* The same filter over seeds sharded across GPUs ("needs a global mean"): after the all-gather
+ * of the displaced points every rank holds all S points; it queries the kNN of ITS rows (sapcu_knn with cloud = all
+ * points, seeds = its rows), computes their mean neighbour distances with sapcu_knn_mean_dist, the row means are
+ * all-gathered (S doubles), and sapcu_outlier_mask_from_means sums them in one fixed order -- the order of the
+ * single-GPU filter -- and masks the rank's rows [row_lo, row_lo + rows): the survivors are bit-identical to
+ * sapcu_outlier_mask for any number of ranks.  d_ws: 256 bytes. */
+int sapcu_knn_mean_dist(const double* d_points, int64_t S, const double* d_query, int64_t rows,
+                        const int32_t* d_idx, int K, double* d_mean, void* stream);
+int sapcu_outlier_mask_from_means(const double* d_mean_all, int64_t S, int64_t row_lo, int64_t rows, double threshold,
+                                  uint8_t* d_keep, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Farthest point sampling ("next" row 3), generate.py:56-74: fp32, start index `start` (the reference uses N/2),
  * running distances initialised to 1e32, ties -> lowest index.  d_out: int32 [npoint] selected indices in order.
@@ -160,7 +171,9 @@ void sapcu_model_destroy(sapcu_model* m);
  * less and chunks internally; it needs at least the size for S = 1). */
 size_t sapcu_model_workspace_bytes(const sapcu_model* m, int64_t S, int M);
 
-/* fn: ImprovedSNNNormalEstimation.forward([S,M,3]) -> [S,3] unit normals (fn/snn_coder.py:670-699). */
+/* fn: ImprovedSNNNormalEstimation.forward([S,M,3]) -> [S,3] unit normals (fn/snn_coder.py:670-699).
+ * `mode`: bits 0-7 = SAPCU_MODE_*; bits 8-11 (tests only) = b in 1..3: stop after transformer block b, leaving ITS
+ * intermediates in the workspace for sapcu_model_tap ("trans<b>.*") -- the normals are then not written. */
 int sapcu_fn_forward(const sapcu_model* m, const float* d_patches, int64_t S, int M,
                      float* d_normals, void* d_ws, size_t ws_bytes, int mode, void* stream);
 
@@ -173,7 +186,9 @@ int sapcu_fd_forward(const sapcu_model* m, const float* d_patches, int64_t S, in
 
 /* Debug taps for the parity tests: location of a named intermediate inside the workspace of the
  * LAST chunk a forward call of the given `mode` processed (valid when S fits one chunk).  Element (row r, col c) is at
- * float offset  off + r*ld + c.  Returns SAPCU_EINVAL for an unknown name. */
+ * float offset  off + r*ld + c.  Returns SAPCU_EINVAL for an unknown name.  fn: "idx", "snn_init", "fcat", "trans<b>.{snn1,
+ * snn_qkv,snn_delta2,snn_gamma,logits,res}" (b = the last block the forward executed), "snn_final", "gmax", "enc_out", "dec_h3";
+ * fd: "idx0", "idxf1".."idxf3" (feature-space graphs of blocks 1..3), "f0", "u0".."u3", "spikes", "pool", "z", "dec_d2", "dec_hidden". */
 int sapcu_model_tap(const sapcu_model* m, const char* name, int64_t S, int M, int mode,
                     int64_t* off_floats, int64_t* rows, int64_t* cols, int64_t* ld);
 /* Storage format the most recent forward used for a tap: 0 = fp32 [rows, ld]; 1 = two consecutive fp16 planes

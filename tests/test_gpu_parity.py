@@ -886,3 +886,138 @@ def test_fd_fp32_any_neighbour_count(lib, sphere):
         got = m(p.to(DEV), forced_idx=forced).cpu().numpy()
         rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
         assert rel.max() < 1e-3, (M, rel)
+
+
+def test_outlier_filter_sharded_equals_single_gpu(lib, golden):
+    """SURVEY.md section 8f-2 on several ranks: per-rank self-kNN of the rank's rows against the gathered points, all-gather of
+    the row means, one fixed-order sum, per-rank mask.  The ranks are emulated in one process (G in {2, 3, 4, 8}); the
+    survivors must be identical to the single-GPU filter (and hence to the reference pipeline's own, checked above)."""
+    from sapcu_b200.generation import Generator3D6
+    from sapcu_b200.sharding import outlier_keep_sharded
+    mfn, mfd, _, _ = _models(False)
+    gen = Generator3D6(mfn, mfd, DEV, remove_outliers=True)
+    g = golden.post
+    pts = g["points"] if "points" in g.files else g[g.files[0]]
+    rng = np.random.default_rng(2)
+    pts = np.concatenate([np.asarray(pts, dtype=np.float64).reshape(-1, 3)[:4000], rng.normal(size=(37, 3)) * 0.7])   # + a few outliers
+    single = gen._outlier_filter(pts)
+    d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to(DEV)
+    for G in (2, 3, 4, 8):
+        keep = outlier_keep_sharded(d_pts, threshold=1.5, k=30, shard=(None, G)).cpu().numpy()
+        assert np.array_equal(pts[keep], single), G
+    assert 0 < single.shape[0] < pts.shape[0]
+
+
+# ----------------------------------------------------------------------------------------- round 2: tighter parity evidence
+@pytest.mark.parametrize("mode", ["fp32", "tc", "fast"])
+def test_fn_block_taps_trans1_trans2(lib, sphere, parity_log, mode):
+    """Blocks 1 and 2 of fn (D = 128 / 256: the other kernel flavours -- 1-CTA tensor-core kernel in `tc`, single-CTA fast
+    flavour in `fast`) are tapped directly: the forward stops after block b (debug field of `mode`) and the block's neuron
+    layers are compared with the oracle's per layer, soft values and binarised spikes."""
+    cloud, seeds = sphere
+    mfn, _, sd_fn, _ = _models(True)
+    mfn.set_mode(mode)
+    B = 48
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx))
+    taps = {}
+    with torch.no_grad():
+        orc.fn_forward(sd_fn, p, taps=taps)
+    tol, agr = (2e-3, 0.999) if mode != "fast" else (3e-3, 0.995)
+    rec = {}
+    for b in (1, 2):
+        mfn(p.to(DEV), _stop_after_block=b)
+        torch.cuda.synchronize()
+        kb = taps["encoder.trans%d" % b]
+        for name, r in (("snn1", _cf(kb["snn1"])), ("snn_qkv", np.concatenate([_cf(kb["q"]), _cf(kb["k"]), _cf(kb["v"])], 1)),
+                        ("snn_delta2", _cf(kb["pos"])), ("snn_gamma", _cf(kb["a1"]))):
+            t = mfn.tap("trans%d.%s" % (b, name), B, 100).cpu().numpy()
+            assert t.shape == r.shape, (b, name, t.shape, r.shape)
+            err, ag = float(np.abs(t - r).max()), _agree(t, r)
+            rec["trans%d.%s" % (b, name)] = dict(max_abs=err, spike_agreement=ag)
+            assert err < tol and ag >= agr, (mode, b, name, err, ag)
+    parity_log.record("fn_block_taps[%s]" % mode, **rec)
+
+
+def _inv_softplus5(d):
+    """pre-Softplus logit of the distance head (Softplus beta = 5, fd/snn_coder.py:725) in float64."""
+    d = np.asarray(d, np.float64)
+    return np.where(5.0 * d > 20.0, d, np.log(np.expm1(np.maximum(5.0 * d, 1e-300))) / 5.0)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("stress", [False, True], ids=["default_init", "stress_init"])
+def test_fd_free_running_logits_and_graph_mismatch(lib, sphere, parity_log, stress, mode):
+    """Free-running fd (own feature-space kNN) judged where the north_star tolerance is meaningful: on the pre-Softplus
+    logit (the Softplus tail turns a 1e-7 absolute difference into a large relative one) and with the per-block rate of
+    feature-space neighbour lists that differ from the oracle's (near-ties among soft spikes) recorded.
+    Patches whose three graphs match the oracle's exactly must meet 1e-3 on the logit; patches with flipped near-tie
+    neighbours are bounded separately and counted."""
+    _, mfd, _, sd_fd = _models(stress)
+    mfd.set_mode(mode)
+    cloud, seeds = sphere
+    B = 48 if mode == "tc" else 16
+    idx = oracle_c.knn(cloud, seeds[:B], 100)
+    rng = np.random.default_rng(9)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:B], idx, rng.normal(size=(B, 3)).astype(np.float32)))
+    taps = {}
+    with torch.no_grad():
+        ref = orc.fd_forward(sd_fd, p, schedule="dce", taps=taps).numpy()
+    got = mfd(p.to(DEV)).cpu().numpy()
+    mism, same = {}, np.ones(B, bool)
+    for b in range(3):
+        mine = mfd.tap("idxf%d" % (b + 1), B, 100, torch.int32).cpu().numpy().reshape(B, 100, 32)
+        theirs = taps["graph_idx"][b].numpy()
+        # neighbour SETS per point (the max over k does not depend on the order inside a list)
+        diff = np.array([[set(mine[s, i]) != set(theirs[s, i]) for i in range(100)] for s in range(B)])
+        mism["block%d" % (b + 1)] = float(diff.mean())
+        same &= ~diff.any(axis=1)
+    z, z_ref = _inv_softplus5(got), _inv_softplus5(ref)
+    rel_logit = np.abs(z - z_ref) / np.maximum(np.abs(z_ref), 1e-3)
+    rel_dist = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
+    rec = dict(point_lists_differing=mism, patches_with_identical_graphs=int(same.sum()), patches=B,
+               logit_rel_max_identical_graphs=float(rel_logit[same].max()) if same.any() else None,
+               logit_rel_max_all=float(rel_logit.max()), dist_rel_max_all=float(rel_dist.max()))
+    parity_log.record("fd_free_running[%s,%s]" % ("stress" if stress else "default", mode), **rec)
+    print("fd free-running", rec)
+    if same.any():
+        assert rel_logit[same].max() < 1e-3, rec
+    assert rel_logit.max() < 5e-3 and rel_dist.max() < 5e-3, rec
+
+
+def test_benchmarked_mode_at_benchmarked_size(lib, sphere, parity_log):
+    """bench.py times `tc` (and `fast`) on 8,192 seeds with several workspace chunks per forward and persistent multi-wave
+    kernels: here exactly that configuration (workspace cap lowered so that fn AND fd split into several chunks) is
+    compared seed by seed with the oracle-pinned `fp32` mode of the same library."""
+    from sapcu_b200._model_base import NativeModel
+    from sapcu_b200.generation import Generator3D6
+    cloud, seeds = sphere
+    mfn, mfd, _, _ = _models(True)
+    gen = Generator3D6(mfn, mfd, DEV, k_neighbors=100, remove_outliers=False)
+    d_c, d_s = torch.from_numpy(cloud).to(DEV), torch.from_numpy(seeds[:8192]).to(DEV)
+    old = NativeModel.WORKSPACE_CAP
+    res = {}
+    try:
+        NativeModel.WORKSPACE_CAP = 6 << 30                      # ~700 fn patches / ~1000 fd patches per chunk
+        for mode in ("fp32", "tc", "fast"):
+            mfn.set_mode(mode), mfd.set_mode(mode)
+            mfn._ws = mfd._ws = None
+            out, idx, n, d = gen.displace_device(d_c, d_s, return_parts=True)
+            torch.cuda.synchronize()
+            N.check_device("8192-seed pass")
+            res[mode] = (out.cpu().numpy(), n.cpu().numpy(), d.cpu().numpy())
+    finally:
+        NativeModel.WORKSPACE_CAP = old
+        mfn._ws = mfd._ws = None
+    rec = {}
+    for mode in ("tc", "fast"):
+        ang = _angle_deg(res[mode][1], res["fp32"][1])
+        rel = np.abs(res[mode][2] - res["fp32"][2]) / np.maximum(np.abs(res["fp32"][2]), 1e-6)
+        pts = np.abs(res[mode][0] - res["fp32"][0]).max()
+        rec[mode] = dict(normal_angle_deg_max=float(ang.max()), dist_rel_max=float(rel.max()), dist_rel_p999=float(np.quantile(rel, 0.999)),
+                         point_abs_max=float(pts))
+    parity_log.record("vs_fp32_at_8192_seeds_multichunk", **rec)
+    print("8192 seeds, several chunks, vs fp32 mode:", rec)
+    # fd runs free here (own feature-space graphs), so the distance bound is the free-running one
+    assert rec["tc"]["normal_angle_deg_max"] < 0.1 and rec["tc"]["dist_rel_max"] < 5e-3 and rec["tc"]["dist_rel_p999"] < 1e-3, rec
+    assert rec["fast"]["normal_angle_deg_max"] < 0.5 and rec["fast"]["dist_rel_max"] < 5e-2, rec
