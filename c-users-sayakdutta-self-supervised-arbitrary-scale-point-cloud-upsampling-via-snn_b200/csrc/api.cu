@@ -140,9 +140,11 @@ int sapcu_profile_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launch
   return 0;
 }
 
+// fp32 SoA copy of the cloud (3 arrays of round_up(N, 4) + 4 floats, see knn_seed.cu) + one scalar
+static size_t knn_c32_bytes(int64_t N) { return align_up((size_t)(3 * ((N + 3) / 4 * 4 + 4)) * sizeof(float), 256); }
 size_t sapcu_knn_workspace_bytes(int64_t N) {
   if (N < 0) return 0;
-  return align_up((size_t)(4 * N) * sizeof(float), 256) + 256;     // float4 per point + one scalar
+  return knn_c32_bytes(N) + 256;
 }
 
 int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S, int K, int32_t* d_idx,
@@ -154,13 +156,13 @@ int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S
     return SAPCU_EWORKSPACE;
   }
   float* c32 = reinterpret_cast<float*>(d_ws);
-  float* rmax = reinterpret_cast<float*>(reinterpret_cast<char*>(d_ws) + align_up((size_t)(4 * N) * sizeof(float), 256));
+  float* rmax = reinterpret_cast<float*>(reinterpret_cast<char*>(d_ws) + knn_c32_bytes(N));
   return launch_knn_seed(d_cloud, N, d_seeds, S, K, d_idx, c32, rmax, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t sapcu_knn_batched_workspace_bytes(int64_t N_total, int B) {
   if (N_total < 0 || B < 0) return 0;
-  return align_up((size_t)(4 * N_total) * sizeof(float), 256) + 256 + align_up(3 * (size_t)(B + 1) * sizeof(int64_t), 256);
+  return knn_c32_bytes(N_total) + 256 + align_up(3 * (size_t)(B + 1) * sizeof(int64_t), 256);
 }
 
 int sapcu_knn_batched(const double* d_clouds, const int64_t* h_cloud_off, const double* d_seeds, const int64_t* h_seed_off,
@@ -175,8 +177,8 @@ int sapcu_knn_batched(const double* d_clouds, const int64_t* h_cloud_off, const 
   }
   char* w = reinterpret_cast<char*>(d_ws);
   float* c32 = reinterpret_cast<float*>(w);
-  float* rmax = reinterpret_cast<float*>(w + align_up((size_t)(4 * N) * sizeof(float), 256));
-  int64_t* tab = reinterpret_cast<int64_t*>(w + align_up((size_t)(4 * N) * sizeof(float), 256) + 256);
+  float* rmax = reinterpret_cast<float*>(w + knn_c32_bytes(N));
+  int64_t* tab = reinterpret_cast<int64_t*>(w + knn_c32_bytes(N) + 256);
   return launch_knn_seed_batched(d_clouds, h_cloud_off, d_seeds, h_seed_off, B, K, d_idx, c32, rmax, tab,
                                  reinterpret_cast<cudaStream_t>(stream));
 }

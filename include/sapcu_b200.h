@@ -77,7 +77,7 @@ int64_t sapcu_profile_report(char* h_buf, size_t cap);
  *     accumulated as ((dx*dx)+(dy*dy))+(dz*dz) without contraction, ties broken by the lowest
  *     cloud index; d_idx[s*K + j] ascending in distance.  K <= 128, K <= N.
  * ---------------------------------------------------------------------------------- */
-size_t sapcu_knn_workspace_bytes(int64_t N);   /* fp32 copy of the cloud + one scalar */
+size_t sapcu_knn_workspace_bytes(int64_t N);   /* fp32 SoA copy of the cloud + one scalar */
 int sapcu_knn(const double* d_cloud, int64_t N, const double* d_seeds, int64_t S, int K,
               int32_t* d_idx, void* d_ws, size_t ws_bytes, void* stream);
 

@@ -286,7 +286,7 @@ def test_fd_forward_parity(lib, sphere, golden, stress, mode):
     got = mfd(p.to(DEV)).cpu().numpy()
     rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
     print("fd %s/%s: teacher-forced max rel %.2e, free-running max rel %.2e" % (tag, mode, rel_tf.max(), rel.max()))
-    assert rel.max() < 5e-3
+    assert rel.max() < 1e-3
     assert (got >= 0).all()
 
 
@@ -980,9 +980,8 @@ def test_fd_free_running_logits_and_graph_mismatch(lib, sphere, parity_log, stre
                logit_rel_max_all=float(rel_logit.max()), dist_rel_max_all=float(rel_dist.max()))
     parity_log.record("fd_free_running[%s,%s]" % ("stress" if stress else "default", mode), **rec)
     print("fd free-running", rec)
-    if same.any():
-        assert rel_logit[same].max() < 1e-3, rec
-    assert rel_logit.max() < 5e-3 and rel_dist.max() < 5e-3, rec
+    # measured (profiles/r02_parity.json): <= 4e-5 on every patch, <= 2e-6 on patches with identical graphs
+    assert rel_logit.max() < 1e-3 and rel_dist.max() < 1e-3, rec
 
 
 def test_benchmarked_mode_at_benchmarked_size(lib, sphere, parity_log):
@@ -1019,5 +1018,5 @@ def test_benchmarked_mode_at_benchmarked_size(lib, sphere, parity_log):
     parity_log.record("vs_fp32_at_8192_seeds_multichunk", **rec)
     print("8192 seeds, several chunks, vs fp32 mode:", rec)
     # fd runs free here (own feature-space graphs), so the distance bound is the free-running one
-    assert rec["tc"]["normal_angle_deg_max"] < 0.1 and rec["tc"]["dist_rel_max"] < 5e-3 and rec["tc"]["dist_rel_p999"] < 1e-3, rec
+    assert rec["tc"]["normal_angle_deg_max"] < 0.1 and rec["tc"]["dist_rel_max"] < 2e-3 and rec["tc"]["dist_rel_p999"] < 1e-3, rec
     assert rec["fast"]["normal_angle_deg_max"] < 0.5 and rec["fast"]["dist_rel_max"] < 5e-2, rec
