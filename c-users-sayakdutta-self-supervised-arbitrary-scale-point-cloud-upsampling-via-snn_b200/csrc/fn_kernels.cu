@@ -137,12 +137,14 @@ edge_pos_lif_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ i
 // offsets are expanded into shared memory, and 4 threads per channel walk the edges (lane = channel, so a warp's 32 stores
 // of a row are 64 contiguous bytes).  LTAB = 0: no usable table -- the reduced-MUFU recurrence instead.
 constexpr int EPF_THREADS = 512;
-template <int LTAB, int CT>     // CT: compile-time channel count (row stride of the output: store offsets become immediates), 0 = run-time
+// PL2: also write the lo plane (y * 2^13 - hi) `plane` halfs behind the hi plane -- the (hi, lo) hand-over format of the
+// parity-grade tensor-core mode, whose LIF^T chains may use the same tables.
+template <int LTAB, int CT, int PL2 = 0>     // CT: compile-time channel count (row stride of the output: store offsets become immediates), 0 = run-time
 __global__ void __launch_bounds__(EPF_THREADS)
 edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int kk, int ldi, int Mpts, int C_rt,
                          int64_t S, const float* __restrict__ W, const float* __restrict__ bias,
                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ np,
-                         int T, __half* __restrict__ out, const uint8_t* __restrict__ tab, uint32_t tab_stride) {
+                         int T, __half* __restrict__ out, const uint8_t* __restrict__ tab, uint32_t tab_stride, int64_t plane) {
   extern __shared__ __align__(16) uint8_t epf_sm[];
   const int C = CT ? CT : C_rt;
   const int EP = Mpts * kk;
@@ -201,7 +203,12 @@ edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restric
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (full || e0 + j < EP) o[j * C] = __float2half_rn(u[j] * 8192.0f);
+        if (full || e0 + j < EP) {
+          const float ys = u[j] * 8192.0f;
+          const __half hv = __float2half_rn(ys);
+          o[j * C] = hv;
+          if (PL2) o[plane + j * C] = __float2half_rn(ys - __half2float(hv));
+        }
       o += 16 * C;
     };
     const int EPfull = EP & ~15;                                               // whole rounds of 4 phases x 4 edges: no bounds checks
@@ -397,7 +404,7 @@ int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32
 // fast mode: single fp16 plane out, tabulated chain when `tab` is usable
 int launch_edge_pos_lif_fast(const float* xyz, const int32_t* idx, int kk, int ldi, int Mpts, int64_t rows, int C,
                              const float* W, const float* bias, const float* scale, const float* shift, const float* np, int T,
-                             float* out_h, const float* tab, uint32_t tab_stride, cudaStream_t st) {
+                             float* out_h, const float* tab, uint32_t tab_stride, cudaStream_t st, bool two_planes) {
   if (rows == 0) return 0;
   SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256 && kk >= 1 && rows % ((int64_t)Mpts * kk) == 0, "edge_pos_lif_fast: edge rows must be whole patches of <= 256 points");
   const int64_t S = rows / ((int64_t)Mpts * kk);
@@ -407,7 +414,8 @@ int launch_edge_pos_lif_fast(const float* xyz, const int32_t* idx, int kk, int l
   static PerDeviceOnce once;
   {
     const int rc = once.run([]() -> int {
-#define SAPCU_EPF_ATTR(L, CQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<L, CQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024))
+#define SAPCU_EPF_ATTR(L, CQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<L, CQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(edge_pos_lif_fast_kernel<L, CQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024))
       SAPCU_EPF_ATTR(0, 0); SAPCU_EPF_ATTR(1, 0); SAPCU_EPF_ATTR(0, 128); SAPCU_EPF_ATTR(1, 128); SAPCU_EPF_ATTR(0, 256); SAPCU_EPF_ATTR(1, 256);
       SAPCU_EPF_ATTR(0, 512); SAPCU_EPF_ATTR(1, 512);
 #undef SAPCU_EPF_ATTR
@@ -419,6 +427,7 @@ int launch_edge_pos_lif_fast(const float* xyz, const int32_t* idx, int kk, int l
   const uint8_t* tabp = lt ? reinterpret_cast<const uint8_t*>(tab) : nullptr;
   const uint32_t tstride = lt ? tab_stride : 0;
   __half* outp = reinterpret_cast<__half*>(out_h);
+  const int64_t plane = rows * (int64_t)C;
 #define SAPCU_EPF_GO(L, CQ)                                                                                             \
   do {                                                                                                                  \
     int occ = 1;                                                                                                        \
@@ -427,8 +436,10 @@ int launch_edge_pos_lif_fast(const float* xyz, const int32_t* idx, int kk, int l
     int64_t gx = ((int64_t)kNumSMs * occ + nblk - 1) / nblk;                                                            \
     if (gx > S) gx = S;                                                                                                 \
     dim3 grid((unsigned)gx, (unsigned)nblk);                                                                            \
-    edge_pos_lif_fast_kernel<L, CQ><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T, \
-                                                                     outp, tabp, tstride);                              \
+    if (two_planes) edge_pos_lif_fast_kernel<L, CQ, 1><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T, \
+                                                                                       outp, tabp, tstride, plane);     \
+    else edge_pos_lif_fast_kernel<L, CQ><<<grid, EPF_THREADS, smem, st>>>(xyz, idx, kk, ldi, Mpts, C, S, W, bias, scale, shift, np, T, \
+                                                                          outp, tabp, tstride, plane);                  \
   } while (0)
   if (lt) { if (C == 128) SAPCU_EPF_GO(1, 128); else if (C == 256) SAPCU_EPF_GO(1, 256); else if (C == 512) SAPCU_EPF_GO(1, 512); else SAPCU_EPF_GO(1, 0); }
   else { if (C == 128) SAPCU_EPF_GO(0, 128); else if (C == 256) SAPCU_EPF_GO(0, 256); else if (C == 512) SAPCU_EPF_GO(0, 512); else SAPCU_EPF_GO(0, 0); }

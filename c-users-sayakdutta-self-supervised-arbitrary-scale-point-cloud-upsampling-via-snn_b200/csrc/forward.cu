@@ -13,6 +13,7 @@
 #include "gemm_tc.h"
 #include "kernels.h"
 #include "model.h"
+#include "lif_table.cuh"
 
 using namespace sapcu;
 
@@ -198,8 +199,8 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
   // second; 4 only pos (fc_delta2 -> fc_gamma + attention tail); 5 all three.  The pos planes are measured slower (the
   // attention tail then issues two 2-byte loads per operand instead of one 4-byte load) and stay off.
   const int h2_env = settings().h2_planes;
-  const bool h2_delta = h2_env == 1 || h2_env == 2 || h2_env == 5, h2_gamma = h2_env == 1 || h2_env == 3 || h2_env == 5,
-             h2_pos = h2_env == 4 || h2_env == 5;
+  const bool h2_delta_env = h2_env == 1 || h2_env == 2 || h2_env == 5, h2_gamma_env = h2_env == 1 || h2_env == 3 || h2_env == 5,
+             h2_pos_env = h2_env == 4 || h2_env == 5;
   for (int b = 0; b < 3; ++b) {
     if (stop_block && b >= stop_block) return 0;            // debug: leave block `stop_block`'s intermediates in the workspace
     const FnBlock& k = f.blk[b];
@@ -253,6 +254,13 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         continue;
       }
     }
+    // Parity-grade mode with tabulated LIF^T chains (SAPCU_TC_LIF_TABLES, default on): the three per-edge LIF layers of a block
+    // whose tables fit next to two pipeline stages read their chains from the tables (lif_table.cuh, |error| <= 4e-5, far
+    // inside the spike tolerance); all three edge tensors are then handed over as fp16 (hi, lo) planes.
+    const bool blk_tab = mode == SAPCU_MODE_TC && settings().tc_tables && factorise && kk >= 2 &&
+                         k.snn_delta.tab_ok && k.snn_delta2.tab_ok && k.snn_gamma.tab_ok && k.snn_delta.tab_stride <= LT_SMEM_BUDGET &&
+                         k.snn_delta2.tab_stride <= LT_SMEM_BUDGET_TC && k.snn_gamma.tab_stride <= LT_SMEM_BUDGET_TC;
+    const bool h2_delta = blk_tab || h2_delta_env, h2_gamma = blk_tab || h2_gamma_env, h2_pos = blk_tab || h2_pos_env;
     if (mode != SAPCU_MODE_FP32) {
       // fc_delta2 on the pos-enc layer-1 spikes.  When it runs on the fp16x3 path, edge_pos_lif hands the spikes over as
       // fp16 (hi, lo) planes of x * 2^13 (same bytes as fp32) and the contraction loads them without converting.
@@ -272,7 +280,16 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         }
         a.out_h2 = e2_h2;
         g_tap_delta2_h2 = e2_h2 ? 1 : 0;
-        SAPCU_TRY(edge_pos(b, Xb, st, 1, a.x_h2));
+        const bool tab_on = blk_tab && a.x_h2 && e2_h2;           // the whole chain of plane hand-overs is in place
+        if (tab_on) {
+          ProfWork w; w.elsteps = (double)E * D * 4; w.bytes = (double)E * D * 4.0;
+          SAPCU_PROF(st, "fn.fc_delta(K=3)+lif (edge_pos_lif)", w,
+                     launch_edge_pos_lif_fast(xyz, p.idx, kk, p.kmax, M, E, D, k.fc_delta.W, k.fc_delta.bias, k.fc_delta.scale,
+                                              k.fc_delta.shift, k.snn_delta.np, 4, Xb, k.snn_delta.tab, k.snn_delta.tab_stride, st, true));
+          a.lif_tab = k.snn_delta2.tab; a.lif_tab_stride = k.snn_delta2.tab_stride;
+        } else {
+          SAPCU_TRY(edge_pos(b, Xb, st, 1, a.x_h2));
+        }
         SAPCU_TRY(g.L("fn.fc_delta2+lif").run(a, A_PLAIN));
       }
       {
@@ -285,6 +302,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         }
         a.out_h2 = xb_h2; a.x_h2 = e2_h2;
         g_tap_gamma_h2 = xb_h2 ? 1 : 0;
+        if (blk_tab && e2_h2 && xb_h2) { a.lif_tab = k.snn_gamma.tab; a.lif_tab_stride = k.snn_gamma.tab_stride; }
         if (factorise && kk >= 2 && (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN))) {
           Layer Lw = k.fc_gamma;
           Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;

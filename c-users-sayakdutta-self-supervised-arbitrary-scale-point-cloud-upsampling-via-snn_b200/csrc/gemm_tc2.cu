@@ -115,7 +115,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   constexpr bool H16 = HM == 1 || HM == 2 || HM == 3;        // fp16 operands (HM == 4: single-pass TF32 on fp32 activations)
   constexpr int CW = CG * 128;                               // output channels per tile
   constexpr bool FASTOP = HM == 3 || HM == 4;               // compact stages: one weight tile + one activation tile
-  constexpr int T2_STAGES = HM == 1 ? 2 : (FASTOP && !LT) ? 4 : (FASTOP && CG == 1) ? 2 : 3;
+  constexpr int T2_STAGES = HM == 1 ? 2 : (FASTOP && !LT) ? 4 : (FASTOP && CG == 1) ? 2 : (!FASTOP && LT) ? 2 : 3;   // HM 2 + table: 2 x 64 KiB
   constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : FASTOP ? (CG == 2 ? 2 : 3) : 4) * TC_TILE_BYTES;   // HM 3/4: W tile + 128 (pair) or 256 activation rows
   constexpr uint32_t X_TILE = FASTOP ? 1 : 2;               // position of the activation (hi) tile inside a stage
   constexpr int BKE = H16 ? 64 : TC_BK;                    // k elements per stage
@@ -617,6 +617,9 @@ int t2_set_attrs_impl() {
   SAPCU_T2_ATTR_H(ACT_NONE, 3, 12); SAPCU_T2_ATTR_H(ACT_NONE, 3, 18); SAPCU_T2_ATTR_H(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_H
 #define SAPCU_T2_ATTR_P(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
+  // parity-grade mode with tabulated LIF^T chains: two 64 KiB stages + the table
+  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 0, 1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * TC_TILE_BYTES + 1024 + 256 + LT_SMEM_BUDGET_TC)));
+  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 2, 1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * TC_TILE_BYTES + 1024 + 256 + LT_SMEM_BUDGET_TC)));
   SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_LIF, 2, 1); SAPCU_T2_ATTR_P(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
 #undef SAPCU_T2_ATTR_P
 #define SAPCU_T2_ATTR_F(A, X, KQ, LTQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 3, LTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_fast(LTQ != 0, LT_SMEM_BUDGET)))
@@ -728,6 +731,17 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   const int grid = 2 * pairs;
 #define SAPCU_T2_LAUNCH_H(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 1><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
 #define SAPCU_T2_LAUNCH_P(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 2><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
+  if (pre && g.act == ACT_LIF && g.lif_tab && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET_TC) {
+    // fp16x3 products on (hi, lo) planes + the layer's tabulated LIF^T chain: 2 stages of 64 KiB leave room for the table
+    pairs = (pairs / p.m_tiles) * p.m_tiles;
+    SAPCU_REQUIRE(pairs >= 1, "gemm_tc2(tables): empty grid");
+    p.lif_tab = reinterpret_cast<const uint8_t*>(g.lif_tab); p.lif_tab_stride = g.lif_tab_stride;
+    const size_t smem = 2 * 4 * (size_t)TC_TILE_BYTES + 1024 + 256 + g.lif_tab_stride;
+    if (g.edge_bias) gemm_tc2_kernel<ACT_LIF, 2, 1, 2, 1><<<2 * pairs, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p);
+    else gemm_tc2_kernel<ACT_LIF, 0, 1, 2, 1><<<2 * pairs, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p);
+    SAPCU_LAUNCH_CHECK();
+    return 0;
+  }
   if (pre) {
     if (g.at_pos) {
       if (g.kk == 12) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH_P(ACT_NONE, 3, 24);

@@ -25,7 +25,7 @@ int launch_pointwise3_lif(bool edge, bool precise, const float* xyz, const int32
                           const float* shift, const float* np, int T, float* out, cudaStream_t st, int nsplit = 1, bool out_h2 = false);
 int launch_edge_pos_lif_fast(const float* xyz, const int32_t* idx, int kk, int ldi, int Mpts, int64_t rows, int C,
                              const float* W, const float* bias, const float* scale, const float* shift, const float* np, int T,
-                             float* out_h, const float* tab, uint32_t tab_stride, cudaStream_t st);
+                             float* out_h, const float* tab, uint32_t tab_stride, cudaStream_t st, bool two_planes = false);
 int launch_pack_idx_u8(const int32_t* idx, int ldi, int64_t P, uint32_t* out, cudaStream_t st);
 int launch_attn_out(bool precise, const float* logits, const float* pos, const float* V, int64_t ldv,
                     const int32_t* idx, int ldi, int kk, int Mpts, int64_t P, int D, float sqrt_hd, float* out,

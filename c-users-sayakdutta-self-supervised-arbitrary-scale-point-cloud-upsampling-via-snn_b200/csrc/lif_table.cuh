@@ -35,6 +35,7 @@ constexpr int LT_CH = 128;                   // channels per block (= UMMA M per
 constexpr uint32_t LT_DESC_BYTES = LT_CH * LT_NCELL * 8;
 constexpr double LT_TOL = 4e-5;              // acceptance bound of the fit, absolute, on soft spikes in (0, 0.7)
 constexpr uint32_t LT_SMEM_BUDGET = 120 * 1024;   // a block above this keeps its layer on the MUFU path
+constexpr uint32_t LT_SMEM_BUDGET_TC = 96 * 1024; // same next to the two 64 KiB stages of the parity-grade (fp16x3) kernels
 
 struct LifTableBlock { size_t off_bytes = 0; uint32_t bytes = 0; uint32_t nseg = 0; };
 struct LifTableHost {
