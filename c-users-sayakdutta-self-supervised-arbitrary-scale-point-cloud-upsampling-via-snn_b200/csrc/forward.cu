@@ -271,12 +271,14 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         a.bias = L.bias; a.scale = L.scale; a.shift = L.shift; a.act = ACT_LIF; a.T = 4; a.nparams = k.snn_delta2.np;
         a.Y = p.E2; a.ldc = D; a.Wh = L.Wh; a.Wl = L.Wl; a.winv = L.winv; a.x_unit = true;   // input: LIF output
         a.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
+        a.x_h2 = true;                                              // tentatively: 128-channel layers run on the 2-CTA engine only from planes
         a.x_h2 = h2_delta && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_fp16x3(a);
         {   // pos (E2) has two readers, fc_gamma's contraction and the fused attention tail: planes when both take them
           GemmArgs a1 = gamma_args(b, p.E2, Xb, p.E3), a2 = gamma2_args(b, Xb, p.E2);
           a1.tc_passes = a2.tc_passes = a.tc_passes;
-          e2_h2 = h2_pos && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a1, A_PLAIN) &&
-                  gemm_tc2_fp16x3(a1) && gemm_tc2_supported(a2, A_PLAIN);
+          a1.x_h2 = a2.x_h2 = a2.pos_h2 = true;                    // the formats this hand-over would give them
+          e2_h2 = h2_pos && a.x_h2 && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a1, A_PLAIN) &&
+                  gemm_tc2_fp16x3(a1) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fp16x3(a2);
         }
         a.out_h2 = e2_h2;
         g_tap_delta2_h2 = e2_h2 ? 1 : 0;
@@ -298,7 +300,9 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         a.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
         {   // fc_gamma's spikes go to fc_gamma2 only: hand them over as fp16 planes when both run on the 2-CTA fp16x3 path
           GemmArgs a2 = gamma2_args(b, Xb, p.E2);
-          xb_h2 = h2_gamma && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fp16x3(a2);
+          a2.x_h2 = true; a2.pos_h2 = e2_h2;
+          GemmArgs at = a; at.x_h2 = e2_h2;
+          xb_h2 = h2_gamma && factorise && kk >= 2 && gemm_tc2_supported(at, A_PLAIN) && gemm_tc2_supported(a2, A_PLAIN) && gemm_tc2_fp16x3(a2);
         }
         a.out_h2 = xb_h2; a.x_h2 = e2_h2;
         g_tap_gamma_h2 = xb_h2 ? 1 : 0;

@@ -111,13 +111,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   // HM: 0 = 3xTF32; 1 = fp16x3, raw fp32 activations converted by the splitter warps; 2 = fp16x3, activations already
   // stored as fp16 (hi, lo) planes of x * 2^13 by the kernel that produced them (map_x = hi plane, map_x2 = lo plane): four
   // TMA loads per stage, no conversion, no raw staging -- a third less shared-memory traffic per k-block
-  static_assert(CG == 2 || HM == 3 || HM == 4, "the single-CTA flavour exists for the fast mode's operand formats only");
+  static_assert(CG == 2 || HM >= 2, "the single-CTA flavour takes ready-made operands only (fp16 planes, or the fast mode's formats)");
   constexpr bool H16 = HM == 1 || HM == 2 || HM == 3;        // fp16 operands (HM == 4: single-pass TF32 on fp32 activations)
   constexpr int CW = CG * 128;                               // output channels per tile
   constexpr bool FASTOP = HM == 3 || HM == 4;               // compact stages: one weight tile + one activation tile
-  constexpr int T2_STAGES = HM == 1 ? 2 : (FASTOP && !LT) ? 4 : (FASTOP && CG == 1) ? 2 : (!FASTOP && LT) ? 2 : 3;   // HM 2 + table: 2 x 64 KiB
-  constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : FASTOP ? (CG == 2 ? 2 : 3) : 4) * TC_TILE_BYTES;   // HM 3/4: W tile + 128 (pair) or 256 activation rows
+  // stages: HM 2 (two fp16 planes per operand, 64 KiB per stage for a pair, 96 KiB single-CTA): 3 / 2 plain, 2 / 1 next to a LIF table
+  constexpr int T2_STAGES = HM == 1 ? 2 : (FASTOP && !LT) ? 4 : (FASTOP && CG == 1) ? 2 : FASTOP ? 3 : (CG == 2 ? (LT ? 2 : 3) : (LT ? 1 : 2));
+  constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : FASTOP ? (CG == 2 ? 2 : 3) : (CG == 2 ? 4 : 6)) * TC_TILE_BYTES;   // HM 3/4: W tile + 128 (pair) or 256 activation rows
   constexpr uint32_t X_TILE = FASTOP ? 1 : 2;               // position of the activation (hi) tile inside a stage
+  constexpr uint32_t X_LO_OFF = (CG == 2 ? 3 : 4) * TC_TILE_BYTES;   // lo activation tile (HM 0..2): behind the hi tile of 128 / 256 rows
   constexpr int BKE = H16 ? 64 : TC_BK;                    // k elements per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -187,11 +189,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // fp16 tiles: 64 halfs x 128 weight rows, x HALF activation rows
             tma_load_2d(st + TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
           } else if (HM == 2) {
-            mbar_expect_tx(bar_raw(s), 4 * TC_TILE_BYTES);
-            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // four fp16 tiles: 64 halfs x 128 rows
+            mbar_expect_tx(bar_raw(s), T2_STAGE_BYTES);
+            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // four fp16 tiles: 64 halfs x 128 (256 single-CTA) rows
             tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * BKE, wrow);
             tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
-            tma_load_2d(st + 3 * TC_TILE_BYTES, &map_x2, bar_raw(s), kb * BKE, xrow);
+            tma_load_2d(st + X_LO_OFF, &map_x2, bar_raw(s), kb * BKE, xrow);
           } else if (H16) {
             mbar_expect_tx(bar_raw(s), 4 * TC_TILE_BYTES);
             tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // fp16 tiles: 64 halfs x 128 rows
@@ -221,7 +223,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           tc_fence_after();
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
           const uint64_t w_hi = umma_desc_sw128(st), w_lo = umma_desc_sw128(st + TC_TILE_BYTES);
-          const uint64_t x_hi = umma_desc_sw128(st + X_TILE * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+          const uint64_t x_hi = umma_desc_sw128(st + X_TILE * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + X_LO_OFF);
           if (HM == 4) {                                         // single-pass TF32 on raw fp32 activations (8 floats = 32 B per MMA)
 #pragma unroll
             for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
@@ -238,9 +240,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {                       // 16 halfs = 32 B = 2 x 16 B along the swizzled row
               const uint64_t adv = (uint64_t)(ks * 2);
-              umma_f16_2cta(tmem_d, w_lo + adv, x_hi + adv, idesc, (kb | ks) ? 1u : 0u);
-              umma_f16_2cta(tmem_d, w_hi + adv, x_lo + adv, idesc, 1u);
-              umma_f16_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
+              if (CG == 2) {
+                umma_f16_2cta(tmem_d, w_lo + adv, x_hi + adv, idesc, (kb | ks) ? 1u : 0u);
+                umma_f16_2cta(tmem_d, w_hi + adv, x_lo + adv, idesc, 1u);
+                umma_f16_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
+              } else {
+                umma_f16_1cta(tmem_d, w_lo + adv, x_hi + adv, idesc, (kb | ks) ? 1u : 0u);
+                umma_f16_1cta(tmem_d, w_hi + adv, x_lo + adv, idesc, 1u);
+                umma_f16_1cta(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
+              }
             }
           } else
 #pragma unroll
@@ -333,7 +341,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     const int part = (warp - T2_EPI_WARP0) >> 2;
     int a = 0; uint32_t aph = 0; bool ok = true;
     // LT: this CTA's 128-channel block of the tabulated LIF^T chain -> shared memory (behind the barriers), once
-    const uint2* lt_desc = nullptr; const float4* lt_coef = nullptr;
+    uint32_t lt_desc = 0, lt_coef = 0;                           // shared-memory addresses: this lane's descriptor column, the coefficients
     if (LT) {
       const int blk = (int)(pair % p.m_tiles) * CG + (int)rank;       // the host keeps npairs a multiple of m_tiles: fixed channel block
       uint8_t* tsm = smem_gen + T2_STAGES * T2_STAGE_BYTES + 256;
@@ -341,8 +349,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
       uint4* dst = reinterpret_cast<uint4*>(tsm);
       for (uint32_t i = threadIdx.x - T2_EPI_WARP0 * 32; i < p.lif_tab_stride / 16; i += T2_EPI * 32) dst[i] = src[i];
       asm volatile("bar.sync 1, %0;" ::"r"(T2_EPI * 32) : "memory");
-      lt_desc = reinterpret_cast<const uint2*>(tsm) + (q * 32 + lane);
-      lt_coef = reinterpret_cast<const float4*>(tsm + LT_DESC_BYTES);
+      lt_desc = smem_u32(tsm) + (uint32_t)(q * 32 + lane) * 8u;
+      lt_coef = smem_u32(tsm) + LT_DESC_BYTES;
     }
     for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
       const int m_t = (int)(t % p.m_tiles);
@@ -417,10 +425,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
               float x0[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) x0[j] = u[j];
-              const uint32_t oob = lif_table_eval_vec<8>(u, lt_desc, lt_coef);
-              if (oob) {                                          // |x| >= 255: the exact chain
+              if (lif_table_eval_vec<8>(u, lt_desc, lt_coef)) {   // some |x| >= 255 (or NaN): the exact chain for those
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (oob & (1u << j)) u[j] = lif_chain<false>(x0[j] + np.th0, np, p.T);
+                for (int j = 0; j < 8; ++j) if (lif_table_oob(x0[j])) u[j] = lif_chain<false>(x0[j] + np.th0, np, p.T);
               }
             } else {
 #pragma unroll
@@ -569,7 +576,8 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   base.at_pos = nullptr; base.pool = nullptr; base.x_h2 = false; base.out_h2 = false; base.pos_h2 = false;
   if (!enabled || !gemm_tc_supported(base, amode)) return false;
   if (g.act == ACT_GELU) return false;
-  if (g.N % 256 != 0 && !(g.N % 128 == 0 && (gemm_tc2_fast(g) || gemm_tc2_fast_tf32(g)))) return false;   // single-CTA flavour: fast mode only
+  // 128-channel layers: the single-CTA flavour takes ready-made operands only (fp16 planes of the parity-grade mode, fast-mode formats)
+  if (g.N % 256 != 0 && !(g.N % 128 == 0 && (gemm_tc2_fast(g) || gemm_tc2_fast_tf32(g) || (g.x_h2 && gemm_tc2_fp16x3(g))))) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
   if (g.R < 4096) return false;
   if (g.pool) {
@@ -630,6 +638,11 @@ int t2_set_attrs_impl() {
   SAPCU_T2_ATTR_F1(ACT_LIF, 0, 1, 0); SAPCU_T2_ATTR_F1(ACT_LIF, 0, 1, 1); SAPCU_T2_ATTR_F1(ACT_LIF, 2, 1, 0); SAPCU_T2_ATTR_F1(ACT_LIF, 2, 1, 1);
   SAPCU_T2_ATTR_F1(ACT_NONE, 3, 12, 0); SAPCU_T2_ATTR_F1(ACT_NONE, 3, 18, 0); SAPCU_T2_ATTR_F1(ACT_NONE, 3, 24, 0);
 #undef SAPCU_T2_ATTR_F1
+  // single-CTA flavour on (hi, lo) planes: 2 stages of 96 KiB, or 1 stage + the LIF table
+#define SAPCU_T2_ATTR_P1(A, X, KQ, LTQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 2, LTQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((LTQ ? 1 : 2) * 6 * TC_TILE_BYTES + 1024 + 256 + (LTQ ? LT_SMEM_BUDGET : 0))))
+  SAPCU_T2_ATTR_P1(ACT_LIF, 0, 1, 0); SAPCU_T2_ATTR_P1(ACT_LIF, 0, 1, 1); SAPCU_T2_ATTR_P1(ACT_LIF, 2, 1, 0); SAPCU_T2_ATTR_P1(ACT_LIF, 2, 1, 1);
+  SAPCU_T2_ATTR_P1(ACT_NONE, 3, 12, 0); SAPCU_T2_ATTR_P1(ACT_NONE, 3, 18, 0); SAPCU_T2_ATTR_P1(ACT_NONE, 3, 24, 0);
+#undef SAPCU_T2_ATTR_P1
 #define SAPCU_T2_ATTR_T(LTQ, CGQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 0, 1, 4, LTQ, CGQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_fast(LTQ != 0, LT_SMEM_BUDGET, CGQ)))
   SAPCU_T2_ATTR_T(0, 1); SAPCU_T2_ATTR_T(1, 1); SAPCU_T2_ATTR_T(0, 2); SAPCU_T2_ATTR_T(1, 2);
 #undef SAPCU_T2_ATTR_T
@@ -664,7 +677,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     const uint16_t* hp = reinterpret_cast<const uint16_t*>(g.A);
     rc = tc_make_map_f16(&mx, hp, g.R, g.K, T2_BN / cg);
     if (rc) return rc;
-    rc = fast ? 0 : tc_make_map_f16(&mx2, hp + g.R * g.K, g.R, g.K, T2_BN / 2);
+    rc = fast ? 0 : tc_make_map_f16(&mx2, hp + g.R * g.K, g.R, g.K, T2_BN / cg);
     if (rc) return rc;
     if (fast) mx2 = mx;
   } else {
@@ -731,6 +744,22 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   const int grid = 2 * pairs;
 #define SAPCU_T2_LAUNCH_H(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 1><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
 #define SAPCU_T2_LAUNCH_P(A, X, KQ) gemm_tc2_kernel<A, X, KQ, 2><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
+  if (pre && cg == 1) {
+    // 128-channel layer on (hi, lo) planes: the single-CTA flavour (fp16x3 products; LIF table next to ONE 96 KiB stage)
+    SAPCU_REQUIRE(g.at_pos || g.act == ACT_LIF, "gemm_tc2: the single-CTA plane path serves the LIF layers and the attention tail");
+    const bool lt = g.act == ACT_LIF && g.lif_tab && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET;
+    if (lt) { pairs = (pairs / p.m_tiles) * p.m_tiles; p.lif_tab = reinterpret_cast<const uint8_t*>(g.lif_tab); p.lif_tab_stride = g.lif_tab_stride; }
+    SAPCU_REQUIRE(pairs >= 1, "gemm_tc2(single-CTA planes): empty grid");
+    const size_t smem = (size_t)(lt ? 1 : 2) * 6 * TC_TILE_BYTES + 1024 + 256 + (lt ? g.lif_tab_stride : 0);
+#define SAPCU_T2_LAUNCH_P1(A, X, KQ, LTQ) gemm_tc2_kernel<A, X, KQ, 2, LTQ, 1><<<pairs, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p)
+    if (g.at_pos) {
+      if (g.kk == 12) SAPCU_T2_LAUNCH_P1(ACT_NONE, 3, 12, 0); else if (g.kk == 18) SAPCU_T2_LAUNCH_P1(ACT_NONE, 3, 18, 0); else SAPCU_T2_LAUNCH_P1(ACT_NONE, 3, 24, 0);
+    } else if (g.edge_bias) { if (lt) SAPCU_T2_LAUNCH_P1(ACT_LIF, 2, 1, 1); else SAPCU_T2_LAUNCH_P1(ACT_LIF, 2, 1, 0); }
+    else { if (lt) SAPCU_T2_LAUNCH_P1(ACT_LIF, 0, 1, 1); else SAPCU_T2_LAUNCH_P1(ACT_LIF, 0, 1, 0); }
+#undef SAPCU_T2_LAUNCH_P1
+    SAPCU_LAUNCH_CHECK();
+    return 0;
+  }
   if (pre && g.act == ACT_LIF && g.lif_tab && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET_TC) {
     // fp16x3 products on (hi, lo) planes + the layer's tabulated LIF^T chain: 2 stages of 64 KiB leave room for the table
     pairs = (pairs / p.m_tiles) * p.m_tiles;

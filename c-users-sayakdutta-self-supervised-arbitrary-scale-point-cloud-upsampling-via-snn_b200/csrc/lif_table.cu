@@ -61,23 +61,22 @@ struct Cheb {
 };
 static const Cheb g_cheb;
 
-// cubic on [y0, y0 + w) of side `sgn`; returns the largest deviation from the exact chain at 9 check points
+// cubic in t in [0, 1] on the segment y in [y0, y0 + w) (y = 2|x| + 2) of side `sgn`; returns the largest deviation from the
+// exact chain at 9 check points, evaluated with the device's fp32 Horner form
 double fit_segment(double sgn, double y0, double w, double d, double a, double r, double th0, int T, float (&c)[4]) {
+  auto u_of = [&](double y) { return th0 + sgn * (y * 0.5 - 1.0); };
   double f[4];
-  for (int i = 0; i < 4; ++i) f[i] = lif_chain_exact_host(th0 + sgn * (y0 + w * g_cheb.t[i] - 1.0), d, a, r, th0, T);
-  double co[4];
-  double wp = 1.0;
+  for (int i = 0; i < 4; ++i) f[i] = lif_chain_exact_host(u_of(y0 + w * g_cheb.t[i]), d, a, r, th0, T);
   for (int j = 0; j < 4; ++j) {
     double s = 0.0;
     for (int i = 0; i < 4; ++i) s += g_cheb.inv[j][i] * f[i];
-    co[j] = s / wp; wp *= w;
-    c[j] = (float)co[j];
+    c[j] = (float)s;
   }
   double worst = 0.0;
   for (int q = 0; q <= 8; ++q) {
-    const float tau = (float)(w * (q == 8 ? 0.999999 : q / 8.0));
-    const float p = fmaf(fmaf(fmaf(c[3], tau, c[2]), tau, c[1]), tau, c[0]);     // the device's Horner form, in fp32
-    const double e = fabs((double)p - lif_chain_exact_host(th0 + sgn * (y0 + (double)tau - 1.0), d, a, r, th0, T));
+    const float t = (float)(q / 8.0);
+    const float p = fmaf(fmaf(fmaf(c[3], t, c[2]), t, c[1]), t, c[0]);
+    const double e = fabs((double)p - lif_chain_exact_host(u_of(y0 + w * (double)t), d, a, r, th0, T));
     worst = e > worst ? e : worst;
   }
   return worst;
@@ -88,8 +87,10 @@ void build_channel(double d, double a, double r, double th0, int T, ChanTab* out
   std::vector<std::array<float, 4>> best;
   for (int side = 0; side < 2; ++side) {
     const double sgn = side ? -1.0 : 1.0;
+    // guard segment: the constant F(theta0), reached only by the downward tie at the very start of the side's first cell
+    out->coef.push_back({(float)lif_chain_exact_host(th0, d, a, r, th0, T), 0.0f, 0.0f, 0.0f});
     for (int e = 0; e < LT_NB; ++e) {
-      const double y0 = ldexp(1.0, e), cw = y0;       // cell [2^e, 2^(e+1))
+      const double y0 = ldexp(1.0, e + 1), cw = y0;   // cell: y = 2|x| + 2 in [2^(e+1), 2^(e+2))
       int k = 0; double kerr = 0.0;
       for (; k <= LT_KMAX; ++k) {
         const int n = 1 << k;
@@ -163,10 +164,13 @@ void lif_table_build(const float* np4, int C, int T, LifTableHost* out) {
       out->max_err = t.err > out->max_err ? t.err : out->max_err;
       uint32_t base = first[w];
       for (int cell = 0; cell < LT_NCELL; ++cell) {
-        // bits(y) >> (23 - k) = (E << k) + segment-in-cell with E = 127 + binade: fold -(E << k) into the byte offset
-        const int k = t.k[cell], E = 127 + cell % LT_NB;
-        desc[2 * (cell * LT_CH + cl)] = (uint32_t)(23 - k);
-        desc[2 * (cell * LT_CH + cl) + 1] = (uint32_t)(16 * ((int)base - (E << k)));
+        // bits(qm) = 0x4B000000 + floor(y * S) with floor(y * S) = 2^k + segment-in-cell: fold both constants into the offset
+        const int k = t.k[cell], e = cell % LT_NB;
+        if (e == 0) base += 1;                                           // the side's guard segment
+        const float S = (float)ldexp(1.0, k - e - 1);
+        uint32_t Sb; memcpy(&Sb, &S, 4);
+        desc[2 * (cell * LT_CH + cl)] = Sb;
+        desc[2 * (cell * LT_CH + cl) + 1] = 16u * (base - (0x4B000000u + (1u << k)));
         base += 1u << k;
       }
       memcpy(coef + 4 * (size_t)first[w], t.coef.data(), t.coef.size() * 16);

@@ -6,21 +6,25 @@
 // the neuron parameters.  The fast mode evaluates F_c from a per-channel piecewise-cubic table held in shared memory
 // (one LDS.U16 + one LDS.128 + ~20 ALU instructions) instead of T x (12 FP + 3 MUFU) instructions.
 //
-// Grid: x = u - theta0_c, y = 1 + |x|.  A CELL is one binade of y on one side of theta0 (2 * LT_NB cells per channel); each
-// cell is split into 2^k equal segments, k in [0, 7] chosen per cell on the host so that the cubic (Chebyshev-node
-// interpolant of the exact fp64 chain) stays within LT_TOL of the exact chain.  The float bits of y give cell, segment and
-// the local coordinate without any transcendental:  cell = exponent(y), segment = top k mantissa bits, tau = y - floor_k(y).
-// |x| >= 2^LT_NB - 1 = 255 (not seen behind a BatchNorm with sane statistics) takes the exact MUFU chain.  Channels of a
-// block with identical neuron parameters (every channel of a default-initialised layer) share their segments.
+// Grid: x = u - theta0_c, y = 2|x| + 2 in [2, 512).  A CELL is one binade of y on one side of theta0 (2 * LT_NB cells per
+// channel; the low three exponent bits of y are the cell number); each cell is split into 2^k equal segments, k in [0, 7]
+// chosen per cell on the host so that the cubic (Chebyshev-node interpolant of the exact fp64 chain, in the segment's own
+// coordinate t in [0, 1]) stays within LT_TOL of the exact chain.  Segment and t come out of two multiply-adds: with the
+// cell's scale S = 2^(k-e-1), q = y*S lies in [2^k, 2^(k+1)) and  qm = fma(y, S, 2^23 - 0.5)  is floor(q) + 2^23 (an exact
+// tie rounds to the neighbouring segment's end point, where the piecewise function is continuous), t = fma(y, S, -(qm - 2^23)).
+// Everything but the clamp, the cell address (shift + and-or) and the sign test runs on the FMA pipe -- the first version
+// of this lookup (shift / mask arithmetic on bits(y)) saturated the ALU pipe.
+// |x| >= 255 (not seen behind a BatchNorm with sane statistics) and NaN take the exact MUFU chain.  Channels of a block with
+// identical neuron parameters (every channel of a default-initialised layer) share their segments.
 //
 // Memory image of one 128-channel block (copied verbatim to shared memory by the kernels):
-//   uint2  desc[LT_NCELL][128]   .x = 23 - k (the shift that turns the float bits of y into a segment number), .y = byte offset
-//                                of the cell's (virtual) segment 0 relative to the coefficient array, biased so that
-//                                segment address = coef + .y + 16 * (bits(y) >> .x) needs no masking of the exponent; the 32
-//                                channels of a warp read 256 contiguous bytes when they sit in the same cell
-//   float4 coef[nseg]            s = c.x + tau*(c.y + tau*(c.z + tau*c.w)); channel c's segments start at an index that is
-//                                congruent to c mod 8, so the 8 lanes of an LDS.128 phase that sit in the same relative
-//                                segment hit 8 different bank groups
+//   uint2  desc[LT_NCELL][128]   .x = bits of S, .y = byte offset (mod 2^32) such that the segment's coefficients sit at
+//                                coef + .y + 16 * bits(qm); the 32 channels of a warp read 256 contiguous bytes when they
+//                                sit in the same cell; cells 0..7: x >= 0, cells 8..15: x < 0
+//   float4 coef[nseg]            s = c.x + t*(c.y + t*(c.z + t*c.w)); every side starts with one guard segment (the constant
+//                                F(theta0)) that catches the downward tie at q = 2^k of its first cell; channel c's segments
+//                                start at an index congruent to c mod 8, so the 8 lanes of an LDS.128 phase that sit in the
+//                                same relative segment hit 8 different bank groups
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
@@ -53,35 +57,40 @@ double lif_chain_exact_host(double u, double d, double a, double r, double th0, 
 
 #ifdef __CUDACC__
 // NV chains of ONE channel, phase-major so the NV descriptor loads, then the NV coefficient loads, are in flight together
-// (no branch between them).  x[i] = u_i - theta0 on entry, the soft spike on exit.  desc_c: this channel's column of the
-// block's descriptor array (cell stride LT_CH); coef: the block's coefficient array; both in shared memory.  Inputs outside
-// the tabulated range (|x| >= 255, NaN) are clamped for the lookup and flagged in the returned bit mask: the caller
-// re-evaluates those with the exact chain.  The index arithmetic is laid out for the SM's two integer-capable pipes: 7
-// ALU-pipe operations (min, compare, 4 shifts, and-mask), the rest multiply-adds.
+// (no branch between them).  x[i] = u_i - theta0 on entry, the soft spike on exit.  desc_lane: shared-memory address of this
+// channel's entry of cell 0 (cell stride LT_CH * 8 bytes); coef: shared-memory address of the block's coefficient array.
+// Returns true when some input lies outside the tabulated range (|x| >= 255) or is NaN: the caller then re-evaluates
+// every element with |x| >= 255 / NaN by the exact chain (the lookup clamps, so its loads stay inside the table).
 template <int NV>
-__device__ __forceinline__ uint32_t lif_table_eval_vec(float (&x)[NV], const uint2* __restrict__ desc_c,
-                                                       const float4* __restrict__ coef) {
-  float y[NV]; uint2 d[NV]; uint32_t oob = 0;
+__device__ __forceinline__ bool lif_table_eval_vec(float (&x)[NV], uint32_t desc_lane, uint32_t coef) {
+  float y[NV]; uint32_t dS[NV], dO[NV];
+  float ymax = 0.0f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const float ya = fabsf(x[i]) + 1.0f;
-    if (!(ya < 256.0f)) oob |= 1u << i;
-    y[i] = fminf(ya, 255.99998f);                                       // NaN -> 255.99998 as well
-    const uint32_t cell = (__float_as_uint(y[i]) >> 23) * (uint32_t)LT_CH + (__float_as_uint(x[i]) >> 31) * (uint32_t)(LT_NB * LT_CH);
-    d[i] = desc_c[(int)cell - 127 * LT_CH];
+    const float y2 = fmaf(fabsf(x[i]), 2.0f, 2.0f);
+    asm("max.NaN.f32 %0, %0, %1;" : "+f"(ymax) : "f"(y2));
+    y[i] = fminf(y2, 511.99997f);                                       // NaN -> 511.99997 as well
+    const uint32_t a = desc_lane + ((__float_as_uint(y[i]) >> 13) & 0x1C00u);     // cell = low 3 exponent bits, 1 KiB per cell
+    // predicated pair of loads instead of a select on the address: the sign costs one compare on the ALU pipe
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %2, 0f00000000;\n\t"
+        "@p ld.shared.v2.u32 {%0, %1}, [%3+8192];\n\t"
+        "@!p ld.shared.v2.u32 {%0, %1}, [%3];\n\t}"
+        : "=r"(dS[i]), "=r"(dO[i]) : "f"(x[i]), "r"(a));
   }
-  float4 c[NV]; float tau[NV];
+  float4 c[NV]; float t[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const uint32_t yb = __float_as_uint(y[i]);
-    const uint32_t t1 = yb >> d[i].x;
-    c[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(coef) + (int)(t1 * 16u + d[i].y));
-    tau[i] = y[i] - __uint_as_float(yb & (0xFFFFFFFFu << d[i].x));
+    const float S = __uint_as_float(dS[i]);
+    const float qm = fmaf(y[i], S, 8388607.5f);                         // floor(y * S) + 2^23
+    t[i] = fmaf(y[i], S, -(qm - 8388608.0f));
+    const uint32_t addr = coef + __float_as_uint(qm) * 16u + dO[i];
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[i].x), "=f"(c[i].y), "=f"(c[i].z), "=f"(c[i].w) : "r"(addr));
   }
 #pragma unroll
-  for (int i = 0; i < NV; ++i) x[i] = fmaf(fmaf(fmaf(c[i].w, tau[i], c[i].z), tau[i], c[i].y), tau[i], c[i].x);
-  return oob;
+  for (int i = 0; i < NV; ++i) x[i] = fmaf(fmaf(fmaf(c[i].w, t[i], c[i].z), t[i], c[i].y), t[i], c[i].x);
+  return !(ymax < 512.0f);
 }
+__device__ __forceinline__ bool lif_table_oob(float x) { return !(fabsf(x) < 255.0f); }
 #endif
 
 }  // namespace sapcu
