@@ -156,13 +156,8 @@ edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restric
   const int c = blockIdx.y * 128 + cl;
   const bool cv = c < C;
   const int cc = cv ? c : 0;
-  if (LTAB) {
-    const uint4* src = reinterpret_cast<const uint4*>(tab + (size_t)blockIdx.y * tab_stride);
-    uint4* dst = reinterpret_cast<uint4*>(tsm);
-    for (uint32_t i = tid; i < tab_stride / 16; i += EPF_THREADS) dst[i] = src[i];
-  }
+  if (LTAB) lif_table_load(tab + (size_t)blockIdx.y * tab_stride, tsm, tab_stride, tid, EPF_THREADS);
   const uint32_t lt_desc = (uint32_t)__cvta_generic_to_shared(tsm) + (uint32_t)cl * 8u;
-  const uint32_t lt_coef = (uint32_t)__cvta_generic_to_shared(tsm) + LT_DESC_BYTES;
   // y = ((w.d + b) * sc + sh) folded into one affine map of the offset
   const float sc = scale[cc];
   const float w0 = W[3 * cc] * sc, w1 = W[3 * cc + 1] * sc, w2 = W[3 * cc + 2] * sc;
@@ -193,7 +188,7 @@ edge_pos_lif_fast_kernel(const float* __restrict__ xyz, const int32_t* __restric
         float x0[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) x0[j] = u[j];
-        if (lif_table_eval_vec<4>(u, lt_desc, lt_coef)) {
+        if (lif_table_eval_vec<4>(u, lt_desc)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (lif_table_oob(x0[j])) u[j] = lif_chain<false>(x0[j] + p.th0, p, T);
         }

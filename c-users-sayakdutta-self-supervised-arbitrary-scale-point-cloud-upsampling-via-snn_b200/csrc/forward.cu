@@ -31,7 +31,7 @@ struct Bump {
 };
 
 struct FnPlan {
-  int32_t* idx; uint32_t* idx8; float *F0, *FCAT, *X, *QKV, *E1, *E2, *E3, *RES, *R1, *G, *GM, *H0, *H1, *H2, *H3;
+  int32_t* idx; uint32_t* idx8; float *F0, *FCAT, *X, *QKV, *QK, *E1, *E2, *E3, *RES, *R1, *G, *GM, *H0, *H1, *H2, *H3;
   size_t bytes; int kmax; int Dl, kl;
 };
 FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
@@ -47,6 +47,7 @@ FnPlan fn_plan(const FnNet& f, int64_t s, int M, void* base) {
   p.idx8 = b.take<uint32_t>(P * ((p.kmax + 3) / 4));       // byte-packed copy of the graph for the fused attention tails
   p.F0 = b.take<float>(P * 64); p.FCAT = b.take<float>(P * 192);
   p.X = b.take<float>(P * 512); p.QKV = b.take<float>(P * 1536);
+  p.QK = b.take<float>(P * 1024);              // [W q | W k] per point (factorised attention input)
   p.E1 = b.take<float>(P * emax); p.E2 = b.take<float>(P * emax); p.E3 = b.take<float>(P * emax);
   p.RES = b.take<float>(P * 512); p.R1 = b.take<float>(P * 512);
   p.G = b.take<float>(P * f.emb); p.GM = b.take<float>(s * f.emb);
@@ -209,7 +210,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
     const int64_t ldin = b == 0 ? 64 : 192;
     const int64_t E = P * kk;
     float* Xb = p.E1;                                             // this block's edge buffer (pos-enc layer 1, then fc_gamma's output)
-    bool xb_h2 = false, e2_h2 = false;                            // fc_gamma's output / pos stored as fp16 planes (see below)
+    bool xb_h2 = false, e2_h2 = false, pos32 = false;             // fc_gamma's output / pos stored as fp16 planes (see below); + fp32 copy of pos
     SAPCU_TRY(g.L("fn.fc1+lif").layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
     SAPCU_TRY(g.L("fn.qkv+lif").layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
     if (mode == SAPCU_MODE_FP32) { g_tap_gamma_h2 = 0; g_tap_delta2_h2 = 0; SAPCU_TRY(edge_pos(b, Xb, st, 1, false)); }
@@ -225,7 +226,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         a.fast = true; a.x_h2 = true; a.out_h2 = true;
         if (use_tables && k.snn_delta2.tab_ok) { a.lif_tab = k.snn_delta2.tab; a.lif_tab_stride = k.snn_delta2.tab_stride; }
       }
-      GemmArgs a1 = gamma_args(b, p.E2, Xb, p.E3), a2 = gamma2_args(b, Xb, p.E2);
+      GemmArgs a1 = gamma_args(b, p.E2, Xb, p.QK), a2 = gamma2_args(b, Xb, p.E2);
       a1.tc_passes = a2.tc_passes = 1;
       a1.fast = true; a1.x_h2 = true; a1.out_h2 = true;
       if (use_tables && k.snn_gamma.tab_ok) { a1.lif_tab = k.snn_gamma.tab; a1.lif_tab_stride = k.snn_gamma.tab_stride; }
@@ -245,8 +246,8 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         SAPCU_TRY(g.L("fn.fc_delta2+lif").run(a, A_PLAIN));
         Layer Lw = k.fc_gamma;
         Lw.bias = nullptr; Lw.scale = nullptr; Lw.shift = nullptr;
-        SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV, 3 * D, P, p.E3, 2 * D, ACT_NONE));
-        SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV + D, 3 * D, P, p.E3 + D, 2 * D, ACT_NONE));
+        SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV, 3 * D, P, p.QK, 2 * D, ACT_NONE));
+        SAPCU_TRY(g.L("fn.fc_gamma(Wq|Wk per point)").layer(Lw, p.QKV + D, 3 * D, P, p.QK + D, 2 * D, ACT_NONE));
         SAPCU_TRY(g.L("fn.fc_gamma+edge_bias+lif").run(a1, A_PLAIN));
         SAPCU_TRY(g.L("fn.fc_gamma2+softmax+sum(attention tail)").run(a2, A_PLAIN));
         SAPCU_TRY(g.L("fn.out_proj").layer(k.out_proj, p.RES, D, P, p.R1, D, ACT_NONE));
@@ -274,7 +275,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         a.x_h2 = true;                                              // tentatively: 128-channel layers run on the 2-CTA engine only from planes
         a.x_h2 = h2_delta && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_fp16x3(a);
         {   // pos (E2) has two readers, fc_gamma's contraction and the fused attention tail: planes when both take them
-          GemmArgs a1 = gamma_args(b, p.E2, Xb, p.E3), a2 = gamma2_args(b, Xb, p.E2);
+          GemmArgs a1 = gamma_args(b, p.E2, Xb, p.QK), a2 = gamma2_args(b, Xb, p.E2);
           a1.tc_passes = a2.tc_passes = a.tc_passes;
           a1.x_h2 = a2.x_h2 = a2.pos_h2 = true;                    // the formats this hand-over would give them
           e2_h2 = h2_pos && a.x_h2 && factorise && kk >= 2 && gemm_tc2_supported(a, A_PLAIN) && gemm_tc2_supported(a1, A_PLAIN) &&
@@ -283,6 +284,10 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         a.out_h2 = e2_h2;
         g_tap_delta2_h2 = e2_h2 ? 1 : 0;
         const bool tab_on = blk_tab && a.x_h2 && e2_h2;           // the whole chain of plane hand-overs is in place
+        // pos has two readers: fc_gamma's contraction takes the planes, the attention tail gathers it per edge and prefers one
+        // 4-byte load over two 2-byte loads -- with the table-driven (ALU-bound) epilogue the extra fp32 store is free
+        pos32 = tab_on && settings().tc_pos_copy;
+        if (pos32) a.Y2 = p.E3;
         if (tab_on) {
           ProfWork w; w.elsteps = (double)E * D * 4; w.bytes = (double)E * D * 4.0;
           SAPCU_PROF(st, "fn.fc_delta(K=3)+lif (edge_pos_lif)", w,
@@ -295,7 +300,7 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         SAPCU_TRY(g.L("fn.fc_delta2+lif").run(a, A_PLAIN));
       }
       {
-        float* QK = p.E3;                                          // [W q | W k], [P, 2D]
+        float* QK = p.QK;                                          // [W q | W k], [P, 2D]
         GemmArgs a = gamma_args(b, p.E2, Xb, QK);
         a.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
         {   // fc_gamma's spikes go to fc_gamma2 only: hand them over as fp16 planes when both run on the 2-CTA fp16x3 path
@@ -319,8 +324,8 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
         }
       }
       {
-        GemmArgs a = gamma2_args(b, Xb, p.E2);
-        a.x_h2 = xb_h2; a.pos_h2 = e2_h2;
+        GemmArgs a = gamma2_args(b, Xb, pos32 ? p.E3 : p.E2);
+        a.x_h2 = xb_h2; a.pos_h2 = e2_h2 && !pos32;
         if (gemm_tc2_supported(a, A_PLAIN) || gemm_tc_supported(a, A_PLAIN)) {
           SAPCU_TRY(g.L("fn.fc_gamma2+softmax+sum(attention tail)").run(a, A_PLAIN));
         } else {

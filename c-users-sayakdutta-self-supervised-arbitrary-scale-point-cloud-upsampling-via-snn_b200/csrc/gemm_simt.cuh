@@ -38,6 +38,7 @@ struct GemmArgs {
   int act = ACT_NONE; int T = 0; const float* nparams = nullptr;   // nparams: [4][N] = d,a,r,th0
   const float* residual = nullptr; int64_t ldr = 0;
   float* Y = nullptr; int64_t ldc = 0;
+  float* Y2 = nullptr;   // 2-CTA tensor-core engine, LIF epilogue writing fp16 planes: optional fp32 copy of the same spikes ([R, N], ld = N)
   int tc_passes = 3;     // tensor-core engine only: 3 = 3xTF32 split, 1 = single-pass TF32
   // tensor-core engine only: fuse softmax_k(Y / at_sqrt) and sum_j a_j (at_v[nb_j] + at_pos[e_j]) into the epilogue; Y becomes [points, N]
   const float* at_pos = nullptr; const float* at_v = nullptr; int64_t at_ldv = 0; float at_sqrt = 1.0f;

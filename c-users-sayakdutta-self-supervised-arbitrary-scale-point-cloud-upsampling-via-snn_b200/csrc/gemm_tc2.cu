@@ -341,16 +341,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     const int part = (warp - T2_EPI_WARP0) >> 2;
     int a = 0; uint32_t aph = 0; bool ok = true;
     // LT: this CTA's 128-channel block of the tabulated LIF^T chain -> shared memory (behind the barriers), once
-    uint32_t lt_desc = 0, lt_coef = 0;                           // shared-memory addresses: this lane's descriptor column, the coefficients
+    uint32_t lt_desc = 0;                                        // shared-memory address of this lane's descriptor column
     if (LT) {
       const int blk = (int)(pair % p.m_tiles) * CG + (int)rank;       // the host keeps npairs a multiple of m_tiles: fixed channel block
       uint8_t* tsm = smem_gen + T2_STAGES * T2_STAGE_BYTES + 256;
-      const uint4* src = reinterpret_cast<const uint4*>(p.lif_tab + (size_t)blk * p.lif_tab_stride);
-      uint4* dst = reinterpret_cast<uint4*>(tsm);
-      for (uint32_t i = threadIdx.x - T2_EPI_WARP0 * 32; i < p.lif_tab_stride / 16; i += T2_EPI * 32) dst[i] = src[i];
+      lif_table_load(p.lif_tab + (size_t)blk * p.lif_tab_stride, tsm, p.lif_tab_stride, threadIdx.x - T2_EPI_WARP0 * 32, T2_EPI * 32);
       asm volatile("bar.sync 1, %0;" ::"r"(T2_EPI * 32) : "memory");
       lt_desc = smem_u32(tsm) + (uint32_t)(q * 32 + lane) * 8u;
-      lt_coef = smem_u32(tsm) + LT_DESC_BYTES;
     }
     for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
       const int m_t = (int)(t % p.m_tiles);
@@ -425,7 +422,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
               float x0[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) x0[j] = u[j];
-              if (lif_table_eval_vec<8>(u, lt_desc, lt_coef)) {   // some |x| >= 255 (or NaN): the exact chain for those
+              if (lif_table_eval_vec<8>(u, lt_desc)) {   // some |x| >= 255 (or NaN): the exact chain for those
 #pragma unroll
                 for (int j = 0; j < 8; ++j) if (lif_table_oob(x0[j])) u[j] = lif_chain<false>(x0[j] + np.th0, np, p.T);
               }
@@ -448,6 +445,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                   if (j < nrows) hp[(uint32_t)j * ld] = __float2half_rn(u[j] * 8192.0f);
               }
             } else if (p.out_h2) {                                // fp16 (hi, lo) planes of y * 2^13 for a fp16x3 consumer
+              if (p.Y2) {                                         // + the fp32 copy a gathering reader (the attention tail) prefers
+                float* y2p = p.Y2 + r0 * p.ldc + c;
+                const uint32_t ld2 = (uint32_t)p.ldc;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < nrows) y2p[(uint32_t)j * ld2] = u[j];
+              }
               __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
               __half* lp = hp + p.R * p.ldc;
 #pragma unroll
@@ -687,7 +690,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   }
   TcParams p;
   p.R = g.R; p.N = g.N; p.K = g.K; p.bias = g.bias; p.scale = g.scale; p.shift = g.shift; p.act = g.act; p.T = g.T;
-  p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc;
+  p.nparams = g.nparams; p.residual = g.residual; p.ldr = g.ldr; p.Y = g.Y; p.ldc = g.ldc; p.Y2 = g.Y2;
   p.aq = g.Q; p.ak = g.Kf; p.ldq = g.ldq; p.idx = g.idx; p.ldi = g.ldi; p.kk = g.kk; p.Mpts = g.Mpts;
   p.pool = g.pool; p.pool_T = g.pool_T; p.pool_rows = (int64_t)g.pool_T * g.pool_M;
   p.idx8 = g.idx8; p.ldi8w = g.ldi8w;

@@ -61,8 +61,21 @@ double lif_chain_exact_host(double u, double d, double a, double r, double th0, 
 // channel's entry of cell 0 (cell stride LT_CH * 8 bytes); coef: shared-memory address of the block's coefficient array.
 // Returns true when some input lies outside the tabulated range (|x| >= 255) or is NaN: the caller then re-evaluates
 // every element with |x| >= 255 / NaN by the exact chain (the lookup clamps, so its loads stay inside the table).
+// Copy one block image into shared memory with `nthreads` threads (thread `tid`), relocating the descriptors' byte offsets
+// to absolute shared-memory addresses so that the lookup needs no base add.
+__device__ __forceinline__ void lif_table_load(const uint8_t* __restrict__ src, uint8_t* dst, uint32_t bytes, uint32_t tid, uint32_t nthreads) {
+  const uint32_t coef = (uint32_t)__cvta_generic_to_shared(dst) + LT_DESC_BYTES;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (uint32_t i = tid; i < bytes / 16; i += nthreads) {
+    uint4 v = s4[i];
+    if (i < LT_DESC_BYTES / 16) { v.y += coef; v.w += coef; }           // two descriptors per 16 bytes
+    d4[i] = v;
+  }
+}
+
 template <int NV>
-__device__ __forceinline__ bool lif_table_eval_vec(float (&x)[NV], uint32_t desc_lane, uint32_t coef) {
+__device__ __forceinline__ bool lif_table_eval_vec(float (&x)[NV], uint32_t desc_lane) {
   float y[NV]; uint32_t dS[NV], dO[NV];
   float ymax = 0.0f;
 #pragma unroll
@@ -83,7 +96,7 @@ __device__ __forceinline__ bool lif_table_eval_vec(float (&x)[NV], uint32_t desc
     const float S = __uint_as_float(dS[i]);
     const float qm = fmaf(y[i], S, 8388607.5f);                         // floor(y * S) + 2^23
     t[i] = fmaf(y[i], S, -(qm - 8388608.0f));
-    const uint32_t addr = coef + __float_as_uint(qm) * 16u + dO[i];
+    const uint32_t addr = __float_as_uint(qm) * 16u + dO[i];            // the kernels add the coefficient array's address to .y while copying the table
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[i].x), "=f"(c[i].y), "=f"(c[i].z), "=f"(c[i].w) : "r"(addr));
   }
 #pragma unroll

@@ -182,6 +182,7 @@ struct TcParams {
   int act, T; const float* nparams;
   const float* residual; int64_t ldr;
   float* Y; int64_t ldc;
+  float* Y2;                  // LIF epilogue with out_h2: optional fp32 copy of the spikes for a second reader that gathers them ([R, N])
   // EXTRA == 2 (fn fc_gamma on the factorised attention input): row e = pt*kk + j of the activation is pos_ij only, and
   // the epilogue adds aq[pt,c] - ak[nb,c] (= W q_i - W k_j, per-POINT products) to the accumulator before the affine
   const float* aq; const float* ak; int64_t ldq; const int32_t* idx; int ldi, kk, Mpts;
