@@ -32,6 +32,21 @@ def rotation_matrix_from_vectors(vec1, vec2):
     return np.eye(3) + k + k.dot(k) * ((1 - c) / (s ** 2))
 
 
+def morton_order(d_pts, bits=10):
+    """Permutation that sorts points [S,3] (cuda, f64) along a 3-D Morton curve (`bits` per axis).  Seeds are independent
+    units, so the pipeline may visit them in any order; in the thread-per-seed kNN of large clouds (N >= 2^20) the 32 seeds
+    of a warp then share their filter survivors (the exact fp64 re-rank runs convergent instead of one lane at a time) and
+    the patch gathers hit the same cache lines.  torch is plumbing here: three quantisations, a bit interleave, one argsort."""
+    lo = d_pts.min(dim=0).values
+    span = (d_pts.max(dim=0).values - lo).clamp_min(1e-300)
+    q = ((d_pts - lo) / span * ((1 << bits) - 1)).to(torch.int64)
+    key = torch.zeros(d_pts.shape[0], dtype=torch.int64, device=d_pts.device)
+    for b in range(bits):
+        for a in range(3):
+            key |= ((q[:, a] >> b) & 1) << (3 * b + a)
+    return torch.argsort(key)
+
+
 def _on_device(fn):
     """Run a Generator3D6 method with the generator's CUDA device current (launches, allocations and the stream the
     C ABI receives all belong to that device, whichever device the calling thread had selected)."""
@@ -58,6 +73,7 @@ class Generator3D6(object):
         self.seeds_per_pass = seeds_per_pass               # device-side pass size (None: everything at once)
         self.remove_outliers = remove_outliers
         self.seed_source = seed_source                     # "gpu": sapcu_seedgen; "dense": the reference's ./dense process
+        self.sort_seeds = True                             # Morton-order the seeds of large clouds (N >= 2^20) before the pipeline
         self.model1.eval()
         self.model2.eval()
         self._bufs = {}
@@ -108,7 +124,7 @@ class Generator3D6(object):
         return h_out.numpy().copy()
 
     @torch.no_grad()
-    def displace_device(self, d_cloud, d_seeds, return_parts=False, batch=None):
+    def displace_device(self, d_cloud, d_seeds, return_parts=False, batch=None, sort=True):
         """Device-resident pipeline: cloud [N,3] f64, seeds [S,3] f64 (cuda) -> [S,3] f64 (cuda).
         batch = (cloud_off, seed_off): host prefix tables ([B+1] ints) when d_cloud / d_seeds are the concatenation of
         B independent (cloud, seed set) problems -- one batched kNN launch, then the same per-seed pipeline."""
@@ -116,6 +132,14 @@ class Generator3D6(object):
         K = self.k_neighbors
         Ncl, S = d_cloud.shape[0], d_seeds.shape[0]
         dev = d_cloud.device
+        if sort and batch is None and self.sort_seeds and Ncl >= (1 << 20) and S > 1 and not return_parts:
+            # large clouds: visit the seeds along a Morton curve (results are per-seed, so only the order of the work changes)
+            with torch.cuda.device(dev):
+                perm = morton_order(d_seeds)
+                res = self.displace_device(d_cloud, d_seeds[perm].contiguous(), sort=False)
+                out = torch.empty_like(res)
+                out[perm] = res
+            return out
         with torch.cuda.device(dev):              # every launch below goes to the tensors' device and its current stream
             st = N.stream_ptr(dev)
             out = torch.empty(S, 3, dtype=torch.float64, device=dev)

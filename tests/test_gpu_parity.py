@@ -1020,3 +1020,49 @@ def test_benchmarked_mode_at_benchmarked_size(lib, sphere, parity_log):
     # fd runs free here (own feature-space graphs), so the distance bound is the free-running one
     assert rec["tc"]["normal_angle_deg_max"] < 0.1 and rec["tc"]["dist_rel_max"] < 2e-3 and rec["tc"]["dist_rel_p999"] < 1e-3, rec
     assert rec["fast"]["normal_angle_deg_max"] < 0.5 and rec["fast"]["dist_rel_max"] < 5e-2, rec
+
+
+@pytest.mark.parametrize("S,M", [(5, 100), (40, 100), (64, 50), (48, 128), (3, 7)])
+def test_fast_mode_small_and_odd_shapes(lib, sphere, S, M):
+    """The fast mode on shapes where parts of it fall back (fewer than 1,024 / 4,096 rows: FFMA or 1-CTA engine; other patch
+    sizes; patches smaller than the graph sizes): outputs stay finite, unit-length and close to the parity-grade mode's."""
+    cloud, seeds = sphere
+    mfn, mfd, _, _ = _models(True)
+    idx = oracle_c.knn(cloud, seeds[:S], M)
+    rng = np.random.default_rng(4)
+    p = torch.from_numpy(orc.gather_center(cloud, seeds[:S], idx)).to(DEV)
+    pr = torch.from_numpy(orc.gather_center(cloud, seeds[:S], idx, rng.normal(size=(S, 3)).astype(np.float32))).to(DEV)
+    out = {}
+    for mode in ("tc", "fast"):
+        mfn.set_mode(mode), mfd.set_mode(mode)
+        n, d = mfn(p), mfd(pr)
+        torch.cuda.synchronize()
+        N.check_device("fast mode, small shapes")
+        out[mode] = (n.cpu().numpy(), d.cpu().numpy())
+    n, d = out["fast"]
+    assert np.isfinite(n).all() and np.isfinite(d).all() and (d >= 0).all()
+    np.testing.assert_allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
+    assert _angle_deg(n, out["tc"][0]).max() < 0.5
+    assert (np.abs(d - out["tc"][1]) / np.maximum(np.abs(out["tc"][1]), 1e-6)).max() < 5e-2
+
+
+def test_morton_ordered_seeds_bit_identical_large_cloud(lib):
+    """Clouds of >= 2^20 points: Generator3D6 visits the seeds along a Morton curve (warp-coherent survivors in the thread-per-seed
+    kNN).  Seeds are independent units, so the displaced points must be bit-identical to the unsorted visit, and the large-cloud
+    kNN itself (TMA-staged SoA tiles, packed fp32 filter) bit-exact against the fp64 oracle on a slice."""
+    from sapcu_b200.generation import Generator3D6, morton_order
+    cloud = syn.cloud(1 << 20, seed=5, shape="sphere")
+    seeds = syn.seeds(cloud, 700.0 / (1 << 20), seed=6)
+    assert seeds.shape[0] == 700
+    mfn, mfd, _, _ = _models(True)
+    mfn.set_mode("tc"), mfd.set_mode("tc")
+    gen = Generator3D6(mfn, mfd, DEV, k_neighbors=100, remove_outliers=False)
+    d_c, d_s = torch.from_numpy(cloud).to(DEV), torch.from_numpy(seeds).to(DEV)
+    a = gen.displace_device(d_c, d_s)                       # Morton-ordered visit
+    gen.sort_seeds = False
+    b, idx, _, _ = gen.displace_device(d_c, d_s, return_parts=True)
+    assert torch.equal(a, b)
+    perm = morton_order(d_s).cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(700))
+    sl = np.r_[0:24, 676:700]
+    assert np.array_equal(idx.cpu().numpy()[sl], oracle_c.knn(cloud, seeds[sl], 100))

@@ -15,6 +15,9 @@ def main():
          for x in csv.DictReader(lines) if x["Metric Name"] == "gpu__time_duration.sum"]
     starts = [i for i, x in enumerate(L) if "knn_seed" in x[0]]
     P = L[starts[-1] - 2:]          # the pass opens with two cloud_to_f32 launches and the seed kNN
+    if len(starts) > 1 and len(P) < starts[-1] - starts[-2]:      # the capture window ended inside the last pass: take the last complete one
+        P = L[starts[-2] - 2: starts[-1] - 2]
+    P = [x for x in P if "at::native" not in x[0] and "elementwise_kernel" not in x[0]]      # torch's own fills / copies between the calls
     agg = collections.OrderedDict()
     for n, t in P:
         k = re.sub(r"\(.*", "", n).replace("void ", "").replace("sapcu::", "")
