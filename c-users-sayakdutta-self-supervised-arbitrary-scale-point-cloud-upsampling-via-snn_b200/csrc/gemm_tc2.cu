@@ -17,8 +17,10 @@
 // halved.  Accumulators: each CTA's TMEM holds its 128 channels x 256 rows (2 buffers of 256 columns).
 //
 // Cross-CTA protocol (all waits are watchdogged):
-//   raw[s]    local   TMA bytes of this CTA landed                       -> this CTA's splitter
-//   split[s]  LEADER  one arrival per splitter thread of both CTAs (the follower arrives remotely via mapa)
+//   raw[s]    local   TMA bytes of this CTA landed                       -> this CTA's splitter              (HM 0, 1)
+//             LEADER  TMA bytes of BOTH CTAs (cp.async.bulk.tensor.cta_group::2 counts the follower's loads on the leader's
+//                     barrier)                                          -> leader's MMA issuer, no splitter  (HM >= 2)
+//   split[s]  LEADER  one arrival per splitter thread of both CTAs (the follower arrives remotely via mapa)   (HM 0, 1)
 //   empty[s]  both    tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11) -> each CTA's TMA producer
 //   tfull[a]  both    multicast commit after the last k-block           -> each CTA's epilogue
 //   tempty[a] LEADER  2 x EPI arrivals (epilogue warps of both CTAs)    -> leader's MMA issuer
@@ -45,6 +47,9 @@ constexpr int T2_BN = 256;                      // rows per pair tile (128 stage
 #endif
 constexpr int T2_SPLIT_WARP0 = 2, T2_SPLIT_WARPS = SAPCU_T2_SPLIT_WARPS;
 constexpr int T2_EPI_WARP0 = T2_SPLIT_WARP0 + T2_SPLIT_WARPS, T2_EPI = 16;
+#ifndef SAPCU_T2_FAST_STAGES
+#define SAPCU_T2_FAST_STAGES 4     // pair flavour on compact (32 KiB) stages without a LIF table: stages in flight
+#endif
 constexpr size_t T2_SMEM_BYTES = (size_t)T2_STAGES_MAX * 4 * TC_TILE_BYTES + 1024 + 256;   // 3 x 64 KiB (tf32) = 2 x 96 KiB (fp16x3)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -96,11 +101,43 @@ __device__ __forceinline__ void umma_f16_1cta(uint32_t tmem_d, uint64_t adesc, u
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// TMA load into THIS CTA's shared memory whose transaction bytes are counted on the barrier at the same offset in the pair's
+// LEADER CTA (shared::cluster addresses carry the CTA's rank inside the pair in bit 24: cleared = the even CTA)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int CG> __device__ __forceinline__ void tma_load_2d_cg(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+}
 template <int CG> __device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
   if (CG == 2) umma_commit_2cta(bar); else umma_commit(bar);
 }
 template <int CG> __device__ __forceinline__ void cta_group_sync() {
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+}
+
+// tile t -> (channel tile m_t, row tile n_t); 32-bit divide when the tile index fits
+__device__ __forceinline__ void tile_split(int64_t t, int m_tiles, int& m_t, int64_t& n_t) {
+  if (t < (1ll << 31)) { const uint32_t q = (uint32_t)t / (uint32_t)m_tiles; n_t = q; m_t = (int)((uint32_t)t - q * (uint32_t)m_tiles); }
+  else { n_t = t / m_tiles; m_t = (int)(t - n_t * m_tiles); }
+}
+// one lane of the (converged) warp, chosen by the hardware: ptxas knows that exactly one thread runs the guarded region and
+// issues its uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) without a per-operand uniformisation loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P_el;\n\t"
+      "elect.sync _|P_el, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P_el;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// whole-warp wait: every lane polls, the outcome is voted so that it (and what depends on it) stays warp-uniform
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int* err) {
+  return __all_sync(0xffffffffu, mbar_wait(bar, parity, err));
 }
 
 // H16 = fp16x3 operand format (activations known to be LIF outputs): W arrives as pre-split fp16 (hi, lo) of W * 2^e, the
@@ -126,11 +163,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   constexpr int CW = CG * 128;                               // output channels per tile
   constexpr bool FASTOP = HM == 3 || HM == 4;               // compact stages: one weight tile + one activation tile
   // stages: HM 2 (two fp16 planes per operand, 64 KiB per stage for a pair, 96 KiB single-CTA): 3 / 2 plain, 2 / 1 next to a LIF table
-  constexpr int T2_STAGES = HM == 1 ? 2 : (FASTOP && !LT) ? 4 : (FASTOP && CG == 1) ? 2 : FASTOP ? 3 : (CG == 2 ? (LT ? 2 : 3) : (LT ? 1 : 2));
+  constexpr int T2_STAGES = HM == 1 ? 2 : (FASTOP && !LT) ? (CG == 2 ? SAPCU_T2_FAST_STAGES : 4) : (FASTOP && CG == 1) ? 2 : FASTOP ? 3 : (CG == 2 ? (LT ? 2 : 3) : (LT ? 1 : 2));
   constexpr uint32_t T2_STAGE_BYTES = (HM == 1 ? 6 : FASTOP ? (CG == 2 ? 2 : 3) : (CG == 2 ? 4 : 6)) * TC_TILE_BYTES;   // HM 3/4: W tile + 128 (pair) or 256 activation rows
   constexpr uint32_t X_TILE = FASTOP ? 1 : 2;               // position of the activation (hi) tile inside a stage
   constexpr uint32_t X_LO_OFF = (CG == 2 ? 3 : 4) * TC_TILE_BYTES;   // lo activation tile (HM 0..2): behind the hi tile of 128 / 256 rows
   constexpr int BKE = H16 ? 64 : TC_BK;                    // k elements per stage
+  constexpr bool DIRECT = HM >= 2;                          // operands arrive ready-made: no splitter hop (see the protocol above)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -143,8 +181,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   const uint32_t tmem_slot = bar_base + 8u * (3 * T2_STAGES + 2 * T2_ACC);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T2_STAGES * T2_STAGE_BYTES + 8 * (3 * T2_STAGES + 2 * T2_ACC));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader
+  // warp index, pair rank and (below) the TMEM base go through a shuffle so that the compiler can prove them warp-uniform: the
+  // single-thread roles (TMA producer, MMA issuer) then keep their loop state, coordinates and descriptors in uniform
+  // registers instead of re-uniformising every operand of every UTMALDG / UTCHMMA (ncu: those two warps, not the tensor
+  // pipe, bounded the 32 KiB-stage flavours at ~850 clocks per k-block)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;  // 0 = leader
   const int64_t pair = blockIdx.x / CG, npairs = gridDim.x / CG;
   const int nk = p.K / BKE;
   const int64_t total_tiles = p.n_tiles * p.m_tiles;       // m_tiles = N / 256 (channel pairs), n_tiles = ceil(R / tile_rows)
@@ -171,39 +213,47 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   tc_fence_before();
   cta_group_sync<CG>();                                     // barriers of both CTAs initialised before any remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_gen, 0);
 
   if (warp == 0) {
     // ======================================================================== TMA producer (each CTA: its own halves)
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0; bool ok = true;
-      for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
-        const int m_t = (int)(t % p.m_tiles);
-        const int64_t n_t = t / p.m_tiles;
-        const int wrow = m_t * CW + (int)rank * 128;
-        const int xrow = (int)(n_t * TR) + (int)rank * HALF;
-        for (int kb = 0; kb < nk; ++kb) {
-          if (p.l2_prefetch > 0) {
-            int kp = kb + p.l2_prefetch; int64_t tp = t;
-            if (kp >= nk) { kp -= nk; tp += npairs; }
-            if (kp < nk && tp < total_tiles) {
-              tma_prefetch_l2_2d(&map_x, kp * BKE, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
-              if (HM == 1) tma_prefetch_l2_2d(&map_x, kp * BKE + 32, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
-              if (HM == 2) tma_prefetch_l2_2d(&map_x2, kp * BKE, (int)((tp / p.m_tiles) * TR) + (int)rank * HALF);
-            }
+    // the whole warp walks the loop (waits are voted warp-uniform), one elected lane issues
+    int s = 0; uint32_t ph = 0; bool ok = true;
+    for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
+      int m_t; int64_t n_t;
+      tile_split(t, p.m_tiles, m_t, n_t);
+      const int wrow = m_t * CW + (int)rank * 128;
+      const int xrow = (int)(n_t * TR) + (int)rank * HALF;
+      int xrow_nx = -1;                                          // activation rows of this pair's next tile (L2 prefetch target)
+      if (p.l2_prefetch > 0 && t + npairs < total_tiles) {
+        int m_n; int64_t n_n;
+        tile_split(t + npairs, p.m_tiles, m_n, n_n);
+        xrow_nx = (int)(n_n * TR) + (int)rank * HALF;
+      }
+      for (int kb = 0; kb < nk; ++kb) {
+        if (p.l2_prefetch > 0) {
+          int kp = kb + p.l2_prefetch, xr = xrow;
+          if (kp >= nk) { kp -= nk; xr = xrow_nx; }
+          if (kp < nk && xr >= 0 && elect_one()) {
+            tma_prefetch_l2_2d(&map_x, kp * BKE, xr);
+            if (HM == 1) tma_prefetch_l2_2d(&map_x, kp * BKE + 32, xr);
+            if (HM == 2) tma_prefetch_l2_2d(&map_x2, kp * BKE, xr);
           }
-          if (!(ok = mbar_wait(bar_empty(s), ph ^ 1u, p.err))) break;
-          const uint32_t st = smem_base + s * T2_STAGE_BYTES;
+        }
+        if (!(ok = mbar_wait_warp(bar_empty(s), ph ^ 1u, p.err))) break;
+        const uint32_t st = smem_base + s * T2_STAGE_BYTES;
+        if (elect_one()) {
           if (FASTOP) {
-            mbar_expect_tx(bar_raw(s), T2_STAGE_BYTES);
-            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // fp16 tiles: 64 halfs x 128 weight rows, x HALF activation rows
-            tma_load_2d(st + TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
+            // DIRECT flavours: only the leader arms its barrier, for the bytes of BOTH CTAs; each CTA's loads report there
+            if (rank == 0) mbar_expect_tx(bar_raw(s), CG * T2_STAGE_BYTES);
+            tma_load_2d_cg<CG>(st, &map_w, bar_raw(s), kb * BKE, wrow);                // fp16 tiles: 64 halfs x 128 weight rows, x HALF activation rows
+            tma_load_2d_cg<CG>(st + TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
           } else if (HM == 2) {
-            mbar_expect_tx(bar_raw(s), T2_STAGE_BYTES);
-            tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // four fp16 tiles: 64 halfs x 128 (256 single-CTA) rows
-            tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * BKE, wrow);
-            tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
-            tma_load_2d(st + X_LO_OFF, &map_x2, bar_raw(s), kb * BKE, xrow);
+            if (rank == 0) mbar_expect_tx(bar_raw(s), CG * T2_STAGE_BYTES);
+            tma_load_2d_cg<CG>(st, &map_w, bar_raw(s), kb * BKE, wrow);                // four fp16 tiles: 64 halfs x 128 (256 single-CTA) rows
+            tma_load_2d_cg<CG>(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * BKE, wrow);
+            tma_load_2d_cg<CG>(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);
+            tma_load_2d_cg<CG>(st + X_LO_OFF, &map_x2, bar_raw(s), kb * BKE, xrow);
           } else if (H16) {
             mbar_expect_tx(bar_raw(s), 4 * TC_TILE_BYTES);
             tma_load_2d(st, &map_w, bar_raw(s), kb * BKE, wrow);                       // fp16 tiles: 64 halfs x 128 rows
@@ -211,29 +261,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             tma_load_2d(st + 4 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE, xrow);    // raw fp32: two 32-float boxes
             tma_load_2d(st + 5 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * BKE + 32, xrow);
           } else {
-          mbar_expect_tx(bar_raw(s), (p.passes == 3 ? 3 : 2) * TC_TILE_BYTES);
-          tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, wrow);
-          if (p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, wrow);
-          tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, xrow);
+            mbar_expect_tx(bar_raw(s), (p.passes == 3 ? 3 : 2) * TC_TILE_BYTES);
+            tma_load_2d(st, &map_w, bar_raw(s), kb * TC_BK, wrow);
+            if (p.passes == 3) tma_load_2d(st + TC_TILE_BYTES, &map_wlo, bar_raw(s), kb * TC_BK, wrow);
+            tma_load_2d(st + 2 * TC_TILE_BYTES, &map_x, bar_raw(s), kb * TC_BK, xrow);
           }
-          if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ======================================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // ======================================================================== MMA issuer (leader CTA only; one elected lane issues)
+    if (rank == 0) {
       int s = 0, a = 0; uint32_t ph = 0, aph = 0; bool ok = true;
       for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
-        if (!(ok = mbar_wait(bar_tempty(a), aph ^ 1u, p.err))) break;
+        if (!(ok = mbar_wait_warp(bar_tempty(a), aph ^ 1u, p.err))) break;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(a * T2_BN);
         for (int kb = 0; kb < nk; ++kb) {
-          if (!(ok = mbar_wait(bar_split(s), ph, p.err))) break;
+          if (!(ok = mbar_wait_warp(DIRECT ? bar_raw(s) : bar_split(s), ph, p.err))) break;
           tc_fence_after();
           const uint32_t st = smem_base + s * T2_STAGE_BYTES;
           const uint64_t w_hi = umma_desc_sw128(st), w_lo = umma_desc_sw128(st + TC_TILE_BYTES);
           const uint64_t x_hi = umma_desc_sw128(st + X_TILE * TC_TILE_BYTES), x_lo = umma_desc_sw128(st + X_LO_OFF);
+          if (elect_one()) {
           if (HM == 4) {                                         // single-pass TF32 on raw fp32 activations (8 floats = 32 B per MMA)
 #pragma unroll
             for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
@@ -260,20 +312,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 umma_f16_1cta(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
               }
             }
-          } else
+          } else {
 #pragma unroll
-          for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-            const uint64_t adv = (uint64_t)(k8 * 2);
-            if (p.passes == 3) {
-              umma_tf32_2cta(tmem_d, w_lo + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
-              umma_tf32_2cta(tmem_d, w_hi + adv, x_lo + adv, idesc, 1u);
-              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
-            } else {
-              umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
+            for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+              const uint64_t adv = (uint64_t)(k8 * 2);
+              if (p.passes == 3) {
+                umma_tf32_2cta(tmem_d, w_lo + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
+                umma_tf32_2cta(tmem_d, w_hi + adv, x_lo + adv, idesc, 1u);
+                umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, 1u);
+              } else {
+                umma_tf32_2cta(tmem_d, w_hi + adv, x_hi + adv, idesc, (kb | k8) ? 1u : 0u);
+              }
             }
           }
           umma_commit_cg<CG>(bar_empty(s));
           if (kb == nk - 1) umma_commit_cg<CG>(bar_tfull(a));
+          }
+          __syncwarp();
           if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
         }
         if (++a == T2_ACC) { a = 0; aph ^= 1u; }
@@ -282,16 +337,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   } else if (warp < T2_EPI_WARP0) {
     // ======================================================================== splitter: X_lo = x - trunc_tf32(x)
     const int tid = threadIdx.x - T2_SPLIT_WARP0 * 32;
-    int s = 0; uint32_t ph = 0; bool ok = true;
+    int s = 0; uint32_t ph = 0; bool ok = !DIRECT;            // ready-made operands: the TMA engine signals the issuer itself
     for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
       for (int kb = 0; kb < nk; ++kb) {
         if (!(ok = mbar_wait(bar_raw(s), ph, p.err))) break;
         uint8_t* st = smem_gen + s * T2_STAGE_BYTES;
-        if (HM >= 2) {                                            // operands arrive ready-made: forward the arrival
-          if (rank == 0) mbar_arrive(bar_split(s)); else mbar_arrive_cluster(bar_split(s), 0);
-          if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
-          continue;
-        }
         if (H16) {
           // raw fp32 boxes (128B-swizzled rows of 32 floats) -> fp16 hi / lo tiles in the same swizzled K-major layout:
           // item (r, c) = 8 consecutive k of row r: two 16-byte raw chunks in, one 16-byte chunk out per tile
@@ -360,8 +410,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
       lt_desc = smem_u32(tsm) + (uint32_t)(q * 32 + lane) * 8u;
     }
     for (int64_t t = pair; t < total_tiles && ok; t += npairs) {
-      const int m_t = (int)(t % p.m_tiles);
-      const int64_t n_t = t / p.m_tiles;
+      int m_t; int64_t n_t;
+      tile_split(t, p.m_tiles, m_t, n_t);
       const int c = m_t * CW + (int)rank * 128 + q * 32 + lane;
       const float bia = p.bias ? p.bias[c] : 0.0f;
       const float sc = p.scale ? p.scale[c] : 1.0f;
@@ -482,15 +532,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
         }
       } else {
-      float mx[8];                                            // EXTRA == 4: running max per step t of patch mx_patch
+      // EXTRA == 4 (conv5 + max over the patch's points): the epilogue function f = act(BN(acc * acc_scale + bias)) is a chain of
+      // monotone roundings, non-decreasing in acc * sgn(BN scale), so max_j f(acc_j) == f(sgn * max_j(sgn * acc_j)) exactly: the
+      // RAW oriented accumulators are pooled (one multiply + a share of a max per element) and f runs once per (patch, step,
+      // channel) at the flush.  mx[q8] = running max of step q8 of patch mx_patch.
+      static_assert(EXTRA != 4 || ACT == ACT_NONE || ACT == ACT_LEAKY, "the pooled epilogue needs a monotone activation");
+      float mx[8];
       int64_t mx_patch = -1;
+      const float sgn = sc < 0.0f ? -1.0f : 1.0f;
 #pragma unroll
       for (int q8 = 0; q8 < 8; ++q8) mx[q8] = -INFINITY;
       auto pool_flush = [&]() {
         if (mx_patch >= 0) {
 #pragma unroll
           for (int q8 = 0; q8 < 8; ++q8)
-            if (q8 < p.pool_T && mx[q8] > -INFINITY) atomic_max_float(p.pool + (mx_patch * p.pool_T + q8) * p.N + c, mx[q8]);
+            if (q8 < p.pool_T && mx[q8] > -INFINITY) {
+              const float m = mx[q8] * sgn;
+              float y = fmaf((H16 ? m * p.acc_scale : m) + bia, sc, sh);
+              if (ACT == ACT_LEAKY) y = act_leaky(y);
+              atomic_max_float(p.pool + (mx_patch * p.pool_T + q8) * p.N + c, y);
+            }
         }
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) mx[q8] = -INFINITY;
@@ -504,23 +565,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         const int64_t r0 = n_t * T2_BN + col0;
         const int nrows = (int)((p.R - r0) < 32 ? (p.R - r0) : 32);
         if (nrows > 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf((H16 ? v[j] * p.acc_scale : v[j]) + bia, sc, sh);
-          if (EXTRA == 1) {
-            const float* rp = p.residual + r0 * p.ldr + c;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { if (j < nrows) v[j] += *rp; rp += p.ldr; }
-          }
-          if (ACT == ACT_LEAKY) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_leaky(v[j]);
-          }
           if (EXTRA == 4) {
-            const int64_t patch = r0 / p.pool_rows;
-            const int64_t prow = r0 - patch * p.pool_rows;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= sgn;
+            int64_t patch; uint32_t prow;                         // r0 = patch * pool_rows + prow (32-bit divide when it fits)
+            if ((uint64_t)r0 <= 0xffffffffull && (uint64_t)p.pool_rows <= 0xffffffffull) {
+              const uint32_t pq = (uint32_t)r0 / (uint32_t)p.pool_rows;
+              patch = pq; prow = (uint32_t)r0 - pq * (uint32_t)p.pool_rows;
+            } else { patch = r0 / p.pool_rows; prow = (uint32_t)(r0 - patch * p.pool_rows); }
             const int lim1 = (int)((p.pool_rows - prow) < nrows ? (p.pool_rows - prow) : nrows);   // rows still in `patch`
             if (patch != mx_patch) { pool_flush(); mx_patch = patch; }
-            int tt = (int)(prow % p.pool_T);
+            int tt = p.pool_T == 7 ? (int)(prow % 7u) : (int)(prow % (uint32_t)p.pool_T);
+            if (p.pool_T == 7 && lim1 == 32) {
+              // whole chunk inside one patch, rows = (point, step) with 7 steps: the rows of residue s (mod 7) share a step
+              float a7[7];
+#pragma unroll
+              for (int s7 = 0; s7 < 7; ++s7) {
+                a7[s7] = v[s7];
+#pragma unroll
+                for (int j = s7 + 7; j < 32; j += 7) a7[s7] = fmaxf(a7[s7], v[j]);
+              }
+#pragma unroll
+              for (int r7 = 0; r7 < 7; ++r7)
+                if (tt == r7) {
+#pragma unroll
+                  for (int s7 = 0; s7 < 7; ++s7) mx[(r7 + s7) % 7] = fmaxf(mx[(r7 + s7) % 7], a7[s7]);
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < lim1) {
@@ -541,7 +612,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 }
               }
             }
+            }
           } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf((H16 ? v[j] * p.acc_scale : v[j]) + bia, sc, sh);
+          if (EXTRA == 1) {
+            const float* rp = p.residual + r0 * p.ldr + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { if (j < nrows) v[j] += *rp; rp += p.ldr; }
+          }
+          if (ACT == ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_leaky(v[j]);
+          }
           float* yp = p.Y + r0 * p.ldc + c;
           if (nrows == 32) {
 #pragma unroll
@@ -625,7 +708,7 @@ bool gemm_tc2_fast_tf32(const GemmArgs& g) {
 
 namespace {
 constexpr size_t t2_smem_fast(bool lt, uint32_t tab_stride, int cg = 2) {
-  return (size_t)(lt ? (cg == 2 ? 3 : 2) : 4) * (cg == 2 ? 2 : 3) * TC_TILE_BYTES + 1024 + 256 + (lt ? tab_stride : 0);
+  return (size_t)(lt ? (cg == 2 ? 3 : 2) : (cg == 2 ? SAPCU_T2_FAST_STAGES : 4)) * (cg == 2 ? 2 : 3) * TC_TILE_BYTES + 1024 + 256 + (lt ? tab_stride : 0);
 }
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per device
 int t2_set_attrs_impl() {

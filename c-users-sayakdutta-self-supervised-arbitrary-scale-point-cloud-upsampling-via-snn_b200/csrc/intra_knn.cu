@@ -8,8 +8,9 @@
 // feature-space graphs of fd blocks 1..3 (C=64/128/256, rows `ld` floats apart).
 //   * <f_i, f_j> is bitwise symmetric (same products, same order), so only the 4x4 register blocks on or above the
 //     diagonal are accumulated (325 of 625 for M = 100) and each feeds both score[i][j] and score[j][i];
-//   * top-k: scores become order-preserving 32-bit keys; per extraction one REDUX.MAX finds the best key in the warp and
-//     one REDUX.MIN the lowest index holding it -- ~20 instructions instead of a 5-round shuffle tournament.
+//   * top-k: scores become order-preserving 32-bit keys, each lane keeps its 4 candidates sorted; per extraction one
+//     REDUX.MAX over the lanes' heads finds the best key and one REDUX.MIN the lowest index holding it, the owner shifts
+//     its list -- ~12 instructions, no divergence.
 // Roofline: shared-memory / issue bound; HBM traffic M*C*4 B in, M*k*4 B out per patch.
 #include "common.cuh"
 #include "kernels.h"
@@ -110,33 +111,40 @@ intra_knn_kernel(const float* __restrict__ feat, int64_t ld, int M, int C, int k
     }
   }
   __syncthreads();
-  // top-k per row: one warp per row, 4 candidates per lane (j = lane + 32 q)
+  // top-k per row: one warp per row, 4 candidates per lane (j = lane + 32 q) kept SORTED (key descending, index ascending
+  // among equal keys) so that the lane's best candidate is always key[0]: retiring a winner is a predicated shift instead of
+  // a divergent rescan, and the winners go to the row's own (consumed) score storage, then out in coalesced stores
   const int warp = tid >> 5, lane = tid & 31;
   int32_t* o = out + (int64_t)blockIdx.x * M * k;
   for (int i = warp; i < M; i += IK_THREADS / 32) {
-    uint32_t key[4];
+    uint32_t key[4], id[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const int j = lane + 32 * q; key[q] = (j < M) ? ik_key(__fadd_rn(sc[i * ss + j], 0.0f)) : 0u; }   // (-0 -> +0: equal scores, equal keys)
-    uint32_t bk = key[0]; int bq = 0;
-#pragma unroll
-    for (int q = 1; q < 4; ++q) if (key[q] > bk) { bk = key[q]; bq = q; }
-    int res = 0;
+    for (int q = 0; q < 4; ++q) {
+      const int j = lane + 32 * q;
+      key[q] = (j < M) ? ik_key(__fadd_rn(sc[i * ss + j], 0.0f)) : 0u;   // (-0 -> +0: equal scores, equal keys)
+      id[q] = (uint32_t)j;
+    }
+    auto cex = [&](int x, int y) {                           // order (x, y): larger key first, then lower index
+      const bool sw = key[x] < key[y] || (key[x] == key[y] && id[x] > id[y]);
+      const uint32_t kx = sw ? key[y] : key[x], ky = sw ? key[x] : key[y], ix = sw ? id[y] : id[x], iy = sw ? id[x] : id[y];
+      key[x] = kx; key[y] = ky; id[x] = ix; id[y] = iy;
+    };
+    cex(0, 1); cex(2, 3); cex(0, 2); cex(1, 3); cex(1, 2);
+    uint32_t ids = id[0] | (id[1] << 8) | (id[2] << 16) | (id[3] << 24);   // indices < 128: one byte each, head in the low byte
+    __syncwarp();                                            // every lane has read its scores: the row is free for the winners
+    int32_t* res = reinterpret_cast<int32_t*>(sc + i * ss);
     for (int t = 0; t < k; ++t) {
-      const uint32_t best = __reduce_max_sync(0xffffffffu, bk);
-      const uint32_t w = __reduce_min_sync(0xffffffffu, bk == best ? (uint32_t)(lane + 32 * bq) : 0xffffffffu);
-      if ((t & 31) == lane) res = (int)w;
-      if ((int)(w & 31u) == lane) {                       // the owner retires the winner and rescans its 4 candidates
-        const int wq = (int)(w >> 5);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (wq == q) key[q] = 0u;
-        bk = key[0]; bq = 0;
-#pragma unroll
-        for (int q = 1; q < 4; ++q) if (key[q] > bk) { bk = key[q]; bq = q; }
-      }
-      if ((t & 31) == 31 || t == k - 1) {                 // coalesced store of up to 32 results
-        if (lane <= (t & 31)) o[i * k + (t & ~31) + lane] = res;
+      const uint32_t best = __reduce_max_sync(0xffffffffu, key[0]);
+      const uint32_t head = ids & 0xffu;
+      const uint32_t w = __reduce_min_sync(0xffffffffu, key[0] == best ? head : 0xffffffffu);
+      if (key[0] == best && w == head) {                     // the owner records and retires the winner
+        res[t] = (int32_t)w;
+        key[0] = key[1]; key[1] = key[2]; key[2] = key[3]; key[3] = 0u;
+        ids >>= 8;
       }
     }
+    __syncwarp();
+    for (int t = lane; t < k; t += 32) o[i * k + t] = res[t];
   }
 }
 
