@@ -114,6 +114,8 @@ struct G {
     const bool prof = prof_begin(st, g.label, w, &slot);
     int rc;
     g.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
+    // fast mode, plain point-level contractions: single-pass TF32 needs no operand split -> the compact-stage flavour
+    if (mode == SAPCU_MODE_FAST && amode == A_PLAIN && g.act == ACT_NONE && !g.residual && !g.at_pos && !g.pool && !g.x_h2 && !g.out_h2 && !g.edge_bias) g.fast = true;
     if (mode != SAPCU_MODE_FP32 && gemm_tc2_supported(g, amode)) rc = launch_gemm_tc2(g, st);
     else if (mode != SAPCU_MODE_FP32 && gemm_tc_supported(g, amode)) rc = launch_gemm_tc(g, amode, st);
     else rc = launch_gemm_simt(g, amode, mode == SAPCU_MODE_FP32, st);

@@ -66,7 +66,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
   asm volatile(
       "{\n\t.reg .b32 remAddr32;\n\t"
       "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
       ::"r"(bar), "r"(cta)
       : "memory");
 }
@@ -702,8 +702,10 @@ bool gemm_tc2_fast(const GemmArgs& g) {
 // SAPCU_MODE_FAST, point-level LIF layers (fp32 activations in and out): single-pass TF32 with compact stages, so that the
 // layer's LIF table fits next to the pipeline (HM = 4)
 bool gemm_tc2_fast_tf32(const GemmArgs& g) {
-  return g.fast && !g.x_h2 && !g.out_h2 && g.act == ACT_LIF && !g.edge_bias && !g.residual && !g.at_pos && !g.pool &&
-         g.Whi && g.K % TC_BK == 0;
+  // LIF layers (any width the engine takes) and plain 256-channel-multiple layers: the operands need no splitter, so they ride
+  // the direct TMA -> issuer protocol of the compact-stage flavour
+  return g.fast && !g.x_h2 && !g.out_h2 && (g.act == ACT_LIF || (g.act == ACT_NONE && g.N % 256 == 0)) && !g.edge_bias && !g.residual &&
+         !g.at_pos && !g.pool && g.Whi && g.K % TC_BK == 0;
 }
 
 namespace {
@@ -741,6 +743,7 @@ int t2_set_attrs_impl() {
 #undef SAPCU_T2_ATTR_P1
 #define SAPCU_T2_ATTR_T(LTQ, CGQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 0, 1, 4, LTQ, CGQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_fast(LTQ != 0, LT_SMEM_BUDGET, CGQ)))
   SAPCU_T2_ATTR_T(0, 1); SAPCU_T2_ATTR_T(1, 1); SAPCU_T2_ATTR_T(0, 2); SAPCU_T2_ATTR_T(1, 2);
+  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_NONE, 0, 1, 4, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_fast(false, 0, 2)));
 #undef SAPCU_T2_ATTR_T
   return 0;
 }
@@ -796,7 +799,7 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   const int64_t total = p.n_tiles * p.m_tiles;
   int pairs = (int)(total < kNumSMs / cg ? total : kNumSMs / cg);
   if (fast_tf32) {
-    const bool lt = g.lif_tab != nullptr && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET;
+    const bool lt = g.act == ACT_LIF && g.lif_tab != nullptr && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET;
     if (lt) pairs = (pairs / p.m_tiles) * p.m_tiles;
     SAPCU_REQUIRE(pairs >= 1, "gemm_tc2(fast tf32): empty grid");
     p.lif_tab = reinterpret_cast<const uint8_t*>(g.lif_tab); p.lif_tab_stride = g.lif_tab_stride;
@@ -804,7 +807,8 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
     const size_t smem = t2_smem_fast(lt, g.lif_tab_stride, cg);
     const int gridf = cg * pairs;
 #define SAPCU_T2_LAUNCH_T(LTQ, CGQ) gemm_tc2_kernel<ACT_LIF, 0, 1, 4, LTQ, CGQ><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p)
-    if (cg == 2) { if (lt) SAPCU_T2_LAUNCH_T(1, 2); else SAPCU_T2_LAUNCH_T(0, 2); }
+    if (g.act == ACT_NONE) gemm_tc2_kernel<ACT_NONE, 0, 1, 4, 0, 2><<<gridf, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p);
+    else if (cg == 2) { if (lt) SAPCU_T2_LAUNCH_T(1, 2); else SAPCU_T2_LAUNCH_T(0, 2); }
     else { if (lt) SAPCU_T2_LAUNCH_T(1, 1); else SAPCU_T2_LAUNCH_T(0, 1); }
 #undef SAPCU_T2_LAUNCH_T
     SAPCU_LAUNCH_CHECK();
