@@ -123,16 +123,22 @@ struct G {
     return rc;
   }
   // plain layer: Y[R, L.N] (ldc) = act(affine(X[R, L.K] (lda)))
-  int layer(const Layer& L, const float* X, int64_t lda, int64_t R, float* Y, int64_t ldc, int act,
-            const Neuron* nr = nullptr, int T = 0, const float* res = nullptr, int64_t ldr = 0, bool x_unit = false) const {
+  GemmArgs args(const Layer& L, const float* X, int64_t lda, int64_t R, float* Y, int64_t ldc, int act,
+                const Neuron* nr = nullptr, int T = 0, const float* res = nullptr, int64_t ldr = 0, bool x_unit = false) const {
     GemmArgs g;
     g.A = X; g.lda = lda; g.R = R; g.K = L.K; g.W = L.W; g.Whi = L.Whi; g.Wlo = L.Wlo; g.N = L.N; g.bias = L.bias; g.scale = L.scale; g.shift = L.shift;
     g.Wh = L.Wh; g.Wl = L.Wl; g.winv = L.winv; g.x_unit = x_unit;
     g.act = act; g.T = T; g.nparams = nr ? nr->np : nullptr; g.residual = res; g.ldr = ldr; g.Y = Y; g.ldc = ldc;
+    g.tc_passes = (mode == SAPCU_MODE_TF32 || mode == SAPCU_MODE_FAST) ? 1 : 3;
     if (mode == SAPCU_MODE_FAST && act == ACT_LIF && nr) {     // point-level LIF layers: compact single-pass TF32 stages + the layer's LIF table
       g.fast = true;
       if (settings().fast_tables && nr->tab_ok && nr->tab_T == T) { g.lif_tab = nr->tab; g.lif_tab_stride = nr->tab_stride; }
     }
+    return g;
+  }
+  int layer(const Layer& L, const float* X, int64_t lda, int64_t R, float* Y, int64_t ldc, int act,
+            const Neuron* nr = nullptr, int T = 0, const float* res = nullptr, int64_t ldr = 0, bool x_unit = false) const {
+    GemmArgs g = args(L, X, lda, R, Y, ldc, act, nr, T, res, ldr, x_unit);
     return run(g, A_PLAIN);
   }
 };
@@ -144,8 +150,8 @@ struct G {
 
 int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* normals, const FnPlan& p, int mode, int stop_block, cudaStream_t st) {
   const FnNet& f = mdl->fn;
-  int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0;
-  struct TapPublish { const sapcu_model* m; int* g; int* d; ~TapPublish() { m->tap_gamma.store(*g, std::memory_order_relaxed); m->tap_delta2.store(*d, std::memory_order_relaxed); } } tap_publish{mdl, &g_tap_gamma_h2, &g_tap_delta2_h2};
+  int g_tap_gamma_h2 = 0, g_tap_delta2_h2 = 0, g_tap_snn1_h2 = 0;
+  struct TapPublish { const sapcu_model* m; int* g; int* d; int* x; ~TapPublish() { m->tap_gamma.store(*g, std::memory_order_relaxed); m->tap_delta2.store(*d, std::memory_order_relaxed); m->tap_snn1.store(*x, std::memory_order_relaxed); } } tap_publish{mdl, &g_tap_gamma_h2, &g_tap_delta2_h2, &g_tap_snn1_h2};
   const int64_t P = s * M;
   const bool precise = mode == SAPCU_MODE_FP32;
   const G g{mode, st};
@@ -213,8 +219,28 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
     const int64_t E = P * kk;
     float* Xb = p.E1;                                             // this block's edge buffer (pos-enc layer 1, then fc_gamma's output)
     bool xb_h2 = false, e2_h2 = false, pos32 = false;             // fc_gamma's output / pos stored as fp16 planes (see below); + fp32 copy of pos
-    SAPCU_TRY(g.L("fn.fc1+lif").layer(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4));
-    SAPCU_TRY(g.L("fn.qkv+lif").layer(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4));
+    {
+      // Parity-grade mode, wide blocks: fc1's spikes have ONE reader, the q/k/v contraction -> handed over as fp16 (hi, lo)
+      // planes in the bytes of the fp32 tensor; q/k/v then runs fp16x3 products (the 22-bit products of 3xTF32 at twice the
+      // tensor rate, no splitter pass) and reads its LIF^T chains from the layer's table when it fits next to two stages.
+      GemmArgs a1 = g.args(k.fc1, fin, ldin, P, p.X, D, ACT_LIF, &k.snn1, 4);
+      GemmArgs a2 = g.args(k.qkv, p.X, D, P, p.QKV, 3 * D, ACT_LIF, &k.snn_qkv, 4);
+      bool x_planes = false;
+      if (mode == SAPCU_MODE_TC && settings().tc_qkv_planes) {
+        GemmArgs t1 = a1, t2 = a2;
+        t1.out_h2 = true; t2.x_h2 = true; t2.x_unit = true; t1.tc2_any_rows = t2.tc2_any_rows = true;
+        x_planes = D % 256 == 0 && gemm_tc2_supported(t1, A_PLAIN) && gemm_tc2_supported(t2, A_PLAIN) && gemm_tc2_fp16x3(t2);
+        if (x_planes) {
+          a1 = t1; a2 = t2;
+          if (settings().tc_tables && k.snn_qkv.tab_ok && k.snn_qkv.tab_T == 4 && k.snn_qkv.tab_stride <= LT_SMEM_BUDGET_TC) {
+            a2.lif_tab = k.snn_qkv.tab; a2.lif_tab_stride = k.snn_qkv.tab_stride;
+          }
+        }
+      }
+      g_tap_snn1_h2 = x_planes ? 1 : 0;
+      SAPCU_TRY(g.L("fn.fc1+lif").run(a1, A_PLAIN));
+      SAPCU_TRY(g.L("fn.qkv+lif").run(a2, A_PLAIN));
+    }
     if (mode == SAPCU_MODE_FP32) { g_tap_gamma_h2 = 0; g_tap_delta2_h2 = 0; SAPCU_TRY(edge_pos(b, Xb, st, 1, false)); }
     if (mode == SAPCU_MODE_FAST) {
       // Fast schedule: every per-edge spike tensor of the block is ONE fp16 plane of x * 2^13, every edge contraction one fp16
@@ -551,6 +577,7 @@ int sapcu_model_tap_format(const sapcu_model* m, const char* name) {
   const bool blk = nm.size() > 7 && nm.compare(0, 5, "trans") == 0 && nm[6] == '.';     // format of the last block the forward executed
   if (m->kind == SAPCU_MODEL_FN && blk && nm.substr(7) == "snn_gamma") return m->tap_gamma.load(std::memory_order_relaxed);
   if (m->kind == SAPCU_MODEL_FN && blk && nm.substr(7) == "snn_delta2") return m->tap_delta2.load(std::memory_order_relaxed);
+  if (m->kind == SAPCU_MODEL_FN && blk && nm.substr(7) == "snn1") return m->tap_snn1.load(std::memory_order_relaxed);
   if (m->kind == SAPCU_MODEL_FD && std::string(name) == "spikes") return m->tap_spk.load(std::memory_order_relaxed);
   return 0;
 }

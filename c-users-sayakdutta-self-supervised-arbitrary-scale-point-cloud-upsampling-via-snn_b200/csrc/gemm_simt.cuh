@@ -40,6 +40,7 @@ struct GemmArgs {
   float* Y = nullptr; int64_t ldc = 0;
   float* Y2 = nullptr;   // 2-CTA tensor-core engine, LIF epilogue writing fp16 planes: optional fp32 copy of the same spikes ([R, N], ld = N)
   int tc_passes = 3;     // tensor-core engine only: 3 = 3xTF32 split, 1 = single-pass TF32
+  bool tc2_any_rows = false;   // 2-CTA engine from 1024 rows on (plane-exchanging point-level layers: chunk-size independent arithmetic)
   // tensor-core engine only: fuse softmax_k(Y / at_sqrt) and sum_j a_j (at_v[nb_j] + at_pos[e_j]) into the epilogue; Y becomes [points, N]
   const float* at_pos = nullptr; const float* at_v = nullptr; int64_t at_ldv = 0; float at_sqrt = 1.0f;
   float* pool = nullptr; int pool_T = 0, pool_M = 0;   // 2-CTA tensor-core engine: rows are (point*T + t); instead of Y emit pool[(patch*T + t), c] = max over the patch's pool_M points (buffer pre-filled with -inf)

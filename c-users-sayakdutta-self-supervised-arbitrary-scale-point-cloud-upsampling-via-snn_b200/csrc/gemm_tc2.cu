@@ -675,7 +675,9 @@ bool gemm_tc2_supported(const GemmArgs& g, int amode) {
   // 128-channel layers: the single-CTA flavour takes ready-made operands only (fp16 planes of the parity-grade mode, fast-mode formats)
   if (g.N % 256 != 0 && !(g.N % 128 == 0 && (gemm_tc2_fast(g) || gemm_tc2_fast_tf32(g) || (g.x_h2 && gemm_tc2_fp16x3(g))))) return false;
   if (!g.Whi || !g.Wlo) return false;                       // pre-split weights only
-  if (g.R < 4096) return false;
+  // point-level layers that exchange fp16 planes keep their arithmetic (fp16x3 products) for every chunk size the tensor-core
+  // engines take at all (>= 1024 rows), so that the result does not depend on how a forward is chunked
+  if (g.R < (g.tc2_any_rows ? 1024 : 4096)) return false;
   if (g.pool) {
     if (g.at_pos || g.residual || g.edge_bias || g.act != ACT_LEAKY || g.pool_T < 1 || g.pool_T > 8 || g.pool_M < 1) return false;
     if (g.R % ((int64_t)g.pool_T * g.pool_M) != 0) return false;

@@ -56,5 +56,5 @@ struct sapcu_model {
   sapcu::FnNet fn;
   sapcu::FdNet fd;
   // storage format of the tapped spike tensors in the most recent forward on this handle (sapcu_model_tap_format)
-  mutable std::atomic<int> tap_gamma{0}, tap_delta2{0}, tap_spk{0};
+  mutable std::atomic<int> tap_gamma{0}, tap_delta2{0}, tap_spk{0}, tap_snn1{0};
 };
