@@ -140,6 +140,41 @@ __device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, in
   return __all_sync(0xffffffffu, mbar_wait(bar, parity, err));
 }
 
+// Store one 8-row piece of a LIF epilogue (one channel per thread): fmt 0 = fp32 rows, 1 = fp16 (hi, lo) planes of y * 2^13 (+ the
+// fp32 copy p.Y2 when set), 2 = one fp16 plane (fast mode).  LD > 0: compile-time row stride, whole piece (STG [base + imm]); LD == 0:
+// run-time stride, `nrows` valid rows.
+template <int LD>
+__device__ __forceinline__ void lif_store_piece(const TcParams& p, const float (&u)[8], int64_t r0, int c, int fmt, int nrows = 8) {
+  const uint32_t ld = LD ? (uint32_t)LD : (uint32_t)p.ldc;
+  const int64_t off = r0 * (LD ? (int64_t)LD : p.ldc) + c;
+  if (fmt == 2) {
+    __half* hp = reinterpret_cast<__half*>(p.Y) + off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (LD || j < nrows) hp[(uint32_t)j * ld] = __float2half_rn(u[j] * 8192.0f);
+  } else if (fmt == 1) {
+    if (p.Y2) {
+      float* y2p = p.Y2 + off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (LD || j < nrows) y2p[(uint32_t)j * ld] = u[j];
+    }
+    __half* hp = reinterpret_cast<__half*>(p.Y) + off;
+    __half* lp = hp + p.R * (LD ? (int64_t)LD : p.ldc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (LD || j < nrows) {
+        const float ys = u[j] * 8192.0f;
+        const __half h = __float2half_rn(ys);
+        hp[(uint32_t)j * ld] = h;
+        lp[(uint32_t)j * ld] = __float2half_rn(ys - __half2float(h));
+      }
+    }
+  } else {
+    float* yp = p.Y + off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (LD || j < nrows) yp[(uint32_t)j * ld] = u[j];
+  }
+}
+
 // H16 = fp16x3 operand format (activations known to be LIF outputs): W arrives as pre-split fp16 (hi, lo) of W * 2^e, the
 // splitter turns the raw fp32 activation tile into fp16 (hi, lo) of x * x_scale, and 12 kind::f16 MMAs per 64-wide
 // k-block (hi*hi + hi*lo + lo*hi, fp32 accumulate) replace 24 kind::tf32 ones: the same 22-bit products at twice the
@@ -440,7 +475,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
           }
         }
         if (part < parts)
-          attn_tail_points<KK>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T2_BN), part, parts, npts, n_t, c, bia, sc, sh, H16 ? p.acc_scale : 1.0f);
+          attn_tail_dispatch<KK>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T2_BN), part, parts, npts, n_t, c, bia, sc, sh, H16 ? p.acc_scale : 1.0f);
       } else if (ACT == ACT_LIF) {
         // 8 columns (= rows of Y) at a time: 24 state + 24 temporary registers leave ptxas room to interleave all 8
         // recurrences (with 32 accumulators live it serialised half of them); the next piece is loaded under the math
@@ -459,14 +494,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         for (int pc = 0; pc < CHUNKS * 4; ++pc) {
           float u[8];
           tmem_wait_ld8(nxt);
+          // LT: the accumulator's power-of-two scale is folded into the BatchNorm scale below (exact), no multiply here
 #pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = H16 ? nxt[j] * p.acc_scale : nxt[j];
+          for (int j = 0; j < 8; ++j) u[j] = (H16 && !LT) ? nxt[j] * p.acc_scale : nxt[j];
           if (pc + 1 < CHUNKS * 4) tmem_ld_piece<8>(tbase + (uint32_t)((pc + 1) * 8), nxt);
           const int64_t r0 = n_t * T2_BN + colw + pc * 8;
           const int nrows = (int)((p.R - r0) < 8 ? (p.R - r0) : 8);
+          float eb[8];                                            // LT: the edge bias joins the table coordinate's multiply-add
           if (EXTRA == 2) {                                       // fold this piece's bias in, fetch the next one under the LIF
 #pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] += qv[j] - kv[j];
+            for (int j = 0; j < 8; ++j) { if (LT) eb[j] = qv[j] - kv[j]; else u[j] += qv[j] - kv[j]; }
             if ((pc & 3) == 0 && pc + 4 < CHUNKS * 4) edge_lane_offsets(p, n_t * T2_BN + colw + (pc + 4) * 8, lane, nx_qo, nx_ko);
             if (pc + 1 < CHUNKS * 4) {
               if (((pc + 1) & 3) == 0) { my_qo = nx_qo; my_ko = nx_ko; }
@@ -477,8 +514,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             if (LT) {
               // one multiply-add from the (scaled) accumulator straight to the table coordinate x = BN(acc + bias) - theta0
               const float bx = fmaf(bia, sc, sh) - np.th0;
+              const float sca = H16 ? sc * p.acc_scale : sc;       // acc_scale is a power of two: acc * (scale * 2^-n) is exact
 #pragma unroll
-              for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j], sc, bx);
+              for (int j = 0; j < 8; ++j) u[j] = fmaf(u[j], sca, EXTRA == 2 ? fmaf(eb[j], sc, bx) : bx);
               float x0[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) x0[j] = u[j];
@@ -492,43 +530,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
               if (FASTOP) lif_chain_vec_fast2<8>(u, np, p.T);
               else lif_chain_vec_fast<8>(u, np, p.T);
             }
-            float* yp = p.Y + r0 * p.ldc + c;
-            if (HM == 3 && p.out_h2 == 2) {                       // fast mode: ONE fp16 plane of y * 2^13
-              __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
-              const uint32_t ld = (uint32_t)p.ldc;                 // one 64-bit multiply-add (IMAD.WIDE) per row address
-              if (nrows == 8) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) hp[(uint32_t)j * ld] = __float2half_rn(u[j] * 8192.0f);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (j < nrows) hp[(uint32_t)j * ld] = __float2half_rn(u[j] * 8192.0f);
-              }
-            } else if (p.out_h2) {                                // fp16 (hi, lo) planes of y * 2^13 for a fp16x3 consumer
-              if (p.Y2) {                                         // + the fp32 copy a gathering reader (the attention tail) prefers
-                float* y2p = p.Y2 + r0 * p.ldc + c;
-                const uint32_t ld2 = (uint32_t)p.ldc;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) if (j < nrows) y2p[(uint32_t)j * ld2] = u[j];
-              }
-              __half* hp = reinterpret_cast<__half*>(p.Y) + r0 * p.ldc + c;
-              __half* lp = hp + p.R * p.ldc;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (j < nrows) {
-                  const float ys = u[j] * 8192.0f;
-                  const __half h = __float2half_rn(ys);
-                  hp[(int64_t)j * p.ldc] = h;
-                  lp[(int64_t)j * p.ldc] = __float2half_rn(ys - __half2float(h));
-                }
-              }
-            } else if (nrows == 8) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { *yp = u[j]; yp += p.ldc; }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { if (j < nrows) *yp = u[j]; yp += p.ldc; }
-            }
+            // whole pieces (all but the tensor's last rows) with one of the model's row strides: the stride becomes a compile-time
+            // constant and every store of the piece an immediate offset from ONE base address per output tensor
+            const int fmt = (HM == 3 && p.out_h2 == 2) ? 2 : p.out_h2 ? 1 : 0;
+            const int64_t ld = p.ldc;
+            if (nrows == 8 && ld == 512) lif_store_piece<512>(p, u, r0, c, fmt);
+            else if (nrows == 8 && ld == 256) lif_store_piece<256>(p, u, r0, c, fmt);
+            else if (nrows == 8 && ld == 128) lif_store_piece<128>(p, u, r0, c, fmt);
+            else if (nrows == 8 && ld == 1536) lif_store_piece<1536>(p, u, r0, c, fmt);
+            else if (nrows == 8 && ld == 768) lif_store_piece<768>(p, u, r0, c, fmt);
+            else lif_store_piece<0>(p, u, r0, c, fmt, nrows);
           }
         }
       } else {

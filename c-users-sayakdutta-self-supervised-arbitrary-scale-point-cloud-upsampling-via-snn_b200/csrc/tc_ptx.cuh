@@ -236,9 +236,12 @@ __device__ __forceinline__ void edge_fetch8(const TcParams& p, int my_qo, int my
 // pp*KK .. pp*KK+KK-1 of this thread's channel c) -> /sqrt(d_h) -> softmax over the KK edges -> sum_j a_j (v[nb_j] + pos[e_j]).
 // Latency plan per point: the neighbour indices were fetched one point ahead; the 2*KK operand loads are issued first,
 // the TMEM read and the softmax run under them, the weighted sum consumes them last.
-template <int KK>
+// NC > 0: the channel count (row stride of pos and of the output) as a compile-time constant -- the KK pos loads of a point
+// become immediate offsets from one base address; NC == 0: run-time p.N.
+template <int KK, int NC = 0>
 __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tmem_cols, int part, int parts, int npts,
                                                  int64_t n_t, int c, float bia, float sc, float sh, float acc_scale) {
+  const int64_t Nn = NC ? (int64_t)NC : (int64_t)p.N;
   const int64_t P_total = p.R / KK;
   const float inv_s = 1.0f / p.at_sqrt;
   const float* vc = p.at_v + c;
@@ -257,44 +260,67 @@ __device__ __forceinline__ void attn_tail_points(const TcParams& p, uint32_t tme
     for (int j = 0; j < KK; ++j) nbn[j >> 2] |= (uint32_t)ip[j] << (8 * (j & 3));
   };
   fetch_row(n_t * npts + part);
-  for (int pp = part; pp < npts; pp += parts) {
+  // first point of the patch that holds this warp's current point: one division per tile, then advanced with the point
+  int64_t patch0 = ((n_t * npts + part) / p.Mpts) * p.Mpts;
+  int prem = (int)(n_t * npts + part - patch0);
+  for (int pp = part; pp < npts; pp += parts, prem += parts) {
     const int64_t pt = n_t * npts + pp;
     if (pt >= P_total) break;                                    // warp-uniform
-    const int64_t patch0 = (pt / p.Mpts) * p.Mpts;
-    const float* ps = p.at_pos + (pt * KK) * (int64_t)p.N + c;
+    while (prem >= p.Mpts) { prem -= p.Mpts; patch0 += p.Mpts; }
+    const float* ps = p.at_pos + (pt * KK) * Nn + c;
     float vr[KK], pr[KK];
     __half prh[KK];                                              // fast mode: the raw halves, converted only where they are consumed
+    // v[nb_j]: one 64-bit base per point, then byte extract (PRMT) + one 32 x 32 -> 64-bit multiply-add (IMAD.WIDE) per neighbour
+    uint64_t vb = (uint64_t)__cvta_generic_to_global(vc) + (uint64_t)(patch0 * p.at_ldv * 4);
+    asm volatile("" : "+l"(vb));                                 // ONE 64-bit base value: the per-neighbour address is a single IMAD.WIDE
+    uint32_t ldvb = (uint32_t)p.at_ldv * 4u;
+    asm volatile("" : "+r"(ldvb));
 #pragma unroll
-    for (int j = 0; j < KK; ++j) vr[j] = vc[(patch0 + (int64_t)((nbn[j >> 2] >> (8 * (j & 3))) & 255u)) * p.at_ldv];
+    for (int j = 0; j < KK; ++j) {
+      const uint32_t nb = __byte_perm(nbn[j >> 2], 0u, 0x4440u + (uint32_t)(j & 3));
+      const uint64_t a = vb + (uint64_t)nb * ldvb;
+      asm("ld.global.f32 %0, [%1];" : "=f"(vr[j]) : "l"(a));     // v was written by an earlier kernel of the stream
+    }
     if (p.pos_h2 == 2) {                                         // fast mode: one fp16 plane of pos * 2^13
-      const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * (int64_t)p.N + c;
+      const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * Nn + c;
 #pragma unroll
-      for (int j = 0; j < KK; ++j) prh[j] = ph[(int64_t)j * p.N];
+      for (int j = 0; j < KK; ++j) prh[j] = ph[(int64_t)j * Nn];
     } else if (p.pos_h2) {
-      const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * (int64_t)p.N + c;
-      const __half* pl = ph + p.R * (int64_t)p.N;
+      const __half* ph = reinterpret_cast<const __half*>(p.at_pos) + (pt * KK) * Nn + c;
+      const __half* pl = ph + p.R * Nn;
 #pragma unroll
-      for (int j = 0; j < KK; ++j) pr[j] = (__half2float(ph[(int64_t)j * p.N]) + __half2float(pl[(int64_t)j * p.N])) * (1.0f / 8192.0f);
+      for (int j = 0; j < KK; ++j) pr[j] = (__half2float(ph[(int64_t)j * Nn]) + __half2float(pl[(int64_t)j * Nn])) * (1.0f / 8192.0f);
     } else {
 #pragma unroll
-      for (int j = 0; j < KK; ++j) pr[j] = ps[(int64_t)j * p.N];
+      for (int j = 0; j < KK; ++j) pr[j] = ps[(int64_t)j * Nn];
     }
     fetch_row(pt + parts);                                       // indices of this warp's next point (clamped at the end)
     float av[KK];
     __syncwarp();
     tmem_ld_cols<KK>(tmem_cols + (uint32_t)(pp * KK), av);
+    // softmax over the point's KK logits l_j = t_j / sqrt(d_h), t = BN(acc + bias): exp(l_j - max l) = 2^(t_j * k - max(t) * k) with
+    // k = log2(e) / sqrt(d_h) > 0 -- one multiply-add per edge; the normalisation is applied once to the weighted sum
     float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < KK; ++j) { av[j] = fmaf(fmaf(av[j], acc_scale, bia), sc, sh) * inv_s; mx = fmaxf(mx, av[j]); }
+    for (int j = 0; j < KK; ++j) { av[j] = fmaf(fmaf(av[j], acc_scale, bia), sc, sh); mx = fmaxf(mx, av[j]); }
+    const float kexp = inv_s * 1.4426950408889634f, mxk = -mx * kexp;
     float sum = 0.0f;
 #pragma unroll
-    for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx((av[j] - mx) * 1.4426950408889634f); sum += av[j]; }
-    const float inv_sum = 1.0f / sum;
+    for (int j = 0; j < KK; ++j) { av[j] = exp2f_approx(fmaf(av[j], kexp, mxk)); sum += av[j]; }
     float res = 0.0f;
 #pragma unroll
-    for (int j = 0; j < KK; ++j) res = fmaf(av[j] * inv_sum, vr[j] + (p.pos_h2 == 2 ? __half2float(prh[j]) * (1.0f / 8192.0f) : pr[j]), res);
-    p.Y[pt * p.ldc + c] = res;
+    for (int j = 0; j < KK; ++j) res = fmaf(av[j], p.pos_h2 == 2 ? fmaf(__half2float(prh[j]), 1.0f / 8192.0f, vr[j]) : vr[j] + pr[j], res);   // 2^-13 * half is exact: same sum
+    p.Y[pt * (NC ? (int64_t)NC : p.ldc) + c] = res * (1.0f / sum);
   }
+}
+
+// the yaml model pairs each neighbour count with one width (24 / 128, 18 / 256, 12 / 512): those get the compile-time stride
+template <int KK>
+__device__ __forceinline__ void attn_tail_dispatch(const TcParams& p, uint32_t tmem_cols, int part, int parts, int npts,
+                                                   int64_t n_t, int c, float bia, float sc, float sh, float acc_scale) {
+  constexpr int NY = KK == 24 ? 128 : KK == 18 ? 256 : KK == 12 ? 512 : 0;
+  if (NY != 0 && p.N == NY && p.ldc == NY) attn_tail_points<KK, NY>(p, tmem_cols, part, parts, npts, n_t, c, bia, sc, sh, acc_scale);
+  else attn_tail_points<KK, 0>(p, tmem_cols, part, parts, npts, n_t, c, bia, sc, sh, acc_scale);
 }
 
 // host helpers (gemm_tc.cu)
