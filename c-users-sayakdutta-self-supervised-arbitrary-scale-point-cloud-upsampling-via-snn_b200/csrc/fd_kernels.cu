@@ -95,6 +95,11 @@ edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __
   }
   const int mq = (Mpts + 3) >> 2;
   const int i_begin = quarter * mq, i_end = min(Mpts, i_begin + mq);
+  // output bases of this patch for this thread's channel pair (offsets inside a patch fit 32 bits: Mpts * T * ldo halfs, checked on the host)
+  __half* const hb = reinterpret_cast<__half*>(spk) + patch0 * T * (int64_t)ldo + choff + c;
+  __half* const lb = hb + plane;
+  float* const s0b = spk0 + patch0 * (int64_t)ldo + choff + c;
+  float* const fb = spk + patch0 * ldspk_row + c;
   const float2* Pc = reinterpret_cast<const float2*>(Ps) + tp;      // row stride 64 float2
   constexpr int NP = EGU_PTS / 2;                                  // points per pass: NP x 2 channels = EGU_PTS recurrences
   for (int i0 = i_begin; i0 < i_end; i0 += NP) {
@@ -133,22 +138,27 @@ edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __
       s[2 * a] = neuron_step_fast<EIF, true>(u[2 * a], m[2 * a], th[2 * a], rho[2 * a], k0);
       s[2 * a + 1] = neuron_step_fast<EIF, true>(u[2 * a + 1], m[2 * a + 1], th[2 * a + 1], rho[2 * a + 1], k1);
     }
-    auto put = [&](int a, int t, float v0, float v1) {
+    // stores: per-thread 64-bit bases of the PATCH (hb / lb / s0b / fb, set up once per CTA) + 32-bit offsets inside it that
+    // advance by one row per step -- one multiply-add per address instead of a 64-bit (row * T + t) * ldo product per store
+    uint32_t offs[NP];
+#pragma unroll
+    for (int a = 0; a < NP; ++a) offs[a] = h2 ? (uint32_t)(i0 + a) * (uint32_t)T * (uint32_t)ldo : (uint32_t)(i0 + a) * (uint32_t)ldspk_row;
+    auto put = [&](int a, bool first, float v0, float v1) {
       if (h2) {
-        __half* hp = reinterpret_cast<__half*>(spk) + ((patch0 + i0 + a) * T + t) * (int64_t)ldo + choff + c;
         const float y0 = v0 * 8192.0f, y1 = v1 * 8192.0f;
         const __half2 hv = __floats2half2_rn(y0, y1);
         const float2 hf = __half22float2(hv);
-        *reinterpret_cast<__half2*>(hp) = hv;
-        if (plane) *reinterpret_cast<__half2*>(hp + plane) = __floats2half2_rn(y0 - hf.x, y1 - hf.y);   // plane == 0: hi plane only (fast mode)
-        if (t == 0) *reinterpret_cast<float2*>(spk0 + (patch0 + i0 + a) * (int64_t)ldo + choff + c) = make_float2(v0, v1);
+        *reinterpret_cast<__half2*>(hb + offs[a]) = hv;
+        if (plane) *reinterpret_cast<__half2*>(lb + offs[a]) = __floats2half2_rn(y0 - hf.x, y1 - hf.y);   // plane == 0: hi plane only (fast mode)
+        if (first) *reinterpret_cast<float2*>(s0b + (uint32_t)(i0 + a) * (uint32_t)ldo) = make_float2(v0, v1);
       } else {
-        *reinterpret_cast<float2*>(spk + (patch0 + i0 + a) * ldspk_row + (int64_t)t * ldo + c) = make_float2(v0, v1);
+        *reinterpret_cast<float2*>(fb + offs[a]) = make_float2(v0, v1);
       }
+      offs[a] += (uint32_t)ldo;
     };
 #pragma unroll
     for (int a = 0; a < NP; ++a)
-      if (i0 + a < i_end) put(a, 0, s[2 * a], s[2 * a + 1]);
+      if (i0 + a < i_end) put(a, true, s[2 * a], s[2 * a + 1]);
     for (int t = 1; t < T; ++t) {
 #pragma unroll
       for (int a = 0; a < NP; ++a) {
@@ -157,7 +167,7 @@ edge_gather_unroll_kernel(const float* __restrict__ PQ, int C, const int32_t* __
       }
 #pragma unroll
       for (int a = 0; a < NP; ++a)
-        if (i0 + a < i_end) put(a, t, s[2 * a], s[2 * a + 1]);
+        if (i0 + a < i_end) put(a, false, s[2 * a], s[2 * a + 1]);
     }
   }
 }
@@ -167,6 +177,7 @@ int launch_edge_gather_unroll(bool eif, const float* PQ, int C, const int32_t* i
                               float* spk, int64_t ldspk_row, int ldo, cudaStream_t st, bool h2, float* spk0, int64_t plane, int choff) {
   SAPCU_REQUIRE(C % 128 == 0, "edge_gather_unroll: C=%d must be a multiple of 128", C);
   SAPCU_REQUIRE(Mpts >= 1 && Mpts <= 256, "edge_gather_unroll: M=%d outside [1,256]", Mpts);
+  SAPCU_REQUIRE((int64_t)Mpts * T * ldo < ((int64_t)1 << 31) && (int64_t)Mpts * ldspk_row < ((int64_t)1 << 31), "edge_gather_unroll: patch rows exceed 32-bit offsets");
   if (S == 0) return 0;
   const size_t smem = sizeof(float) * (size_t)Mpts * 128 + (((size_t)Mpts * kk + 15) & ~(size_t)15);
   static PerDeviceOnce once;
