@@ -81,7 +81,6 @@ __device__ __forceinline__ bool lif_table_eval_vec(float (&x)[NV], uint32_t desc
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const float y2 = fmaf(fabsf(x[i]), 2.0f, 2.0f);
-    asm("max.NaN.f32 %0, %0, %1;" : "+f"(ymax) : "f"(y2));
     y[i] = fminf(y2, 511.99997f);                                       // NaN -> 511.99997 as well
     const uint32_t a = desc_lane + ((__float_as_uint(y[i]) >> 13) & 0x1C00u);     // cell = low 3 exponent bits, 1 KiB per cell
     // predicated pair of loads instead of a select on the address: the sign costs one compare on the ALU pipe
@@ -90,6 +89,10 @@ __device__ __forceinline__ bool lif_table_eval_vec(float (&x)[NV], uint32_t desc
         "@!p ld.shared.v2.u32 {%0, %1}, [%3];\n\t}"
         : "=r"(dS[i]), "=r"(dO[i]) : "f"(x[i]), "r"(a));
   }
+  // out of range or NaN <=> the clamp bit: y == 511.99997 (3-input maxima: half an instruction per element)
+#pragma unroll
+  for (int i = 0; i + 1 < NV; i += 2) ymax = fmaxf(fmaxf(ymax, y[i]), y[i + 1]);
+  if (NV & 1) ymax = fmaxf(ymax, y[NV - 1]);
   float4 c[NV]; float t[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -101,7 +104,7 @@ __device__ __forceinline__ bool lif_table_eval_vec(float (&x)[NV], uint32_t desc
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) x[i] = fmaf(fmaf(fmaf(c[i].w, t[i], c[i].z), t[i], c[i].y), t[i], c[i].x);
-  return !(ymax < 512.0f);
+  return ymax >= 511.99997f;
 }
 __device__ __forceinline__ bool lif_table_oob(float x) { return !(fabsf(x) < 255.0f); }
 #endif
