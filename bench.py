@@ -198,8 +198,11 @@ def run_reference(args):
     _, _, sd_fn, sd_fd = build_models(None)
     cloud, seeds, batch = workload(args.config, 1)
     n_sample = 48 if args.config != 5 else 16      # ~7 s of host work per step on 16 cores
-    # keep the whole --steps K --warmup W run within a few minutes whatever K and W are (cost is per seed: the rate is unaffected)
-    n_sample = max(8, min(n_sample, n_sample * 24 // max(1, args.steps + args.warmup)))
+    # keep the whole --steps K --warmup W run within a few minutes on any host, whatever K and W are (cost is per seed, so the
+    # rate does not depend on the sample): one calibration pass of 8 seeds, then the per-step sample that fits ~150 s in total
+    c0, s0 = sample_problem(args.config, cloud, seeds, batch, 9)
+    r0, _ = cpu_reference_rate(sd_fn, sd_fd, c0, s0, 8)
+    n_sample = int(max(4, min(n_sample, r0 * 150.0 / max(1, args.steps + args.warmup))))
     c1, s1 = sample_problem(args.config, cloud, seeds, batch, max(n_sample * (args.steps + args.warmup), n_sample + 1))
     rate, sec = cpu_reference_rate(sd_fn, sd_fd, c1, s1, n_sample, steps=args.steps, warmup=args.warmup)
     c = CONFIGS[args.config]
