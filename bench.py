@@ -249,6 +249,8 @@ def kernel_rooflines(report, steps, peaks, step_ms_total, products=1):
                "lif_elsteps_per_s": ls, "mufu_frac": fr["mufu"]}
         if tabulated:
             row["lif"] = "tabulated LIF^T chain: no MUFU recurrence executed, the MUFU roofline does not apply"
+        if max(cand.values()) < 0.15:
+            row["note"] = "below 15 % of every roofline: issue / latency-bound (shared-memory top-k, gathers); pipe utilisation in the ncu summaries under profiles/"
         out.append(row)
     out.sort(key=lambda r: -r["ms_per_step"])
     return out

@@ -142,3 +142,29 @@ def test_shard_batch_offsets():
             assert loc[0] == 0 and loc[-1] == hi - lo and (np.diff(loc) >= 0).all()
             total += np.diff(loc)
         assert np.array_equal(total, np.diff(so))
+
+
+def test_bench_kernel_roofline_grading():
+    """bench.kernel_rooflines: the tensor bound is chosen on the issued products (3 per MAC in the parity-grade mode) while `frac`
+    stays algorithmic; a layer running above the MUFU ceiling is tabulated and is not graded on the MUFU roofline."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    peaks = {"bf16_tflops_sustained": 1000.0, "hbm_gbs": 5000.0}
+    ms = 10.0
+    rep = [
+        # 200 TFLOP/s algorithmic (0.2), 2 TB/s (0.4), LIF 2x the ceiling -> tabulated, tensor issued 0.6 wins over hbm 0.4
+        {"label": "fn.fc_delta2+lif", "launches": 3, "ms": ms, "flops": 200e12 * ms / 1e3, "bytes": 2000e9 * ms / 1e3, "lif_elsteps": 2 * bench.LIF_CEILING * ms / 1e3},
+        # a MUFU-bound layer below the ceiling keeps the MUFU roofline
+        {"label": "fn.conv1+lif", "launches": 1, "ms": ms, "flops": 0.0, "bytes": 100e9 * ms / 1e3, "lif_elsteps": 0.5 * bench.LIF_CEILING * ms / 1e3},
+        # top-k kernel: flops recorded but not a contraction, far below every roofline
+        {"label": "fd.intra_knn(features)", "launches": 3, "ms": ms, "flops": 1e12 * ms / 1e3, "bytes": 50e9 * ms / 1e3, "lif_elsteps": 0.0},
+    ]
+    rows = {r["kernel"]: r for r in bench.kernel_rooflines(rep, 1, peaks, 3 * ms, products=3)}
+    d2 = rows["fn.fc_delta2+lif"]
+    assert d2["bound"] == "tensor" and abs(d2["frac"] - 0.2) < 1e-9 and abs(d2["tensor_issued_frac"] - 0.6) < 1e-9 and "lif" in d2
+    c1 = rows["fn.conv1+lif"]
+    assert c1["bound"] == "mufu" and abs(c1["frac"] - 0.5) < 1e-9 and "lif" not in c1
+    kn = rows["fd.intra_knn(features)"]
+    assert kn["tensor_issued_frac"] == kn["tensor_frac"] and "note" in kn
