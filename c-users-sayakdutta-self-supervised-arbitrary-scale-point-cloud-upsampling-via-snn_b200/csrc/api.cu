@@ -38,6 +38,8 @@ const Settings& settings() {
     t.tc_tables = env_int("SAPCU_TC_LIF_TABLES", 1) != 0;
     t.tc_pos_copy = env_int("SAPCU_TC_POS_COPY", 1) != 0;
     t.tc_qkv_planes = env_int("SAPCU_TC_QKV_PLANES", 1) != 0;
+    t.tc_pq_unit = env_int("SAPCU_TC_PQ_FP16X3", 1) != 0;
+    t.tc_fc1_table = env_int("SAPCU_TC_FC1_TABLE", 1) != 0;
     t.sync_check = env_int("SAPCU_TC_SYNC_CHECK", 0) != 0;
     t.h2_planes = env_int("SAPCU_TC_H2_PLANES", 1);
     t.l2pf = env_int("SAPCU_TC_L2PF", 4);

@@ -61,7 +61,7 @@ constexpr int kNumSMs = 148;   // B200
 // Process-wide A/B switches (environment), read ONCE under C++11 static-initialisation locking and
 // immutable afterwards: concurrent forwards from several threads / streams all see the same values.
 struct Settings {
-  bool tc_2cta, fuse_attnout, factor_attnin, fuse_pool, fp16x3, spike_planes, fast_tables, tc_tables, tc_pos_copy, tc_qkv_planes, sync_check;
+  bool tc_2cta, fuse_attnout, factor_attnin, fuse_pool, fp16x3, spike_planes, fast_tables, tc_tables, tc_pos_copy, tc_qkv_planes, tc_pq_unit, tc_fc1_table, sync_check;
   int h2_planes, l2pf, tc_bn, tc_epi, tc_rawhi;
 };
 const Settings& settings();

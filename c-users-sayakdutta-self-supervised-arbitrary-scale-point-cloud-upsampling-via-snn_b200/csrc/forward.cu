@@ -235,6 +235,10 @@ int fn_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
           if (settings().tc_tables && k.snn_qkv.tab_ok && k.snn_qkv.tab_T == 4 && k.snn_qkv.tab_stride <= LT_SMEM_BUDGET_TC) {
             a2.lif_tab = k.snn_qkv.tab; a2.lif_tab_stride = k.snn_qkv.tab_stride;
           }
+          // fc1 itself keeps 3xTF32 products (its input is not a spike tensor) and reads its chain from the table as well
+          if (settings().tc_tables && settings().tc_fc1_table && k.snn1.tab_ok && k.snn1.tab_T == 4 && k.snn1.tab_stride <= LT_SMEM_BUDGET_TC) {
+            a1.lif_tab = k.snn1.tab; a1.lif_tab_stride = k.snn1.tab_stride;
+          }
         }
       }
       g_tap_snn1_h2 = x_planes ? 1 : 0;
@@ -451,7 +455,16 @@ int fd_chunk(const sapcu_model* mdl, const float* xyz, int64_t s, int M, float* 
     if (mode != SAPCU_MODE_FP32) {
       // factorised EdgeConv: one per-POINT contraction [P, Cin] x [2 Cout, Cin]^T, then gather / BN / LeakyReLU / max_k
       Layer L = f.convf[b];
-      SAPCU_TRY(g.L("fd.edgeconv(per-point P|Q)").layer(L, S0 + off_in[b], ld0, P, p.PQ, 2 * cout[b], ACT_NONE));
+      {
+        // the input is a slice of the step-0 spike tensor: parity-grade mode -> fp16x3 products (the splitter converts the fp32
+        // rows), on the 2-CTA engine from 1,024 rows on so that the arithmetic does not depend on the chunking
+        GemmArgs a = g.args(L, S0 + off_in[b], ld0, P, p.PQ, 2 * cout[b], ACT_NONE);
+        if (mode == SAPCU_MODE_TC && settings().tc_pq_unit) {
+          GemmArgs t = a; t.x_unit = true; t.tc2_any_rows = true;
+          if (gemm_tc2_supported(t, A_PLAIN) && gemm_tc2_fp16x3(t)) a = t;
+        }
+        SAPCU_TRY(g.L("fd.edgeconv(per-point P|Q)").run(a, A_PLAIN));
+      }
       ProfWork w; w.elsteps = (double)P * cout[b] * T; w.bytes = (double)P * cout[b] * (8.0 + 4.0 * T) + (double)P * p.k * 4.0;
       SAPCU_PROF(st, "fd.edgeconv gather+max+neuron unroll", w,
                  launch_edge_gather_unroll(b == 0, p.PQ, cout[b], idx, p.k, M, s, f.conv[b].scale, f.conv[b].shift,

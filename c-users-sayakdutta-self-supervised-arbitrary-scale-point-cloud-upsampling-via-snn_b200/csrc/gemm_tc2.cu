@@ -737,6 +737,7 @@ int t2_set_attrs_impl() {
 #undef SAPCU_T2_ATTR_H
 #define SAPCU_T2_ATTR_P(A, X, KQ) SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<A, X, KQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES))
   // parity-grade mode with tabulated LIF^T chains: two 64 KiB stages + the table
+  SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 0, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * TC_TILE_BYTES + 1024 + 256 + LT_SMEM_BUDGET_TC)));
   SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 0, 1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * TC_TILE_BYTES + 1024 + 256 + LT_SMEM_BUDGET_TC)));
   SAPCU_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<ACT_LIF, 2, 1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * TC_TILE_BYTES + 1024 + 256 + LT_SMEM_BUDGET_TC)));
   SAPCU_T2_ATTR_P(ACT_LIF, 0, 1); SAPCU_T2_ATTR_P(ACT_LIF, 2, 1); SAPCU_T2_ATTR_P(ACT_LEAKY, 4, 1); SAPCU_T2_ATTR_P(ACT_NONE, 3, 12); SAPCU_T2_ATTR_P(ACT_NONE, 3, 18); SAPCU_T2_ATTR_P(ACT_NONE, 3, 24);
@@ -906,6 +907,16 @@ int launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
   }
 #undef SAPCU_T2_LAUNCH_H
 #undef SAPCU_T2_LAUNCH_P
+  if (g.act == ACT_LIF && !g.edge_bias && g.lif_tab && g.lif_tab_stride > 0 && g.lif_tab_stride <= LT_SMEM_BUDGET_TC) {
+    // 3xTF32 products (splitter path) + the layer's tabulated LIF^T chain: two 64 KiB stages next to the table
+    pairs = (pairs / p.m_tiles) * p.m_tiles;
+    SAPCU_REQUIRE(pairs >= 1, "gemm_tc2(3xTF32 + table): empty grid");
+    p.lif_tab = reinterpret_cast<const uint8_t*>(g.lif_tab); p.lif_tab_stride = g.lif_tab_stride;
+    const size_t smem = 2 * 4 * (size_t)TC_TILE_BYTES + 1024 + 256 + g.lif_tab_stride;
+    gemm_tc2_kernel<ACT_LIF, 0, 1, 0, 1><<<2 * pairs, (T2_EPI_WARP0 + 16) * 32, smem, st>>>(mw, mwlo, mx, mx2, p);
+    SAPCU_LAUNCH_CHECK();
+    return 0;
+  }
 #define SAPCU_T2_LAUNCH(A, X, KQ) gemm_tc2_kernel<A, X, KQ><<<grid, (T2_EPI_WARP0 + 16) * 32, T2_SMEM_BYTES, st>>>(mw, mwlo, mx, mx2, p)
   if (g.at_pos) {
     if (g.kk == 12) SAPCU_T2_LAUNCH(ACT_NONE, 3, 12); else if (g.kk == 18) SAPCU_T2_LAUNCH(ACT_NONE, 3, 18); else SAPCU_T2_LAUNCH(ACT_NONE, 3, 24);
