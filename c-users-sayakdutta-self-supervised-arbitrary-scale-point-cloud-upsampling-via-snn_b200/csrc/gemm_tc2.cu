@@ -2,13 +2,15 @@
 // same pipeline (template CG = 1), for the 128-channel layers whose operands arrive ready-made.
 //
 // Operand formats (template HM) and what each mode uses them for:
-//   0  fp32 rows, 3xTF32 split in the kernel (or single-pass TF32)      point-level layers, every mode
-//   1  fp32 rows converted to fp16 (hi, lo) by the splitter warps        spike-tensor layers without plane hand-over (A/B only)
-//   2  fp16 (hi, lo) planes written by the producer, fp16x3 products     SAPCU_MODE_TC: fc_delta2, fc_gamma, fc_gamma2 + tail, fd conv5
+//   0  fp32 rows, 3xTF32 split in the kernel (or single-pass TF32)      point-level layers, every mode (+ LT: fc1 of the wide blocks, SAPCU_MODE_TC)
+//   1  fp32 rows converted to fp16 (hi, lo) by the splitter warps        spike-tensor layers without plane hand-over: fd's per-point P|Q (SAPCU_MODE_TC)
+//   2  fp16 (hi, lo) planes written by the producer, fp16x3 products     SAPCU_MODE_TC: fc_delta2, fc_gamma, fc_gamma2 + tail, q/k/v of the wide blocks, fd conv5
 //   3  ONE fp16 plane, ONE product per MAC, 32 KiB stages                SAPCU_MODE_FAST: the same layers
 //   4  fp32 rows, single-pass TF32, compact stages                       SAPCU_MODE_FAST: point-level LIF layers
 // Template LT = 1: the LIF^T chain of the epilogue comes from the layer's table in shared memory (lif_table.cuh); the stage
 // count shrinks so that pipeline + table fit 227 KiB.
+// LIF epilogues store whole 8-row pieces through lif_store_piece<LD>: the model's row strides are compile-time constants there, so
+// every store is an immediate offset from one base address per output tensor (the run-time-stride form is the fallback).
 //
 // A CTA pair (thread-block cluster of 2, same TPC) computes a 256-channel x 256-row tile with ONE
 // tcgen05.mma.cta_group::2 stream issued by the leader CTA: each CTA stages only ITS 128 weight rows and ITS
