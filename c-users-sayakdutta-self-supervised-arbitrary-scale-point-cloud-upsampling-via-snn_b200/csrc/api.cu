@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <string.h>
 #include <stdlib.h>
+#include <cmath>
+#include "lif_table.cuh"
 #include "../../include/sapcu_b200.h"
 #include "gemm_simt.cuh"
 #include "gemm_tc.h"
@@ -214,6 +216,34 @@ int sapcu_lif_chain(const float* d_x, int64_t rows, int C, int T, const float* d
   // allocation-free by requiring the caller to pass CLAMPED parameters (the Python shim clamps).
   return launch_neuron_unroll(d_eif2 != nullptr, true, d_x, C, rows, C, T, d_params4, d_eif2, all_steps, d_out, C,
                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sapcu_lif_table_selftest(const float* h_params4, int C, int T, int samples, double* max_err, double* fit_err, uint32_t* max_block_bytes) {
+  SAPCU_REQUIRE(h_params4 && C >= 1 && T >= 1 && T <= 16 && samples >= 1 && max_err && fit_err && max_block_bytes, "lif_table_selftest: bad argument");
+  LifTableHost t;
+  lif_table_build(h_params4, C, T, &t);
+  *fit_err = t.max_err; *max_block_bytes = t.max_block_bytes;
+  double worst = 0.0;
+  for (int c = 0; c < C; ++c) {
+    const double d = h_params4[c], a = h_params4[C + c], r = h_params4[2 * C + c], th0 = h_params4[3 * C + c];
+    auto probe = [&](float x) {
+      const float got = lif_table_eval_host(t, c, x);
+      const double want = lif_chain_exact_host((double)th0 + (double)x, d, a, r, th0, T);
+      const double e = std::isnan(got) ? 1e30 : std::fabs((double)got - want);
+      worst = e > worst ? e : worst;
+    };
+    for (int i = 0; i < samples; ++i) {            // geometric spread over both sides, 2^-12 .. 254.9
+      const float mag = std::ldexp(1.0f, -12) * std::pow(254.9f / std::ldexp(1.0f, -12), (float)(i + 0.5f) / (float)samples);
+      probe(mag); probe(-mag);
+    }
+    probe(0.0f); probe(-0.0f); probe(1e-30f); probe(-1e-30f); probe(254.99998f); probe(-254.99998f);
+    for (int e = 0; e < LT_NB; ++e) {              // both neighbours of every cell boundary y = 2^(e+1): |x| = 2^e - 1
+      const float xb = std::ldexp(1.0f, e) - 1.0f;
+      for (float s : {1.0f, -1.0f}) { probe(s * xb); probe(s * std::nextafter(xb, 1e9f)); if (xb > 0.0f) probe(s * std::nextafter(xb, 0.0f)); }
+    }
+  }
+  *max_err = worst;
+  return 0;
 }
 
 int sapcu_intra_knn(const float* d_feat, int64_t ld, int64_t S, int M, int C, int k, int32_t* d_idx, void* stream) {

@@ -181,4 +181,25 @@ void lif_table_build(const float* np4, int C, int T, LifTableHost* out) {
   }
 }
 
+// Host restatement of the device lookup (lif_table_eval_vec in lif_table.cuh) on a built image: the same fp32 operations in
+// the same order, with the descriptor offsets taken relative to the block's coefficient array (the kernels add its shared-memory
+// address while copying the block in).  Returns NaN when the lookup would leave the block's coefficient array.
+float lif_table_eval_host(const LifTableHost& t, int c, float x) {
+  const LifTableBlock& b = t.blocks[(size_t)(c / LT_CH)];
+  const int cl = c % LT_CH;
+  const uint8_t* img = t.image.data() + b.off_bytes;
+  const float y = fminf(fmaf(fabsf(x), 2.0f, 2.0f), 511.99997f);
+  uint32_t yb; memcpy(&yb, &y, 4);
+  const uint32_t cell = ((yb >> 23) & 7u) + (x < 0.0f ? (uint32_t)LT_NB : 0u);
+  const uint32_t* d = reinterpret_cast<const uint32_t*>(img) + 2 * ((size_t)cell * LT_CH + cl);
+  float S; memcpy(&S, &d[0], 4);
+  const float qm = fmaf(y, S, 8388607.5f);
+  const float tt = fmaf(y, S, -(qm - 8388608.0f));
+  uint32_t qb; memcpy(&qb, &qm, 4);
+  const uint32_t off = qb * 16u + d[1];                         // byte offset inside the coefficient array (mod 2^32)
+  if (off % 16u != 0 || off / 16u >= b.nseg) return NAN;
+  const float* cf = reinterpret_cast<const float*>(img + LT_DESC_BYTES + off);
+  return fmaf(fmaf(fmaf(cf[3], tt, cf[2]), tt, cf[1]), tt, cf[0]);
+}
+
 }  // namespace sapcu

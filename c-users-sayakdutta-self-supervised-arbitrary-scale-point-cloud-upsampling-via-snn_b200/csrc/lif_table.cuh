@@ -52,6 +52,8 @@ struct LifTableHost {
 };
 // np4 = [4][C] rows {d, a, r, theta0}, already clamped; exact chain evaluated in fp64 on the host
 void lif_table_build(const float* np4, int C, int T, LifTableHost* out);
+// host restatement of the device lookup for channel c at x = u - theta0 (|x| < 255); NaN if the lookup leaves the table
+float lif_table_eval_host(const LifTableHost& t, int c, float x);
 // exact T-step chain from the zero state in fp64 (the reference's formula, clamps included)
 double lif_chain_exact_host(double u, double d, double a, double r, double th0, int T);
 

@@ -209,6 +209,13 @@ int sapcu_model_tap_format(const sapcu_model* m, const char* name);
 int sapcu_lif_chain(const float* d_x, int64_t rows, int C, int T, const float* d_params4,
                     const float* d_eif2 /*nullable {delta_T, theta_rh}*/, int all_steps,
                     float* d_out, void* stream);
+/* HOST-ONLY self-test of the tabulated LIF^T chains (no GPU, no stream): builds the table for h_params4 = [4][C] rows {decay, adapt,
+ * refr_decay, theta0} (HOST memory, already clamped) and T steps exactly as sapcu_model_finalize does, evaluates the host restatement
+ * of the kernels' lookup at `samples` magnitudes per side and channel (geometric over 2^-12 .. 254.9) plus zero, the cell boundaries
+ * and their fp32 neighbours, and reports max_err = the largest |table - exact fp64 chain| (the reference's recurrence,
+ * fn/snn_coder.py:87-153), fit_err = the builder's own acceptance figure and the largest 128-channel block image in bytes. */
+int sapcu_lif_table_selftest(const float* h_params4, int C, int T, int samples, double* max_err, double* fit_err,
+                             uint32_t* max_block_bytes);
 /* intra-patch kNN of fn/fd `knn()` (fn/snn_coder.py:31-39, fd/snn_coder.py:25-32): features
  * [S*M, C] rows (ld floats apart), top-k of -|xi-xj|^2 in the reference's expanded form, ties -> lowest
  * index.  d_idx: int32 [S*M, k] patch-local indices. */

@@ -168,3 +168,27 @@ def test_bench_kernel_roofline_grading():
     assert c1["bound"] == "mufu" and abs(c1["frac"] - 0.5) < 1e-9 and "lif" not in c1
     kn = rows["fd.intra_knn(features)"]
     assert kn["tensor_issued_frac"] == kn["tensor_frac"] and "note" in kn
+
+
+def test_lif_table_host_selftest():
+    """The tabulated LIF^T chains without a GPU: the library builds the table as sapcu_model_finalize does and evaluates the host
+    restatement of the kernels' lookup (same fp32 operations) against the exact fp64 recurrence -- default-initialised neurons
+    (all channels share one fit) and parameters spread over the reference's clamp ranges, incl. zero, the cell boundaries and
+    their fp32 neighbours.  Bound: 5e-5 absolute on soft spikes in (0, 0.7) (the fit accepts 4e-5 at its check points)."""
+    import ctypes
+    import numpy as np
+    import sapcu_b200
+    L = sapcu_b200.lib()
+    rng = np.random.default_rng(5)
+    C = 256
+    default = np.stack([np.full(C, 0.9), np.full(C, 0.01), np.full(C, 0.5), np.full(C, 1.0)]).astype(np.float32)
+    spread = np.stack([rng.uniform(0.5, 0.99, C), rng.uniform(0.0, 0.1, C), rng.uniform(0.1, 0.9, C), rng.uniform(0.5, 2.0, C)]).astype(np.float32)
+    for name, prm, T in (("default", default, 4), ("spread", spread, 4), ("spread_T6", spread[:, :128].copy(), 6)):
+        prm = np.ascontiguousarray(prm)
+        err, fit, blk = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint32()
+        rc = L.sapcu_lif_table_selftest(prm.ctypes.data_as(ctypes.c_void_p), prm.shape[1], T, 400, ctypes.byref(err), ctypes.byref(fit), ctypes.byref(blk))
+        assert rc == 0, sapcu_b200.lib().sapcu_last_error()
+        print("lif table [%s]: max |table - exact| %.2e, fit %.2e, largest block %d bytes" % (name, err.value, fit.value, blk.value))
+        assert err.value < 5e-5 and fit.value <= 4.0001e-5
+        assert blk.value <= 120 * 1024
+    assert L.sapcu_lif_table_selftest(None, 4, 4, 10, ctypes.byref(err), ctypes.byref(fit), ctypes.byref(blk)) != 0
